@@ -1,0 +1,187 @@
+/* voxpop.h - C ABI of the B200-native VoxPopuli render hot path.
+ *
+ * Drop-in boundary for the path  Renderer::Update -> Trace -> FindNearest / IsOccluded /
+ * Illumination -> accumulator  of Tycro-Games/Raytracer-VoxPopuli.  The reference has no
+ * FFI or plugin interface; its seam is the `Renderer` class (reference renderer.h:42-245).
+ * Every entry point below names the reference member it replaces.  Plain C types only:
+ * no PyTorch, no C++ types, no exceptions cross this boundary.  All functions return 0 on
+ * success and a negative VP_E* code on failure; vp_last_error() gives the message for the
+ * calling thread.  There is NO CPU fallback behind these calls: without a CUDA device
+ * vp_create fails with VP_ENODEVICE.
+ *
+ * The same POD structs describe a scene to the three implementations that must agree:
+ *   libvoxpop_b200.so (this ABI, CUDA sm_100a)  - the product
+ *   oracle/libvporacle.so (vpo_* , plain C)     - test infrastructure
+ *   oracle/_ref/libvpref.so (vpref_*, the reference's own C++ built headless) - test infrastructure
+ */
+#ifndef VOXPOP_H
+#define VOXPOP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VP_OK 0
+#define VP_EINVAL (-1)    /* bad argument */
+#define VP_ENODEVICE (-2) /* no usable CUDA device / CUDA runtime failure at create */
+#define VP_ECUDA (-3)     /* CUDA error during upload or render */
+#define VP_ENOMEM (-4)
+#define VP_ESTATE (-5)    /* call order (e.g. render before set_volumes) */
+
+#define VP_MAT_NONE 255   /* MaterialType::NONE, reference template/scene.h:56 */
+#define VP_MAX_MATERIALS 256
+#define VP_MAX_DEPTH 64
+
+/* One voxel volume = reference `Scene` data members (template/scene.h:252-266).
+ * grid is N*N*N bytes, index x + y*N + z*N*N (Scene::GetVoxel, template/scene.h:241-248),
+ * 255 = empty.  matrix / inv_matrix are the row-major mat4 cells (tmpl8math.h:2596).
+ * cube_min/cube_max = Scene::cube.b[0..1].  The library copies everything at upload. */
+typedef struct VpVolume {
+  const uint8_t* grid;
+  uint32_t n;            /* gridsize (== worldsize), any value 1..1024 */
+  float cube_min[3];
+  float cube_max[3];
+  float matrix[16];
+  float inv_matrix[16];
+} VpVolume;
+
+/* reference src/Materials/Material.h:3-12 */
+typedef struct VpMaterial {
+  float albedo[3];
+  float roughness;
+  float emissive;
+  float ior;
+} VpMaterial;
+
+/* reference src/Lighting/PointLight.h:3-7 */
+typedef struct VpPointLight { float position[3]; float color[3]; } VpPointLight;
+/* reference src/Lighting/SphereAreaLight.h:2-9 */
+typedef struct VpAreaLight { float position[3]; float color[3]; float color_multiplier; float radius; } VpAreaLight;
+/* reference src/Lighting/SpotLight.h:12-18; angle is the COSINE of the cone half angle */
+typedef struct VpSpotLight { float position[3]; float direction[3]; float color[3]; float angle; } VpSpotLight;
+/* reference src/Lighting/DirectionalLight.h:2-6; always counted in lightCount (renderer.cpp:2295) */
+typedef struct VpDirLight { float direction[3]; float color[3]; } VpDirLight;
+
+/* reference src/BVH/Shapes.h:4-66 */
+typedef struct VpSphere { float center[3]; float radius; uint32_t material; } VpSphere;
+/* reference src/BVH/Shapes.h:69-145: world vertices are position + vertexK */
+typedef struct VpTriangle { float vertex0[3]; float vertex1[3]; float vertex2[3]; float position[3]; uint32_t material; } VpTriangle;
+
+/* The fields of reference `Camera` (template/camera.h:175-183) that GetPrimaryRay reads. */
+typedef struct VpCamera {
+  float cam_pos[3];
+  float top_left[3];
+  float top_right[3];
+  float bottom_left[3];
+  float right[3];
+  float up[3];
+  float focal_distance;
+  float defocus_jitter;
+} VpCamera;
+
+/* Per-call frame parameters = the Renderer members Update() reads
+ * (renderer.h:175,186,199,205) plus the deterministic RNG contract:
+ * every pixel of sample-frame f reseeds xorshift32 with
+ *   s = WangHash(pixel_index + f * W*H + seed);  if (s == 0) s = 0x9E3779B9
+ * (WangHash/xorshift32: reference template/tmpl8math.cpp:20-27,119-125). */
+typedef struct VpFrameParams {
+  int32_t width, height;
+  int32_t max_bounces;     /* Renderer::maxBounces; Trace(depth = max_bounces) */
+  int32_t spp;             /* number of Update() passes accumulated by this call */
+  uint32_t frame_index;    /* Renderer::numRenderedFrames before the first pass */
+  uint32_t seed;
+  float aa_strength;       /* Renderer::antiAliasingStrength */
+  int32_t row_begin, row_end; /* rows [row_begin,row_end) rendered; 0,0 = whole frame */
+  int32_t row_tile, row_tile_stride, row_tile_phase; /* interleaved row tiles for multi-GPU:
+                              row y is rendered iff ((y / row_tile) % row_tile_stride) == row_tile_phase;
+                              row_tile == 0 disables the filter */
+} VpFrameParams;
+
+/* Result of one Renderer::FindNearest call (renderer.cpp:946-1018). */
+typedef struct VpHit {
+  int32_t volume;   /* index into volumes; -1 sphere/triangle; -2 miss */
+  uint32_t cell;    /* x + y*N + z*N*N of the hit voxel; 0xFFFFFFFF if none */
+  float t;          /* ray.t after the call (1e34f on miss) */
+  float normal[3];  /* ray.rayNormal (world space, normalised) */
+  uint8_t material; /* ray.indexMaterial; 255 on miss */
+  int8_t face;      /* object-space face before the matrix: sx + 3*sy + 9*sz, s in {0:none,1:+1,2:-1}; -1 if none */
+  uint8_t inside;   /* ray.isInsideGlass after the call */
+  uint8_t pad;
+} VpHit;
+
+/* A ray as handed to Renderer::FindNearest / IsOccluded / Trace: O, D (used as given;
+ * the reference always passes normalised D), t = max distance, inside = isInsideGlass. */
+typedef struct VpRay { float o[3]; float d[3]; float t; uint32_t inside; } VpRay;
+
+/* Ray counters, SURVEY section 8(d): one ray = one Renderer::FindNearest call
+ * (primary or secondary) or one Renderer::IsOccluded call (shadow).  Medium-exit
+ * traversals are reported separately and do not count toward Mrays/s. */
+typedef struct VpStats {
+  uint64_t primary_rays;
+  uint64_t secondary_rays;
+  uint64_t shadow_rays;
+  uint64_t exit_rays;
+  uint64_t dda_steps;       /* grid cell visits over all traversals */
+  double device_ms;         /* device time of the render call (CUDA events) */
+  uint64_t kernel_launches; /* kernels launched by this call */
+} VpStats;
+
+typedef struct vp_ctx vp_ctx;
+
+/* Renderer::Init replacement (renderer.cpp:688-736, minus asset/game setup).
+ * device < 0 selects the current CUDA device. */
+vp_ctx* vp_create(int device);
+void vp_destroy(vp_ctx* ctx);
+const char* vp_last_error(void);
+
+/* Renderer::voxelVolumes (renderer.h:217) - full replacement, uploaded once. */
+int vp_set_volumes(vp_ctx* ctx, const VpVolume* volumes, int n);
+/* Scene::Set / ResetGrid dirty range (template/scene.cpp:358-361,711-714): re-upload
+ * bytes [offset, offset+len) of volume i's grid. */
+int vp_update_volume_grid(vp_ctx* ctx, int volume, uint32_t offset, uint32_t len, const uint8_t* bytes);
+/* Scene::SetTransform result (template/scene.cpp:373-404) for a moving volume. */
+int vp_update_volume_transform(vp_ctx* ctx, int volume, const float matrix[16], const float inv_matrix[16],
+                               const float cube_min[3], const float cube_max[3]);
+/* Renderer::materials (renderer.h:196), n <= 256. */
+int vp_set_materials(vp_ctx* ctx, const VpMaterial* materials, int n);
+/* Renderer::pointLights/areaLights/spotLights/dirLight + numCheckShadowsAreaLight
+ * (renderer.h:200-205); lightCount = np + na + ns + 1 (renderer.cpp:2290-2296). */
+int vp_set_lights(vp_ctx* ctx, const VpPointLight* point, int np, const VpAreaLight* area, int na,
+                  const VpSpotLight* spot, int ns, const VpDirLight* dir, int area_shadow_samples);
+/* Renderer::spheres / triangles (renderer.h:213-214). */
+int vp_set_prims(vp_ctx* ctx, const VpSphere* spheres, int ns, const VpTriangle* triangles, int nt);
+/* Renderer::skyPixels/skyWidth/skyHeight/HDRLightContribution/activateSky
+ * (renderer.h:225,232-234); rgb is w*h*3 floats. */
+int vp_set_sky(vp_ctx* ctx, const float* rgb, int w, int h, float contribution, int active);
+
+/* Renderer::Update (renderer.cpp:1646-1891), scalar pixel path (:1851-1881), `spp`
+ * passes.  accum_rgba: W*H float4, in-out (Renderer::accumulator); rgb8: W*H uint32
+ * (screen->pixels), may be NULL.  HOST pointers; copies are part of the call. */
+int vp_render(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, float* accum_rgba, uint32_t* rgb8,
+              VpStats* stats);
+/* Same work with the accumulator kept resident in device memory between calls
+ * (vp_accum_reset / vp_accum_download bracket a sequence of passes). */
+int vp_render_resident(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, VpStats* stats);
+int vp_accum_reset(vp_ctx* ctx, int width, int height);  /* Renderer::ResetAccumulator, renderer.cpp:343-346 */
+int vp_accum_download(vp_ctx* ctx, float* accum_rgba, uint32_t* rgb8);
+/* Device pointers of the resident buffers (for NCCL gather / display interop). */
+int vp_accum_device_ptrs(vp_ctx* ctx, void** accum_rgba_dev, void** rgb8_dev);
+
+/* Primary-ray seam: Camera::GetPrimaryRay (template/camera.h:85-101) + Renderer::FindNearest
+ * per pixel, RNG contract as above (2 AA draws then 2 disc draws). hits: W*H. */
+int vp_trace_primary(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, VpHit* hits);
+/* Batch seams: Renderer::FindNearest (renderer.cpp:946), Renderer::IsOccluded (:209),
+ * Renderer::Trace (:1076) with per-ray RNG seeds (xorshift32 state, must be non-zero). */
+int vp_find_nearest(vp_ctx* ctx, const VpRay* rays, int n, VpHit* hits);
+int vp_is_occluded(vp_ctx* ctx, const VpRay* rays, int n, uint8_t* out);
+int vp_trace(vp_ctx* ctx, const VpRay* rays, const uint32_t* seeds, int n, int depth, float* rgb_out);
+
+/* Build/runtime facts for the harness: fills up to `cap` bytes of a JSON string. */
+int vp_info(vp_ctx* ctx, char* buf, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXPOP_H */
