@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py - headline benchmark of the render hot path (BASELINE.json metric).
+
+A "step" is one Renderer::Update() pass (1 spp) of the workload over the whole frame.
+  value     Mrays/s (primary + shadow + secondary rays of all ranks / max-over-ranks device
+            time), accumulator resident in HBM, kernels enqueued on torch's current stream and
+            timed with CUDA events around exactly K steps.
+  e2e       the same metric through the reference-facing C-ABI call vp_render() with HOST
+            buffers: float4 accumulator in (pinned) + accumulator and RGB8 out, every step.
+  roofline  dominant kernel (k_render): algorithmic bytes (SURVEY.md 8d formula) / its
+            average device time, against the measured HBM copy bandwidth.
+  cpu_baseline  the reference's own CPU Trace (oracle/_ref) timed on this box's host cores.
+`--impl reference` times that CPU path alone with the same config/metric.
+Multi-GPU (torchrun): the frame is sharded as interleaved 8-row tiles (scene replicated,
+no per-sample communication); finished RGB8 tiles are gathered with one NCCL all_gather
+per step inside the timed region.  Total work is fixed => "scaling": "strong".
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+vp = importlib.import_module("raytracer-voxpopuli_b200")
+scenes = importlib.import_module("raytracer-voxpopuli_b200.scenes")
+abi = vp.abi
+
+METRIC = "Mrays/s (primary+shadow+secondary)"
+ROW_TILE = 8
+
+
+def frame_params(fpd, **over):
+    d = dict(fpd)
+    d.update(over)
+    return vp.frame_params(d["width"], d["height"], max_bounces=d["max_bounces"], spp=d.get("spp", 1),
+                           frame_index=d.get("frame_index", 0), seed=scenes.SEED, aa_strength=d["aa_strength"],
+                           row_tile=d.get("row_tile", 0), row_tile_stride=d.get("row_tile_stride", 1),
+                           row_tile_phase=d.get("row_tile_phase", 0), flags=d.get("flags", 0))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def load_checker():
+    """The reference itself when its build travelled with the repo, else the plain-C port."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "libvpref.so")
+    if os.path.exists(ref):
+        lib = abi.Lib(ref, "vpref_")
+        lib.dll.vpref_threads.restype = C.c_int
+        return lib, "reference", lib.dll.vpref_threads()
+    so = os.path.join(ROOT, "oracle", "libvporacle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libvporacle.so"])
+    lib = abi.Lib(so, "vpo_")
+    lib.dll.vpo_threads.restype = C.c_int
+    return lib, "port", lib.dll.vpo_threads()
+
+
+def cpu_frame_times(lib, sc, cam, fpd, reps, first_frame=0):
+    """Times `reps` full-frame Update() passes of the CPU path; returns (seconds list, rays list)."""
+    W, H = fpd["width"], fpd["height"]
+    times, rays = [], []
+    with vp.Session(lib) as s:
+        s.set_scene(sc)
+        acc = np.zeros((H, W, 4), np.float32)
+        for i in range(reps):
+            t0 = time.perf_counter()
+            acc, _, st = s.render(cam, frame_params(fpd, frame_index=first_frame + i), accum=acc)
+            times.append(time.perf_counter() - t0)
+            rays.append(st.rays)
+    return times, rays
+
+
+def run_reference(args, cfg_idx):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sc, cam, fpd = scenes.config(cfg_idx)
+    lib, kind, cores = load_checker()
+    times, rays = cpu_frame_times(lib, sc, cam, fpd, args.warmup + args.steps)
+    t, r = times[args.warmup:], rays[args.warmup:]
+    total = sum(t)
+    value = sum(r) / total / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "reference assets (room.vox grid fixture), synthetic camera/lights",
+            "config": {"workload": scenes.WORKLOAD_NAMES[cfg_idx], "rays_per_step": int(np.mean(r))},
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                             "sample": f"{args.steps} full {fpd['width']}x{fpd['height']} frames (1 spp each) after {args.warmup} warm-up"},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, help="workload (SURVEY.md 8d); 2 = room.vox 1920x1080, the metric's config")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args, args.config)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    lib = vp.load_product()
+    sc, cam, fpd = scenes.config(args.config)
+    W, H = fpd["width"], fpd["height"]
+    shard = dict(row_tile=ROW_TILE, row_tile_stride=world, row_tile_phase=rank) if world > 1 else {}
+    sess = vp.Session(lib, local)
+    sess.set_scene(sc)
+    cc = cam.to_c()
+    accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    rgb8 = torch.zeros((H, W), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    # rows owned by each rank (interleaved 8-row tiles) for the gather
+    ntile = (H + ROW_TILE - 1) // ROW_TILE
+    tiles_r = [list(range(r, ntile, world)) for r in range(world)]
+    max_tiles = max(len(t) for t in tiles_r)
+    rgb_tiles = rgb8.view(-1)[: ntile * ROW_TILE * W] if H % ROW_TILE == 0 else None
+    gather_out = torch.zeros((world, max_tiles, ROW_TILE, W), dtype=torch.int32, device=dev) if world > 1 else None
+    my_pack = torch.zeros((max_tiles, ROW_TILE, W), dtype=torch.int32, device=dev) if world > 1 else None
+    my_idx = torch.tensor(tiles_r[rank], device=dev, dtype=torch.long) if world > 1 else None
+
+    def step(i, stats=None):
+        fp = frame_params(fpd, frame_index=i, **shard)
+        lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp), accum.data_ptr(), rgb8.data_ptr(), stream.cuda_stream,
+                                      C.byref(stats) if stats is not None else None), "render_device")
+        if world > 1:
+            # pack own tiles -> one NCCL all_gather -> de-interleave into the full frame (every rank ends with the image)
+            v = rgb8.view(ntile, ROW_TILE, W) if H % ROW_TILE == 0 else None
+            my_pack[: len(tiles_r[rank])] = v[my_idx]
+            dist.all_gather_into_tensor(gather_out.view(-1), my_pack.view(-1))
+            for r in range(world):
+                if r != rank:
+                    v[r::world] = gather_out[r, : len(tiles_r[r])]
+
+    if world > 1:
+        assert H % ROW_TILE == 0, "sharded bench expects H to be a multiple of the row tile"
+
+    # L2 flush between timed iterations (the frame's working set is far below the 126 MB L2)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize(dev)
+
+    lib.check(lib.c_stats_begin(sess.ctx), "stats_begin")
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        ev[i][0].record(stream)
+        step(args.warmup + i)
+        ev[i][1].record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    clocks = sampler.finish()
+    st = abi.VpStats()
+    lib.check(lib.c_stats_end(sess.ctx, C.byref(st)), "stats_end")
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms, float(st.rays), float(st.kernel_launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, rays_total, launches = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    else:
+        rays_total, launches = float(st.rays), float(st.kernel_launches)
+    value = rays_total / (total_ms * 1e-3) / 1e6
+
+    # ---- e2e: the reference-facing C-ABI call with host buffers, copies inside the timed region ----
+    h_acc = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
+    h_rgb = torch.zeros((H, W), dtype=torch.int32).pin_memory()
+    e2e_rays, e2e_t = 0, 0.0
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2 + e2e_steps):
+        fp = frame_params(fpd, frame_index=i, **shard)
+        s1 = abi.VpStats()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        lib.check(lib.c_render(sess.ctx, C.byref(cc), C.byref(fp), h_acc.data_ptr(), h_rgb.data_ptr(), C.byref(s1)), "render")
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            e2e_rays += s1.rays
+            e2e_t += dt
+    e = torch.tensor([e2e_t, float(e2e_rays)], dtype=torch.float64, device=dev)
+    if world > 1:
+        emax, esum = e.clone(), e.clone()
+        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(esum, op=dist.ReduceOp.SUM)
+        e2e_t, e2e_rays = float(emax[0]), float(esum[1])
+    e2e_value = e2e_rays / e2e_t / 1e6
+    own_rows = sum(min(ROW_TILE, H - k * ROW_TILE) for k in tiles_r[rank])
+    h2d = W * H * 16  # the ABI takes and returns the full-frame accumulator / image
+    d2h = W * H * 16 + W * H * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_render), single-GPU algorithmic bytes per launch ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    inst = abi.VpStats()
+    acc2 = torch.zeros_like(accum)
+    fp = frame_params(fpd, frame_index=args.warmup, flags=abi.VP_FLAG_COUNT_STEPS, **shard)
+    lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp), acc2.data_ptr(), rgb8.data_ptr(), stream.cuda_stream, C.byref(inst)),
+              "render_device(count steps)")
+    nvol = len(sc.volumes)
+    px_rank = own_rows * W if world > 1 else W * H
+    alg_bytes = inst.dda_steps * 1 + (inst.rays + inst.exit_rays) * nvol * 128 + px_rank * 32 + px_rank * 4 + inst.sky_samples * 12
+    kernel_ms = total_ms / args.steps  # one k_render launch per step dominates the step (see profiles/)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k_render_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "k_render", "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                "dda_steps_per_launch": int(inst.dda_steps),
+                "note": "latency/divergence-bound traversal of an L2-resident grid: the HBM fraction is expected to be ~1%"}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        clib, kind, cores = load_checker()
+        reps = 4
+        times, rays = cpu_frame_times(clib, sc, cam, fpd, reps)
+        best = int(np.argmin(times[1:])) + 1
+        cpu_baseline = {"value": rays[best] / times[best] / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                        "ms_per_frame": 1e3 * times[best],
+                        "sample": f"best of {reps - 1} full {W}x{H} frames (1 spp) after 1 warm-up, same scene/camera/seeds"}
+
+    line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "reference assets (room.vox grid fixture), synthetic camera/lights",
+            "config": {"workload": scenes.WORKLOAD_NAMES[args.config], "resolution": [W, H], "spp_per_step": 1,
+                       "rays_per_step": rays_total / args.steps, "sharding": f"interleaved {ROW_TILE}-row tiles x{world}" if world > 1 else "none",
+                       "l2": "flushed between timed iterations (256 MiB fill)"},
+            "ms_per_frame": total_ms / args.steps,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_t / e2e_steps, "api": "vp_render (host float4 accumulator in/out + RGB8 out)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

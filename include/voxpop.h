@@ -32,7 +32,7 @@ extern "C" {
 
 #define VP_MAT_NONE 255   /* MaterialType::NONE, reference template/scene.h:56 */
 #define VP_MAX_MATERIALS 256
-#define VP_MAX_DEPTH 64
+#define VP_MAX_BOUNCES 31 /* Renderer::maxBounces limit of this build (reference default: 14) */
 
 /* One voxel volume = reference `Scene` data members (template/scene.h:252-266).
  * grid is N*N*N bytes, index x + y*N + z*N*N (Scene::GetVoxel, template/scene.h:241-248),
@@ -97,7 +97,10 @@ typedef struct VpFrameParams {
   int32_t row_tile, row_tile_stride, row_tile_phase; /* interleaved row tiles for multi-GPU:
                               row y is rendered iff ((y / row_tile) % row_tile_stride) == row_tile_phase;
                               row_tile == 0 disables the filter */
+  uint32_t flags;          /* VP_FLAG_* */
 } VpFrameParams;
+
+#define VP_FLAG_COUNT_STEPS 1u /* also count DDA cell visits (instrumented kernel variant, slower) */
 
 /* Result of one Renderer::FindNearest call (renderer.cpp:946-1018). */
 typedef struct VpHit {
@@ -123,7 +126,8 @@ typedef struct VpStats {
   uint64_t secondary_rays;
   uint64_t shadow_rays;
   uint64_t exit_rays;
-  uint64_t dda_steps;       /* grid cell visits over all traversals */
+  uint64_t dda_steps;       /* grid cell visits over all traversals (only with VP_FLAG_COUNT_STEPS) */
+  uint64_t sky_samples;     /* paths that ended in Renderer::SampleSky */
   double device_ms;         /* device time of the render call (CUDA events) */
   uint64_t kernel_launches; /* kernels launched by this call */
 } VpStats;
@@ -161,13 +165,20 @@ int vp_set_sky(vp_ctx* ctx, const float* rgb, int w, int h, float contribution, 
  * (screen->pixels), may be NULL.  HOST pointers; copies are part of the call. */
 int vp_render(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, float* accum_rgba, uint32_t* rgb8,
               VpStats* stats);
-/* Same work with the accumulator kept resident in device memory between calls
- * (vp_accum_reset / vp_accum_download bracket a sequence of passes). */
+/* Same work on DEVICE buffers owned by the caller (accumulator resident in HBM across
+ * calls, e.g. a torch tensor that NCCL gathers afterwards).  accum_rgba_dev: W*H float4,
+ * rgb8_dev: W*H uint32 or NULL.  cuda_stream: a cudaStream_t (NULL = default stream).
+ * With stats == NULL the call only enqueues work and returns; otherwise it synchronises
+ * the stream and fills the counters. */
+int vp_render_device(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, void* accum_rgba_dev, void* rgb8_dev,
+                     void* cuda_stream, VpStats* stats);
+/* Library-owned resident accumulator: Renderer::accumulator kept in HBM between frames.
+ * vp_accum_reset = allocate/zero (Renderer::ResetAccumulator, renderer.cpp:343-346, plus
+ * the memset of Init :702); vp_render_resident = Update() on it; vp_accum_download
+ * copies accumulator and/or RGB8 image to host (either pointer may be NULL). */
+int vp_accum_reset(vp_ctx* ctx, int width, int height);
 int vp_render_resident(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, VpStats* stats);
-int vp_accum_reset(vp_ctx* ctx, int width, int height);  /* Renderer::ResetAccumulator, renderer.cpp:343-346 */
 int vp_accum_download(vp_ctx* ctx, float* accum_rgba, uint32_t* rgb8);
-/* Device pointers of the resident buffers (for NCCL gather / display interop). */
-int vp_accum_device_ptrs(vp_ctx* ctx, void** accum_rgba_dev, void** rgb8_dev);
 
 /* Primary-ray seam: Camera::GetPrimaryRay (template/camera.h:85-101) + Renderer::FindNearest
  * per pixel, RNG contract as above (2 AA draws then 2 disc draws). hits: W*H. */
@@ -177,6 +188,12 @@ int vp_trace_primary(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, 
 int vp_find_nearest(vp_ctx* ctx, const VpRay* rays, int n, VpHit* hits);
 int vp_is_occluded(vp_ctx* ctx, const VpRay* rays, int n, uint8_t* out);
 int vp_trace(vp_ctx* ctx, const VpRay* rays, const uint32_t* seeds, int n, int depth, float* rgb_out);
+
+/* Cumulative counters over asynchronous launches: vp_stats_begin zeroes them, vp_stats_end
+ * synchronises and reads them (rays of every vp_render* call in between; device_ms is not
+ * filled - time with CUDA events on the stream you passed). */
+int vp_stats_begin(vp_ctx* ctx);
+int vp_stats_end(vp_ctx* ctx, VpStats* stats);
 
 /* Build/runtime facts for the harness: fills up to `cap` bytes of a JSON string. */
 int vp_info(vp_ctx* ctx, char* buf, int cap);

@@ -37,6 +37,8 @@ VP_HIDDEN float sinf(float x) noexcept { return (float)sin((double)x); }
 VP_HIDDEN float cosf(float x) noexcept { return (float)cos((double)x); }
 VP_HIDDEN float expf(float x) noexcept { return (float)exp((double)x); }
 VP_HIDDEN float powf(float x, float y) noexcept { return (float)pow((double)x, (double)y); }
+// g++ merges sinf(x)/cosf(x) pairs (RandomSphereSample, RandomPointInCircle) into one sincosf call
+VP_HIDDEN void sincosf(float x, float* s, float* c) noexcept { *s = (float)sin((double)x); *c = (float)cos((double)x); }
 }
 
 #include "tmpl8math.cpp"
@@ -292,6 +294,7 @@ int vpref_render(vpref_ctx* c, const VpCamera* cam, const VpFrameParams* fp, flo
     stats->shadow_rays = shadow;
     stats->exit_rays = exitray;
     stats->dda_steps = steps;
+    stats->sky_samples = 0;  // not instrumented in the reference build
     stats->device_ms = (t1 - t0) * 1e3;
     stats->kernel_launches = 0;
   }

@@ -63,7 +63,7 @@ typedef struct vpo_ctx {
   float* sky; int skyw, skyh; float sky_contrib; int sky_active;
 } vpo_ctx;
 
-typedef struct { uint64_t nearest, shadow, exitray, steps; uint32_t lastcell; int lastface; int in_light; } Counters;
+typedef struct { uint64_t nearest, shadow, exitray, steps, sky; uint32_t lastcell; int lastface; int in_light; } Counters;
 
 typedef struct { vpo_ctx* c; uint32_t seed; Counters cnt; } Thread;
 
@@ -653,7 +653,7 @@ static f3 trace(Thread* T, Ray* ray, int depth)
   vpo_ctx* c = T->c;
   if (depth < 0) return v3s(0);
   const int voxIndex = find_nearest(T, ray);
-  if (ray->mat == VP_MAT_NONE) return sample_sky(c, ray->D);
+  if (ray->mat == VP_MAT_NONE) { T->cnt.sky++; return sample_sky(c, ray->D); }
   const int m = ray->mat;
   if (m >= 5 && m <= 7) { /* METAL_HIGH/MID/LOW :1103-1114 */
     const f3 refl = reflect3(ray->D, ray->N);
@@ -899,7 +899,7 @@ int vpo_render(vpo_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* 
 {
   const int W = fp->width, H = fp->height;
   const uint32_t npix = (uint32_t)W * (uint32_t)H;
-  uint64_t nearest = 0, shadow = 0, exitray = 0, steps = 0, primary = 0;
+  uint64_t nearest = 0, shadow = 0, exitray = 0, steps = 0, primary = 0, sky = 0;
   double t0 = 0, t1 = 0;
 #ifdef _OPENMP
   t0 = omp_get_wtime();
@@ -908,7 +908,7 @@ int vpo_render(vpo_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* 
     const uint32_t frame = fp->frame_index + (uint32_t)s;
     const float weight = 1.0f / ((float)frame + 1.0f); /* renderer.cpp:1651 */
     const float invWeight = 1.0f - weight;
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nearest, shadow, exitray, steps, primary)
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nearest, shadow, exitray, steps, primary, sky)
     for (int y = 0; y < H; y++) {
       if (!row_selected(fp, y)) continue;
       Thread T; memset(&T, 0, sizeof(T)); T.c = c;
@@ -930,7 +930,7 @@ int vpo_render(vpo_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* 
         if (out8) out8[px] = rgb8(reinhard_jodie(v3(r, g, b)));
         if (fp->max_bounces >= 0) primary++;
       }
-      nearest += T.cnt.nearest; shadow += T.cnt.shadow; exitray += T.cnt.exitray; steps += T.cnt.steps;
+      nearest += T.cnt.nearest; shadow += T.cnt.shadow; exitray += T.cnt.exitray; steps += T.cnt.steps; sky += T.cnt.sky;
     }
   }
 #ifdef _OPENMP
@@ -938,7 +938,7 @@ int vpo_render(vpo_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* 
 #endif
   if (stats) {
     stats->primary_rays = primary; stats->secondary_rays = nearest - primary; stats->shadow_rays = shadow;
-    stats->exit_rays = exitray; stats->dda_steps = steps; stats->device_ms = (t1 - t0) * 1e3; stats->kernel_launches = 0;
+    stats->exit_rays = exitray; stats->dda_steps = steps; stats->sky_samples = sky; stats->device_ms = (t1 - t0) * 1e3; stats->kernel_launches = 0;
   }
   return 0;
 }

@@ -56,12 +56,12 @@ class VpFrameParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("max_bounces", C.c_int32), ("spp", C.c_int32),
                 ("frame_index", C.c_uint32), ("seed", C.c_uint32), ("aa_strength", C.c_float),
                 ("row_begin", C.c_int32), ("row_end", C.c_int32), ("row_tile", C.c_int32),
-                ("row_tile_stride", C.c_int32), ("row_tile_phase", C.c_int32)]
+                ("row_tile_stride", C.c_int32), ("row_tile_phase", C.c_int32), ("flags", C.c_uint32)]
 
 
 class VpStats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("secondary_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
-                ("exit_rays", C.c_uint64), ("dda_steps", C.c_uint64), ("device_ms", C.c_double),
+                ("exit_rays", C.c_uint64), ("dda_steps", C.c_uint64), ("sky_samples", C.c_uint64), ("device_ms", C.c_double),
                 ("kernel_launches", C.c_uint64)]
 
     def as_dict(self):
@@ -72,6 +72,9 @@ class VpStats(C.Structure):
         return self.primary_rays + self.secondary_rays + self.shadow_rays
 
 
+VP_OK, VP_EINVAL, VP_ENODEVICE, VP_ECUDA, VP_ENOMEM, VP_ESTATE = 0, -1, -2, -3, -4, -5
+VP_FLAG_COUNT_STEPS = 1
+
 HIT_DTYPE = np.dtype([("volume", "<i4"), ("cell", "<u4"), ("t", "<f4"), ("normal", "<f4", (3,)),
                       ("material", "u1"), ("face", "i1"), ("inside", "u1"), ("pad", "u1")])
 RAY_DTYPE = np.dtype([("o", "<f4", (3,)), ("d", "<f4", (3,)), ("t", "<f4"), ("inside", "<u4")])
@@ -81,7 +84,7 @@ assert HIT_DTYPE.itemsize == 28 and RAY_DTYPE.itemsize == 32
 ABI_SYMBOLS = [
     "create", "destroy", "last_error", "set_volumes", "update_volume_grid", "update_volume_transform",
     "set_materials", "set_lights", "set_prims", "set_sky", "render", "render_resident", "accum_reset",
-    "accum_download", "accum_device_ptrs", "trace_primary", "find_nearest", "is_occluded", "trace", "info",
+    "accum_download", "render_device", "trace_primary", "find_nearest", "is_occluded", "trace", "info", "stats_begin", "stats_end",
 ]
 
 
@@ -126,8 +129,11 @@ class Lib:
           optional=True)
         f("accum_reset", C.c_int, [C.c_void_p, C.c_int, C.c_int], optional=True)
         f("accum_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p], optional=True)
-        f("accum_device_ptrs", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)], optional=True)
+        f("render_device", C.c_int, [C.c_void_p, C.POINTER(VpCamera), C.POINTER(VpFrameParams), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.POINTER(VpStats)], optional=True)
         f("info", C.c_int, [C.c_void_p, C.c_char_p, C.c_int], optional=True)
+        f("stats_begin", C.c_int, [C.c_void_p], optional=True)
+        f("stats_end", C.c_int, [C.c_void_p, C.POINTER(VpStats)], optional=True)
 
     def _f(self, name, restype, argtypes, optional=False):
         try:

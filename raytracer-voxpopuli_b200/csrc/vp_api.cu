@@ -1,0 +1,572 @@
+// vp_api.cu - extern "C" layer of libvoxpop_b200.so (include/voxpop.h).
+// Plain CUDA runtime; no PyTorch, no CPU fallback: every compute entry point launches
+// the sm_100a kernels of vp_kernels.cuh or fails with an error code.
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vp_kernels.cuh"
+
+using namespace vp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail(VP_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct HostVolume {
+  uint32_t n = 0, nb = 0, nc = 0;
+  uint8_t* grid = nullptr;
+  unsigned long long* fine = nullptr;
+  uint32_t* coarse = nullptr;
+  size_t coarse_words = 0;
+  DVolume d{};
+};
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n ? n : 1;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct vp_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<HostVolume> vols;
+  DevBuf<DVolume> d_vols;
+  DevBuf<VpMaterial> d_mat;
+  DevBuf<VpPointLight> d_pl;
+  DevBuf<VpAreaLight> d_al;
+  DevBuf<VpSpotLight> d_sl;
+  DevBuf<VpSphere> d_sph;
+  DevBuf<VpTriangle> d_tri;
+  DevBuf<float> d_sky;
+  DevBuf<unsigned long long> d_counters;  // 8 counters + tile counter slot
+  DevBuf<float4> d_accum;                 // library-owned resident accumulator / staging for vp_render
+  DevBuf<uint32_t> d_rgb8;
+  DevBuf<unsigned char> d_scratch_in, d_scratch_out, d_scratch_aux;
+  int acc_w = 0, acc_h = 0;
+  DScene sc{};
+  bool have_volumes = false;
+  int blocks_per_sm = 0;
+};
+
+namespace {
+
+int bind(vp_ctx* c)
+{
+  CU(cudaSetDevice(c->device));
+  return 0;
+}
+
+void free_volume(HostVolume& v)
+{
+  if (v.grid) cudaFree(v.grid);
+  if (v.fine) cudaFree(v.fine);
+  if (v.coarse) cudaFree(v.coarse);
+  v = HostVolume();
+}
+
+int build_masks(vp_ctx* c, HostVolume& v)
+{
+  const uint32_t nbricks = v.nb * v.nb * v.nb, ncoarse = v.nc * v.nc * v.nc;
+  CU(cudaMemsetAsync(v.coarse, 0, v.coarse_words * sizeof(uint32_t), c->stream));
+  k_fine<<<(nbricks + 127) / 128, 128, 0, c->stream>>>(v.grid, v.n, v.nb, v.fine);
+  k_coarse<<<(ncoarse + 127) / 128, 128, 0, c->stream>>>(v.fine, v.nb, v.nc, v.coarse);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+void fill_dvolume(HostVolume& v, const float* M, const float* iM, const float* bmin, const float* bmax)
+{
+  memcpy(v.d.iM, iM, 12 * sizeof(float));
+  memcpy(v.d.M, M, 12 * sizeof(float));
+  memcpy(v.d.bmin, bmin, 12);
+  memcpy(v.d.bmax, bmax, 12);
+  v.d.n = v.n; v.d.nb = v.nb; v.d.nc = v.nc; v.d.pad = 0;
+  v.d.grid = v.grid; v.d.fine = v.fine; v.d.coarse = v.coarse;
+}
+
+int upload_volume_table(vp_ctx* c)
+{
+  std::vector<DVolume> tab(c->vols.size());
+  for (size_t i = 0; i < c->vols.size(); i++) tab[i] = c->vols[i].d;
+  CU(c->d_vols.reserve(tab.size()));
+  if (!tab.empty()) CU(cudaMemcpyAsync(c->d_vols.p, tab.data(), tab.size() * sizeof(DVolume), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->sc.vol = c->d_vols.p;
+  c->sc.nvol = (int)tab.size();
+  return 0;
+}
+
+template <class T>
+int upload_array(vp_ctx* c, DevBuf<T>& buf, const T* src, int n)
+{
+  CU(buf.reserve((size_t)(n > 0 ? n : 1)));
+  if (n > 0) CU(cudaMemcpyAsync(buf.p, src, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+size_t smem_bytes(const vp_ctx* c) { return (size_t)c->sc.nvol * sizeof(DVolume) + 16; }
+
+int check_frame(const vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp)
+{
+  if (!c) return fail(VP_EINVAL, "null context");
+  if (!cam || !fp) return fail(VP_EINVAL, "null camera / frame params");
+  if (fp->width <= 0 || fp->height <= 0 || (long long)fp->width * fp->height > 0x7FFFFFFFll) return fail(VP_EINVAL, "bad resolution %dx%d", fp->width, fp->height);
+  if (fp->max_bounces >= VP_MAX_LEVELS) return fail(VP_EINVAL, "max_bounces %d exceeds the supported %d", fp->max_bounces, VP_MAX_LEVELS - 1);
+  if (fp->spp < 0) return fail(VP_EINVAL, "negative spp");
+  if (fp->row_tile > 0 && (fp->row_tile_stride <= 0 || fp->row_tile_phase < 0 || fp->row_tile_phase >= fp->row_tile_stride))
+    return fail(VP_EINVAL, "bad row tile interleave %d/%d/%d", fp->row_tile, fp->row_tile_stride, fp->row_tile_phase);
+  if (!c->have_volumes) return fail(VP_ESTATE, "vp_set_volumes has not been called");
+  return 0;
+}
+
+void fill_params(const vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, RenderParams& p)
+{
+  p.sc = c->sc;
+  p.cam = *cam;
+  p.W = fp->width; p.H = fp->height;
+  p.max_bounces = fp->max_bounces; p.spp = fp->spp;
+  p.frame0 = fp->frame_index; p.seed = fp->seed; p.aa = fp->aa_strength;
+  p.row_begin = fp->row_begin; p.row_end = fp->row_end;
+  if (p.row_begin == 0 && p.row_end == 0) p.row_end = fp->height;
+  p.row_tile = fp->row_tile; p.row_tile_stride = fp->row_tile_stride; p.row_tile_phase = fp->row_tile_phase;
+  p.accum = nullptr; p.rgb8 = nullptr; p.hits = nullptr;
+  p.counters = c->d_counters.p;
+  p.tile_counter = reinterpret_cast<unsigned int*>(c->d_counters.p + 8);
+}
+
+int grid_blocks(const vp_ctx* c, long long work_warps)
+{
+  long long full = (long long)c->sm_count * c->blocks_per_sm;
+  long long need = (work_warps + (kBlock / 32) - 1) / (kBlock / 32);
+  if (need < 1) need = 1;
+  return (int)(need < full ? need : full);
+}
+
+// core: enqueue the render kernel on `stream` for device buffers
+int launch_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream,
+                  VpStats* stats)
+{
+  RenderParams p;
+  fill_params(c, cam, fp, p);
+  p.accum = accum; p.rgb8 = rgb8;
+  unsigned long long before[8] = {0};
+  if (stats) {
+    CU(cudaMemcpyAsync(before, c->d_counters.p, sizeof(before), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+  }
+  CU(cudaMemsetAsync(c->d_counters.p + 8, 0, sizeof(unsigned long long), stream));
+  const long long tiles = (long long)((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
+  const int blocks = grid_blocks(c, tiles);
+  if (stats) CU(cudaEventRecord(c->ev0, stream));
+  if (fp->flags & VP_FLAG_COUNT_STEPS) k_render<true><<<blocks, kBlock, smem_bytes(c), stream>>>(p);
+  else k_render<false><<<blocks, kBlock, smem_bytes(c), stream>>>(p);
+  CU(cudaGetLastError());
+  if (stats) {
+    CU(cudaEventRecord(c->ev1, stream));
+    unsigned long long h[8];
+    CU(cudaMemcpyAsync(h, c->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    for (int k = 0; k < 8; k++) h[k] -= before[k];
+    stats->primary_rays = h[4];
+    stats->secondary_rays = h[0] - h[4];
+    stats->shadow_rays = h[1];
+    stats->exit_rays = h[2];
+    stats->dda_steps = h[3];
+    stats->sky_samples = h[6];
+    stats->device_ms = ms;
+    stats->kernel_launches = h[7];
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vp_last_error(void) { return g_err.c_str(); }
+
+vp_ctx* vp_create(int device)
+{
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fail(VP_ENODEVICE, "no CUDA device: %s (this library has no CPU fallback)", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return nullptr;
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= ndev) { fail(VP_ENODEVICE, "device %d out of range (%d devices)", device, ndev); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { fail(VP_ENODEVICE, "cudaSetDevice(%d) failed", device); return nullptr; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { fail(VP_ENODEVICE, "cudaGetDeviceProperties failed"); return nullptr; }
+  if (prop.major != 10) { fail(VP_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return nullptr; }
+  vp_ctx* c = new vp_ctx;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+      cudaEventCreate(&c->ev1) != cudaSuccess || c->d_counters.reserve(16) != cudaSuccess ||
+      cudaMemset(c->d_counters.p, 0, 16 * sizeof(unsigned long long)) != cudaSuccess) {
+    fail(VP_ENODEVICE, "CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return nullptr;
+  }
+  // default tables: 256 white diffuse materials (reference renderer.cpp:434-441), zero directional light
+  std::vector<VpMaterial> mats(256);
+  for (auto& m : mats) { m.albedo[0] = m.albedo[1] = m.albedo[2] = 1.0f; m.roughness = 1.0f; m.emissive = 0.0f; m.ior = 1.5f; }
+  if (upload_array(c, c->d_mat, mats.data(), 256) != 0) { delete c; return nullptr; }
+  c->sc.mat = c->d_mat.p;
+  c->sc.dl.direction[0] = 1; c->sc.dl.direction[1] = c->sc.dl.direction[2] = 0;
+  c->sc.dl.color[0] = c->sc.dl.color[1] = c->sc.dl.color[2] = 0;
+  c->sc.area_samples = 3;
+  c->sc.sky_contrib = 1.0f;
+  int occ = 0;
+  cudaFuncSetAttribute(k_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_render<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_occluded, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render<false>, kBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
+  c->blocks_per_sm = occ;
+  return c;
+}
+
+void vp_destroy(vp_ctx* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (auto& v : c->vols) free_volume(v);
+  c->d_vols.release(); c->d_mat.release(); c->d_pl.release(); c->d_al.release(); c->d_sl.release();
+  c->d_sph.release(); c->d_tri.release(); c->d_sky.release(); c->d_counters.release(); c->d_accum.release();
+  c->d_rgb8.release(); c->d_scratch_in.release(); c->d_scratch_out.release(); c->d_scratch_aux.release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int vp_set_volumes(vp_ctx* c, const VpVolume* vols, int n)
+{
+  if (!c || n < 0 || (n > 0 && !vols)) return fail(VP_EINVAL, "bad arguments to vp_set_volumes");
+  if ((size_t)n * sizeof(DVolume) + 16 > 64 * 1024) return fail(VP_EINVAL, "too many volumes (%d)", n);
+  if (bind(c)) return VP_ECUDA;
+  for (int i = 0; i < n; i++)
+    if (!vols[i].grid || vols[i].n == 0 || vols[i].n > 1024) return fail(VP_EINVAL, "volume %d: bad grid pointer or size %u", i, vols[i].n);
+  for (auto& v : c->vols) free_volume(v);
+  c->vols.assign((size_t)n, HostVolume());
+  for (int i = 0; i < n; i++) {
+    HostVolume& v = c->vols[i];
+    v.n = vols[i].n; v.nb = (v.n + 3) / 4; v.nc = (v.n + 15) / 16;
+    const size_t bytes = (size_t)v.n * v.n * v.n;
+    v.coarse_words = ((size_t)v.nc * v.nc * v.nc + 31) / 32;
+    CU(cudaMalloc(&v.grid, bytes));
+    CU(cudaMalloc(&v.fine, (size_t)v.nb * v.nb * v.nb * sizeof(unsigned long long)));
+    CU(cudaMalloc(&v.coarse, v.coarse_words * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(v.grid, vols[i].grid, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (build_masks(c, v)) return VP_ECUDA;
+    fill_dvolume(v, vols[i].matrix, vols[i].inv_matrix, vols[i].cube_min, vols[i].cube_max);
+  }
+  if (upload_volume_table(c)) return VP_ECUDA;
+  c->have_volumes = true;
+  return 0;
+}
+
+int vp_update_volume_grid(vp_ctx* c, int vi, uint32_t offset, uint32_t len, const uint8_t* bytes)
+{
+  if (!c || vi < 0 || vi >= (int)c->vols.size() || !bytes) return fail(VP_EINVAL, "bad arguments to vp_update_volume_grid");
+  HostVolume& v = c->vols[vi];
+  const size_t total = (size_t)v.n * v.n * v.n;
+  if ((size_t)offset + len > total) return fail(VP_EINVAL, "dirty range [%u,+%u) exceeds grid of %zu bytes", offset, len, total);
+  if (bind(c)) return VP_ECUDA;
+  CU(cudaMemcpyAsync(v.grid + offset, bytes, len, cudaMemcpyHostToDevice, c->stream));
+  if (build_masks(c, v)) return VP_ECUDA;
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int vp_update_volume_transform(vp_ctx* c, int vi, const float M[16], const float iM[16], const float bmin[3], const float bmax[3])
+{
+  if (!c || vi < 0 || vi >= (int)c->vols.size() || !M || !iM || !bmin || !bmax) return fail(VP_EINVAL, "bad arguments to vp_update_volume_transform");
+  if (bind(c)) return VP_ECUDA;
+  fill_dvolume(c->vols[vi], M, iM, bmin, bmax);
+  return upload_volume_table(c);
+}
+
+int vp_set_materials(vp_ctx* c, const VpMaterial* m, int n)
+{
+  if (!c || !m || n < 0 || n > VP_MAX_MATERIALS) return fail(VP_EINVAL, "bad arguments to vp_set_materials (n=%d)", n);
+  if (bind(c)) return VP_ECUDA;
+  if (n > 0) CU(cudaMemcpyAsync(c->d_mat.p, m, sizeof(VpMaterial) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int vp_set_lights(vp_ctx* c, const VpPointLight* p, int np, const VpAreaLight* a, int na, const VpSpotLight* s, int ns,
+                  const VpDirLight* d, int area_samples)
+{
+  if (!c || np < 0 || na < 0 || ns < 0 || (np && !p) || (na && !a) || (ns && !s)) return fail(VP_EINVAL, "bad arguments to vp_set_lights");
+  if (bind(c)) return VP_ECUDA;
+  if (upload_array(c, c->d_pl, p, np) || upload_array(c, c->d_al, a, na) || upload_array(c, c->d_sl, s, ns)) return VP_ECUDA;
+  c->sc.pl = c->d_pl.p; c->sc.npl = np;
+  c->sc.al = c->d_al.p; c->sc.nal = na;
+  c->sc.sl = c->d_sl.p; c->sc.nsl = ns;
+  if (d) c->sc.dl = *d;
+  c->sc.area_samples = area_samples;
+  return 0;
+}
+
+int vp_set_prims(vp_ctx* c, const VpSphere* s, int ns, const VpTriangle* t, int nt)
+{
+  if (!c || ns < 0 || nt < 0 || (ns && !s) || (nt && !t)) return fail(VP_EINVAL, "bad arguments to vp_set_prims");
+  if (bind(c)) return VP_ECUDA;
+  if (upload_array(c, c->d_sph, s, ns) || upload_array(c, c->d_tri, t, nt)) return VP_ECUDA;
+  c->sc.sph = c->d_sph.p; c->sc.nsph = ns;
+  c->sc.tri = c->d_tri.p; c->sc.ntri = nt;
+  return 0;
+}
+
+int vp_set_sky(vp_ctx* c, const float* rgb, int w, int h, float contribution, int active)
+{
+  if (!c || w < 0 || h < 0) return fail(VP_EINVAL, "bad arguments to vp_set_sky");
+  if (bind(c)) return VP_ECUDA;
+  const bool have = rgb && w > 0 && h > 0;
+  if (have) {
+    const size_t n = (size_t)w * h * 3;
+    CU(c->d_sky.reserve(n));
+    CU(cudaMemcpyAsync(c->d_sky.p, rgb, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  c->sc.sky = have ? c->d_sky.p : nullptr;
+  c->sc.skyw = have ? w : 0; c->sc.skyh = have ? h : 0;
+  c->sc.sky_contrib = contribution;
+  c->sc.sky_active = (active && have) ? 1 : 0;
+  return 0;
+}
+
+int vp_render_device(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, void* accum_dev, void* rgb8_dev, void* stream,
+                     VpStats* stats)
+{
+  if (int rc = check_frame(c, cam, fp)) return rc;
+  if (!accum_dev) return fail(VP_EINVAL, "null accumulator");
+  if (bind(c)) return VP_ECUDA;
+  return launch_render(c, cam, fp, (float4*)accum_dev, (uint32_t*)rgb8_dev, (cudaStream_t)stream, stats);
+}
+
+int vp_accum_reset(vp_ctx* c, int w, int h)
+{
+  if (!c || w <= 0 || h <= 0) return fail(VP_EINVAL, "bad arguments to vp_accum_reset");
+  if (bind(c)) return VP_ECUDA;
+  const size_t n = (size_t)w * h;
+  CU(c->d_accum.reserve(n));
+  CU(c->d_rgb8.reserve(n));
+  CU(cudaMemsetAsync(c->d_accum.p, 0, n * sizeof(float4), c->stream));
+  CU(cudaMemsetAsync(c->d_rgb8.p, 0, n * sizeof(uint32_t), c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->acc_w = w; c->acc_h = h;
+  return 0;
+}
+
+int vp_render_resident(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, VpStats* stats)
+{
+  if (int rc = check_frame(c, cam, fp)) return rc;
+  if (c->acc_w != fp->width || c->acc_h != fp->height) return fail(VP_ESTATE, "vp_accum_reset(%d,%d) must precede vp_render_resident", fp->width, fp->height);
+  if (bind(c)) return VP_ECUDA;
+  return launch_render(c, cam, fp, c->d_accum.p, c->d_rgb8.p, c->stream, stats);
+}
+
+int vp_accum_download(vp_ctx* c, float* accum, uint32_t* rgb8)
+{
+  if (!c || c->acc_w <= 0) return fail(VP_ESTATE, "no resident accumulator");
+  if (bind(c)) return VP_ECUDA;
+  const size_t n = (size_t)c->acc_w * c->acc_h;
+  if (accum) CU(cudaMemcpyAsync(accum, c->d_accum.p, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  if (rgb8) CU(cudaMemcpyAsync(rgb8, c->d_rgb8.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* accum, uint32_t* rgb8, VpStats* stats)
+{
+  if (int rc = check_frame(c, cam, fp)) return rc;
+  if (!accum) return fail(VP_EINVAL, "null accumulator");
+  if (bind(c)) return VP_ECUDA;
+  const size_t n = (size_t)fp->width * fp->height;
+  CU(c->d_accum.reserve(n));
+  CU(c->d_rgb8.reserve(n));
+  c->acc_w = fp->width; c->acc_h = fp->height;
+  CU(cudaMemcpyAsync(c->d_accum.p, accum, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  VpStats local;
+  if (int rc = launch_render(c, cam, fp, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, stats ? stats : &local)) return rc;
+  CU(cudaMemcpyAsync(accum, c->d_accum.p, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  if (rgb8) CU(cudaMemcpyAsync(rgb8, c->d_rgb8.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int vp_trace_primary(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, VpHit* hits)
+{
+  if (int rc = check_frame(c, cam, fp)) return rc;
+  if (!hits) return fail(VP_EINVAL, "null hits");
+  if (bind(c)) return VP_ECUDA;
+  const size_t n = (size_t)fp->width * fp->height;
+  CU(c->d_scratch_out.reserve(n * sizeof(VpHit)));
+  CU(cudaMemsetAsync(c->d_scratch_out.p, 0, n * sizeof(VpHit), c->stream));
+  RenderParams p;
+  fill_params(c, cam, fp, p);
+  p.hits = reinterpret_cast<VpHit*>(c->d_scratch_out.p);
+  CU(cudaMemsetAsync(c->d_counters.p + 8, 0, sizeof(unsigned long long), c->stream));
+  const long long tiles = (long long)((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
+  k_primary<<<grid_blocks(c, tiles), kBlock, smem_bytes(c), c->stream>>>(p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(hits, c->d_scratch_out.p, n * sizeof(VpHit), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int batch_common(vp_ctx* c, const VpRay* rays, int n, BatchParams& p)
+{
+  if (!c || n < 0 || (n && !rays)) return fail(VP_EINVAL, "bad batch arguments");
+  if (!c->have_volumes) return fail(VP_ESTATE, "vp_set_volumes has not been called");
+  if (bind(c)) return VP_ECUDA;
+  CU(c->d_scratch_in.reserve((size_t)(n ? n : 1) * sizeof(VpRay)));
+  if (n) CU(cudaMemcpyAsync(c->d_scratch_in.p, rays, (size_t)n * sizeof(VpRay), cudaMemcpyHostToDevice, c->stream));
+  memset(&p, 0, sizeof(p));
+  p.sc = c->sc;
+  p.rays = reinterpret_cast<const VpRay*>(c->d_scratch_in.p);
+  p.n = n;
+  return 0;
+}
+
+int vp_find_nearest(vp_ctx* c, const VpRay* rays, int n, VpHit* hits)
+{
+  BatchParams p;
+  if (int rc = batch_common(c, rays, n, p)) return rc;
+  if (n == 0) return 0;
+  if (!hits) return fail(VP_EINVAL, "null hits");
+  CU(c->d_scratch_out.reserve((size_t)n * sizeof(VpHit)));
+  p.hits = reinterpret_cast<VpHit*>(c->d_scratch_out.p);
+  k_nearest<<<grid_blocks(c, (n + 31) / 32), kBlock, smem_bytes(c), c->stream>>>(p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(hits, c->d_scratch_out.p, (size_t)n * sizeof(VpHit), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int vp_is_occluded(vp_ctx* c, const VpRay* rays, int n, uint8_t* out)
+{
+  BatchParams p;
+  if (int rc = batch_common(c, rays, n, p)) return rc;
+  if (n == 0) return 0;
+  if (!out) return fail(VP_EINVAL, "null output");
+  CU(c->d_scratch_out.reserve((size_t)n));
+  p.occ = c->d_scratch_out.p;
+  k_occluded<<<grid_blocks(c, (n + 31) / 32), kBlock, smem_bytes(c), c->stream>>>(p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, c->d_scratch_out.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int vp_trace(vp_ctx* c, const VpRay* rays, const uint32_t* seeds, int n, int depth, float* rgb)
+{
+  BatchParams p;
+  if (int rc = batch_common(c, rays, n, p)) return rc;
+  if (n == 0) return 0;
+  if (!seeds || !rgb) return fail(VP_EINVAL, "null seeds / output");
+  if (depth >= VP_MAX_LEVELS) return fail(VP_EINVAL, "depth %d exceeds the supported %d", depth, VP_MAX_LEVELS - 1);
+  CU(c->d_scratch_aux.reserve((size_t)n * sizeof(uint32_t)));
+  CU(cudaMemcpyAsync(c->d_scratch_aux.p, seeds, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CU(c->d_scratch_out.reserve((size_t)n * 3 * sizeof(float)));
+  p.seeds = reinterpret_cast<const uint32_t*>(c->d_scratch_aux.p);
+  p.depth = depth;
+  p.rgb = reinterpret_cast<float*>(c->d_scratch_out.p);
+  k_trace<<<grid_blocks(c, (n + 31) / 32), kBlock, smem_bytes(c), c->stream>>>(p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(rgb, c->d_scratch_out.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int vp_stats_begin(vp_ctx* c)
+{
+  if (!c) return fail(VP_EINVAL, "null context");
+  if (bind(c)) return VP_ECUDA;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemset(c->d_counters.p, 0, 8 * sizeof(unsigned long long)));
+  return 0;
+}
+
+int vp_stats_end(vp_ctx* c, VpStats* stats)
+{
+  if (!c || !stats) return fail(VP_EINVAL, "bad arguments to vp_stats_end");
+  if (bind(c)) return VP_ECUDA;
+  CU(cudaDeviceSynchronize());
+  unsigned long long h[8];
+  CU(cudaMemcpy(h, c->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+  stats->primary_rays = h[4];
+  stats->secondary_rays = h[0] - h[4];
+  stats->shadow_rays = h[1];
+  stats->exit_rays = h[2];
+  stats->dda_steps = h[3];
+  stats->sky_samples = h[6];
+  stats->device_ms = 0;
+  stats->kernel_launches = h[7];
+  return 0;
+}
+
+int vp_info(vp_ctx* c, char* buf, int cap)
+{
+  if (!c || !buf || cap <= 0) return fail(VP_EINVAL, "bad arguments to vp_info");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) return fail(VP_ECUDA, "cudaGetDeviceProperties failed");
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, k_render<false>);
+  snprintf(buf, (size_t)cap,
+           "{\"device\": %d, \"name\": \"%s\", \"sm\": \"%d.%d\", \"sm_count\": %d, \"blocks_per_sm\": %d, \"block\": %d, "
+           "\"k_render_regs\": %d, \"k_render_local_bytes\": %zu, \"volumes\": %d, \"max_levels\": %d}",
+           c->device, prop.name, prop.major, prop.minor, c->sm_count, c->blocks_per_sm, kBlock, fa.numRegs, fa.localSizeBytes,
+           c->sc.nvol, VP_MAX_LEVELS);
+  return 0;
+}
+
+}  // extern "C"

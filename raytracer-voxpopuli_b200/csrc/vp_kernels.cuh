@@ -1,0 +1,240 @@
+// vp_kernels.cuh - kernels of the render path (sm_100a).
+//
+// K_render   : primary-gen + path walk + fold + accumulate + tonemap + RGB8, one lane per
+//              pixel, persistent blocks pulling 8x4-pixel warp tiles from a global counter.
+// K_primary  : primary-gen + nearest hit only (bit-exact hit dumps).
+// K_nearest / K_occluded / K_trace : batch seams of Renderer::FindNearest / IsOccluded / Trace.
+// K_fine / K_coarse : occupancy hierarchy build (per upload / dirty update).
+#pragma once
+#include "vp_device.cuh"
+
+namespace vp {
+
+struct RenderParams {
+  DScene sc;
+  VpCamera cam;
+  int W, H;
+  int max_bounces;
+  int spp;
+  uint32_t frame0;
+  uint32_t seed;
+  float aa;
+  int row_begin, row_end, row_tile, row_tile_stride, row_tile_phase;
+  float4* accum;
+  uint32_t* rgb8;
+  unsigned long long* counters;  // [0] nearest [1] shadow [2] exit [3] steps [4] primary [5] in_light [6] sky [7] launches
+  unsigned int* tile_counter;
+  VpHit* hits;
+};
+
+constexpr int kTileW = 8, kTileH = 4;  // one warp = one 8x4 pixel tile (coherent primary rays)
+constexpr int kBlock = 128;
+
+__device__ __forceinline__ bool row_selected(const RenderParams& p, int y)
+{
+  if (y < p.row_begin || y >= p.row_end) return false;
+  if (p.row_tile > 0 && ((y / p.row_tile) % p.row_tile_stride) != p.row_tile_phase) return false;
+  return true;
+}
+
+// stage the volume table into shared memory (read by every ray of the block)
+__device__ __forceinline__ const DVolume* stage_volumes(const DScene& sc, unsigned char* smem)
+{
+  DVolume* sv = reinterpret_cast<DVolume*>(smem);
+  const int words = sc.nvol * (int)(sizeof(DVolume) / 4);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(sc.vol);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(sv);
+  for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+  __syncthreads();
+  return sv;
+}
+
+__device__ __forceinline__ void flush_counters(const RenderParams& p, const Counters& cn, unsigned int primary, int in_light)
+{
+  unsigned long long v[7] = {cn.nearest, cn.shadow, cn.exitray, cn.steps, primary, (unsigned long long)in_light, cn.sky};
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    unsigned long long x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(p.counters + k, x);
+  }
+}
+
+template <bool kCountSteps>
+__global__ void __launch_bounds__(kBlock) k_render(const __grid_constant__ RenderParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DVolume* svol = stage_volumes(p.sc, smem);
+  const int lane = threadIdx.x & 31;
+  const int tiles_x = (p.W + kTileW - 1) / kTileW;
+  const int tiles_y = (p.H + kTileH - 1) / kTileH;
+  const unsigned int ntiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+  const uint32_t npix = (uint32_t)p.W * (uint32_t)p.H;
+  Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
+  unsigned int primary = 0;
+  int in_light = 0;
+  Level stack[VP_MAX_LEVELS];
+  for (;;) {
+    unsigned int tile = 0;
+    if (lane == 0) tile = atomicAdd(p.tile_counter, 1u);
+    tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+    if (tile >= ntiles) break;
+    const int ty = (int)(tile / (unsigned int)tiles_x), tx = (int)(tile % (unsigned int)tiles_x);
+    const int x = tx * kTileW + (lane & (kTileW - 1));
+    const int y = ty * kTileH + (lane / kTileW);
+    if (x >= p.W || y >= p.H || !row_selected(p, y)) continue;
+    const uint32_t px = (uint32_t)y * (uint32_t)p.W + (uint32_t)x;
+    float4 acc = p.accum[px];
+    for (int s = 0; s < p.spp; s++) {
+      const uint32_t frame = p.frame0 + (uint32_t)s;
+      uint32_t seed = pixel_seed(px, frame, npix, p.seed);
+      // Renderer::Update scalar pixel loop, renderer.cpp:1851-1881
+      const float rx = rnd(seed) * p.aa;
+      const float ry = rnd(seed) * p.aa;
+      const Ray pr = primary_ray(p.cam, (float)x + rx, (float)y + ry, p.W, p.H, seed);
+      const f3 col = trace_path<kCountSteps>(p.sc, svol, pr, p.max_bounces, seed, cn, stack, &in_light);
+      if (p.max_bounces >= 0) primary++;
+      const float weight = 1.0f / ((float)frame + 1.0f);  // renderer.cpp:1651
+      const float invWeight = 1.0f - weight;
+      const float w1 = 1.0f - invWeight;                   // BlendColor, renderer.cpp:1630-1633
+      acc.x = col.x * w1 + acc.x * invWeight;
+      acc.y = col.y * w1 + acc.y * invWeight;
+      acc.z = col.z * w1 + acc.z * invWeight;
+      acc.w = 0.0f * w1 + acc.w * invWeight;
+    }
+    p.accum[px] = acc;
+    if (p.rgb8) p.rgb8[px] = rgb8(reinhard_jodie(v3(acc.x, acc.y, acc.z)));
+  }
+  flush_counters(p, cn, primary, in_light);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.counters + 7, 1ull);
+}
+
+__global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ RenderParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DVolume* svol = stage_volumes(p.sc, smem);
+  const int lane = threadIdx.x & 31;
+  const int tiles_x = (p.W + kTileW - 1) / kTileW;
+  const int tiles_y = (p.H + kTileH - 1) / kTileH;
+  const unsigned int ntiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+  const uint32_t npix = (uint32_t)p.W * (uint32_t)p.H;
+  Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
+  for (;;) {
+    unsigned int tile = 0;
+    if (lane == 0) tile = atomicAdd(p.tile_counter, 1u);
+    tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+    if (tile >= ntiles) break;
+    const int ty = (int)(tile / (unsigned int)tiles_x), tx = (int)(tile % (unsigned int)tiles_x);
+    const int x = tx * kTileW + (lane & (kTileW - 1));
+    const int y = ty * kTileH + (lane / kTileW);
+    if (x >= p.W || y >= p.H || !row_selected(p, y)) continue;
+    const uint32_t px = (uint32_t)y * (uint32_t)p.W + (uint32_t)x;
+    uint32_t seed = pixel_seed(px, p.frame0, npix, p.seed);
+    const float rx = rnd(seed) * p.aa;
+    const float ry = rnd(seed) * p.aa;
+    Ray ray = primary_ray(p.cam, (float)x + rx, (float)y + ry, p.W, p.H, seed);
+    NearestOut no; no.cell = 0xFFFFFFFFu; no.face = -1;
+    const int vol = find_nearest<false>(p.sc, svol, ray, cn, &no);
+    VpHit h;
+    h.volume = vol; h.t = ray.t;
+    h.normal[0] = ray.N.x; h.normal[1] = ray.N.y; h.normal[2] = ray.N.z;
+    h.material = (uint8_t)ray.mat; h.inside = (uint8_t)(ray.inside != 0); h.pad = 0;
+    h.cell = vol >= 0 ? no.cell : 0xFFFFFFFFu;
+    h.face = (int8_t)(vol >= 0 ? no.face : -1);
+    p.hits[px] = h;
+  }
+}
+
+struct BatchParams {
+  DScene sc;
+  const VpRay* rays;
+  const uint32_t* seeds;
+  int n;
+  int depth;
+  VpHit* hits;
+  uint8_t* occ;
+  float* rgb;
+};
+
+__global__ void __launch_bounds__(kBlock) k_nearest(const __grid_constant__ BatchParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DVolume* svol = stage_volumes(p.sc, smem);
+  Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+    const VpRay r = p.rays[i];
+    Ray ray; ray.O = ld3(r.o); ray.D = ld3(r.d); ray.N = v3s(0); ray.t = r.t; ray.inside = r.inside != 0; ray.mat = VP_MAT_NONE;
+    NearestOut no; no.cell = 0xFFFFFFFFu; no.face = -1;
+    const int vol = find_nearest<false>(p.sc, svol, ray, cn, &no);
+    VpHit h;
+    h.volume = vol; h.t = ray.t;
+    h.normal[0] = ray.N.x; h.normal[1] = ray.N.y; h.normal[2] = ray.N.z;
+    h.material = (uint8_t)ray.mat; h.inside = (uint8_t)(ray.inside != 0); h.pad = 0;
+    h.cell = vol >= 0 ? no.cell : 0xFFFFFFFFu;
+    h.face = (int8_t)(vol >= 0 ? no.face : -1);
+    p.hits[i] = h;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_occluded(const __grid_constant__ BatchParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DVolume* svol = stage_volumes(p.sc, smem);
+  Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+    const VpRay r = p.rays[i];
+    p.occ[i] = is_occluded_raw<false>(p.sc, svol, ld3(r.o), ld3(r.d), r.t, cn) ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ BatchParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DVolume* svol = stage_volumes(p.sc, smem);
+  Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
+  Level stack[VP_MAX_LEVELS];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+    const VpRay r = p.rays[i];
+    Ray ray; ray.O = ld3(r.o); ray.D = ld3(r.d); ray.N = v3s(0); ray.t = r.t; ray.inside = r.inside != 0; ray.mat = VP_MAT_NONE;
+    uint32_t seed = p.seeds[i];
+    const f3 c = trace_path<false>(p.sc, svol, ray, p.depth, seed, cn, stack, nullptr);
+    p.rgb[3 * i] = c.x; p.rgb[3 * i + 1] = c.y; p.rgb[3 * i + 2] = c.z;
+  }
+}
+
+// ---- occupancy hierarchy build ----------------------------------------------------------
+// one thread per 4x4x4 brick: 16 row reads of 4 bytes (edge bricks of non-multiple-of-4 grids clamp)
+__global__ void k_fine(const uint8_t* __restrict__ grid, uint32_t n, uint32_t nb, unsigned long long* __restrict__ fine)
+{
+  const uint32_t total = nb * nb * nb;
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < total; b += gridDim.x * blockDim.x) {
+    const uint32_t bx = b % nb, by = (b / nb) % nb, bz = b / (nb * nb);
+    unsigned long long m = 0;
+    for (uint32_t z = 0; z < 4; z++)
+      for (uint32_t y = 0; y < 4; y++)
+        for (uint32_t x = 0; x < 4; x++) {
+          const uint32_t X = bx * 4 + x, Y = by * 4 + y, Z = bz * 4 + z;
+          if (X < n && Y < n && Z < n && grid[X + (Y + Z * n) * n] != VP_MAT_NONE) m |= 1ull << (x + 4 * y + 16 * z);
+        }
+    fine[b] = m;
+  }
+}
+// one thread per 16^3 region: OR of its 4x4x4 bricks
+__global__ void k_coarse(const unsigned long long* __restrict__ fine, uint32_t nb, uint32_t nc, uint32_t* __restrict__ coarse)
+{
+  const uint32_t total = nc * nc * nc;
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
+    const uint32_t cx = c % nc, cy = (c / nc) % nc, cz = c / (nc * nc);
+    unsigned long long any = 0;
+    for (uint32_t z = 0; z < 4; z++)
+      for (uint32_t y = 0; y < 4; y++)
+        for (uint32_t x = 0; x < 4; x++) {
+          const uint32_t bx = cx * 4 + x, by = cy * 4 + y, bz = cz * 4 + z;
+          if (bx < nb && by < nb && bz < nb) any |= fine[bx + (by + bz * nb) * nb];
+        }
+    if (any) atomicOr(coarse + (c >> 5), 1u << (c & 31u));
+  }
+}
+
+}  // namespace vp

@@ -61,9 +61,9 @@ class Camera:
 
 
 def frame_params(width, height, max_bounces=14, spp=1, frame_index=0, seed=0x12345678, aa_strength=1.0,
-                 row_begin=0, row_end=0, row_tile=0, row_tile_stride=1, row_tile_phase=0):
+                 row_begin=0, row_end=0, row_tile=0, row_tile_stride=1, row_tile_phase=0, flags=0):
     return abi.VpFrameParams(width, height, max_bounces, spp, frame_index, seed, aa_strength, row_begin, row_end,
-                             row_tile, row_tile_stride, row_tile_phase)
+                             row_tile, row_tile_stride, row_tile_phase, flags)
 
 
 class Session:

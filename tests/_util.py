@@ -1,0 +1,94 @@
+"""Shared test helpers: library loading (product + checkers) and comparison utilities.
+The checkers (oracle/libvporacle.so, oracle/_ref/libvpref.so) are test infrastructure and are
+loaded ONLY from here, from __graft_entry__.smoke() and from bench.py's baseline legs."""
+import ctypes as C
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+vp = importlib.import_module("raytracer-voxpopuli_b200")
+abi = vp.abi
+scenes = importlib.import_module("raytracer-voxpopuli_b200.scenes")
+host = importlib.import_module("raytracer-voxpopuli_b200.host")
+
+ORACLE_SO = os.path.join(ROOT, "oracle", "libvporacle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libvpref.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def oracle_lib():
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ROOT, "oracle", "vp_oracle.c")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libvporacle.so"])
+    lib = abi.Lib(ORACLE_SO, "vpo_")
+    _pin_protos(lib, "vpo_")
+    return lib
+
+
+def ref_lib():
+    """The reference itself (built by oracle/ref/build_ref.py); None when it is not available."""
+    if not os.path.exists(REF_SO):
+        return None
+    lib = abi.Lib(REF_SO, "vpref_")
+    _pin_protos(lib, "vpref_")
+    d = lib.dll
+    d.vpref_load_vox.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    d.vpref_make_transform.argtypes = [C.c_void_p] * 3 + [C.c_uint32] + [C.c_void_p] * 4
+    d.vpref_default_materials.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    return lib
+
+
+def _pin_protos(lib, pre):
+    d = lib.dll
+    getattr(d, pre + "offset_ray").argtypes = [C.c_void_p] * 3
+    getattr(d, pre + "sample_sky").argtypes = [C.c_void_p] * 3
+    getattr(d, pre + "wang_hash").argtypes = [C.c_uint32]
+    getattr(d, pre + "wang_hash").restype = C.c_uint32
+    getattr(d, pre + "rng_floats").argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+    getattr(d, pre + "sampling").argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    getattr(d, pre + "tonemap").argtypes = [C.c_void_p] * 4
+    getattr(d, pre + "threads").restype = C.c_int
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+def hits_equal(a, b):
+    """Field-wise bit comparison of two VpHit arrays; returns {field: mismatch count}."""
+    out = {}
+    for f in a.dtype.names:
+        if f == "pad":
+            continue
+        x, y = a[f], b[f]
+        if x.dtype == np.float32:
+            x, y = x.view(np.uint32), y.view(np.uint32)
+        out[f] = int(np.count_nonzero(x != y))
+    return out
+
+
+def assert_hits_equal(a, b, what=""):
+    mm = hits_equal(a, b)
+    assert all(v == 0 for v in mm.values()), f"{what} hit mismatches: {mm}"
+
+
+def small_config(idx, width, height, **over):
+    sc, cam, fpd = scenes.config(idx, width, height)
+    fpd.update(over)
+    return sc, cam, fpd
+
+
+def params(fpd, **over):
+    d = dict(fpd)
+    d.update(over)
+    return vp.frame_params(d["width"], d["height"], max_bounces=d["max_bounces"], spp=d["spp"],
+                           frame_index=d.get("frame_index", 0), seed=d.get("seed", scenes.SEED),
+                           aa_strength=d["aa_strength"], row_begin=d.get("row_begin", 0), row_end=d.get("row_end", 0),
+                           row_tile=d.get("row_tile", 0), row_tile_stride=d.get("row_tile_stride", 1),
+                           row_tile_phase=d.get("row_tile_phase", 0), flags=d.get("flags", 0))

@@ -1,0 +1,227 @@
+"""CUDA library (through the C ABI) against the oracle on the same seeded inputs, against
+the committed goldens, and - at BASELINE.json's full sizes - through checksums and
+size-independent properties.  Bars (BASELINE.json north_star): primary hit
+{volume, cell, t, normal, material, face} bit-exact; shaded RGB |d| <= 1e-3 per channel;
+accumulated frame relative L2 <= 1e-4.  The implementation folds colours in the reference's
+operation order, so in practice the accumulators are bit-identical; the tests assert the
+stated bars and additionally that (almost) all pixels are bit-identical."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+from _util import GOLDEN, abi, assert_hits_equal, bits, params, scenes, small_config, vp
+
+pytestmark = pytest.mark.gpu
+
+RGB_ABS_TOL = 1e-3      # north_star: shaded RGB within 1e-3 absolute per channel
+ACCUM_REL_L2_TOL = 1e-4  # north_star: relative L2 of accumulated frames
+
+
+def check_accum(a, b, what):
+    d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    rel = np.linalg.norm((a - b).astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-30)
+    nbit = int(np.count_nonzero((bits(a) != bits(b)).any(axis=-1)))
+    npx = a.shape[0] * a.shape[1]
+    print(f"{what}: max|d|={d.max():.3g} relL2={rel:.3g} pixels not bit-identical={nbit}/{npx}")
+    assert d.max() <= RGB_ABS_TOL, f"{what}: max abs diff {d.max()}"
+    assert rel <= ACCUM_REL_L2_TOL, f"{what}: rel L2 {rel}"
+    assert nbit <= max(1, npx // 1000), f"{what}: {nbit} pixels differ bitwise"
+
+
+def hit_digest(hits):
+    h = hashlib.sha256()
+    for f in ("volume", "cell", "t", "normal", "material", "face"):
+        h.update(np.ascontiguousarray(hits[f]).tobytes())
+    return h.hexdigest()
+
+
+CASES = [
+    (1, 160, 90, {}),
+    (1, 160, 90, dict(max_bounces=4, spp=2)),
+    (2, 160, 90, dict(spp=2)),
+    (3, 128, 72, dict(spp=3)),
+    (4, 160, 90, dict(spp=2)),
+    (5, 96, 54, dict(spp=1)),
+]
+
+
+@pytest.mark.parametrize("idx,w,h,over", CASES)
+def test_config_vs_oracle(product, oracle, idx, w, h, over):
+    sc, cam, fpd = small_config(idx, w, h, **over)
+    res = []
+    for lib in (oracle, product):
+        with vp.Session(lib) as s:
+            s.set_scene(sc)
+            hits = s.trace_primary(cam, params(fpd))
+            acc, rgb8, st = s.render(cam, params(fpd, flags=abi.VP_FLAG_COUNT_STEPS))
+            res.append((hits, acc, rgb8, st))
+    assert_hits_equal(res[0][0], res[1][0], f"cfg{idx}")
+    check_accum(res[1][1], res[0][1], f"cfg{idx} accum")
+    assert np.count_nonzero(res[0][2] != res[1][2]) <= max(1, w * h // 1000)
+    a, b = res[0][3], res[1][3]
+    for k in ("primary_rays", "secondary_rays", "shadow_rays", "exit_rays", "dda_steps", "sky_samples"):
+        assert getattr(a, k) == getattr(b, k), (k, getattr(a, k), getattr(b, k))
+    assert b.kernel_launches >= 1
+
+
+@pytest.mark.parametrize("idx", [1, 2, 3, 4, 5])
+def test_config_vs_golden(product, idx):
+    g = np.load(os.path.join(GOLDEN, f"cfg{idx}_64x36.npz"))
+    sc, cam, fpd = small_config(idx, 64, 36)
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        hits = s.trace_primary(cam, params(fpd))
+        acc, rgb8, st = s.render(cam, params(fpd, spp=int(g["spp"])))
+    assert_hits_equal(g["hits"], hits, f"cfg{idx} golden")
+    check_accum(acc, g["accum"], f"cfg{idx} golden accum")
+    assert [st.primary_rays, st.secondary_rays, st.shadow_rays, st.exit_rays] == list(g["stats"][:4])
+
+
+@pytest.mark.parametrize("idx", [1, 2, 3, 4, 5])
+def test_fullres_primary_hits_digest(product, idx):
+    """Bit-exact primary hits at BASELINE.json's full resolutions (checksum of the dump made
+    by the reference build)."""
+    want = json.load(open(os.path.join(GOLDEN, "fullres_hit_digests.json")))[f"cfg{idx}"]
+    sc, cam, fpd = scenes.config(idx)
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        hits = s.trace_primary(cam, params(fpd))
+    assert int((hits["volume"] >= 0).sum()) == want["hit_pixels"]
+    assert hit_digest(hits) == want["sha256"]
+
+
+def test_batch_seams_and_prims(product, oracle):
+    sc, cam, fpd = small_config(4, 64, 36)
+    sc.spheres = [((0.2, 0.6, -0.5), 0.3, 5), ((1.0, 0.4, 0.2), 0.25, 1), ((-0.8, 0.5, 0.1), 0.2, 20)]
+    sc.triangles = [((-0.5, 0, 0), (0, 0.6, 0), (0.5, 0, 0), (0.4, 0.1, -0.9), 7), ((-1, 0, 0), (0, 1, 0), (1, 0, 0), (0.0, 0.2, 3.5), 30)]
+    rng = np.random.default_rng(3)
+    n = 50000
+    o = rng.uniform(-2.5, 3.0, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    rays = vp.make_rays(o, d)
+    rays["t"][::3] = rng.uniform(0.2, 3.0, rays["t"][::3].shape).astype(np.float32)
+    seeds = rng.integers(1, 2 ** 32 - 1, n, dtype=np.uint64).astype(np.uint32)
+    res = []
+    for lib in (oracle, product):
+        with vp.Session(lib) as s:
+            s.set_scene(sc)
+            res.append((s.find_nearest(rays), s.is_occluded(rays), s.trace(rays, seeds, 6)))
+    assert_hits_equal(res[0][0], res[1][0], "find_nearest")
+    assert np.array_equal(res[0][1], res[1][1])
+    assert np.abs(res[0][2] - res[1][2]).max() <= RGB_ABS_TOL
+    assert np.count_nonzero((bits(res[0][2]) != bits(res[1][2])).any(axis=1)) <= n // 1000
+
+
+def test_edge_cases(product, oracle):
+    """Empty volume list, empty grid, 1^3 volumes (the reference's scaled single-voxel
+    platforms, renderer.cpp:482-530), ragged resolution, rays starting inside solids,
+    axis-aligned rays (NaN tmax path), zero spp."""
+    full = np.zeros(1, np.uint8)  # NON_METAL_WHITE
+    M, iM, a, b = __import__("_util").host.make_transform((0, 0, 1), (0, 0.4, 0), (3.0, 0.5, 2.0))
+    one = vp.Volume(full, 1, a, b, M, iM)
+    M2, iM2, a2, b2 = __import__("_util").host.make_transform((-1, 0, 0))
+    empty = vp.Volume(np.full(8 ** 3, 255, np.uint8), 8, a2, b2, M2, iM2)
+    g7 = np.full(7 ** 3, 255, np.uint8)
+    g7[::5] = 17
+    M3, iM3, a3, b3 = __import__("_util").host.make_transform((1, 0, 0))
+    odd = vp.Volume(g7, 7, a3, b3, M3, iM3)
+    mats = __import__("_util").host.default_materials()
+    for vols in ([], [empty], [one], [one, empty, odd]):
+        sc = vp.SceneDesc(volumes=vols, materials=mats, point_lights=[((0.5, 3.0, 0.0), (5, 5, 5))])
+        cam = __import__("_util").host.look_at((0.5, 1.2, -2.0), (0.5, 0.2, 1.2), 61, 37)
+        fp = vp.frame_params(61, 37, max_bounces=5, spp=2)
+        res = []
+        for lib in (oracle, product):
+            with vp.Session(lib) as s:
+                s.set_scene(sc)
+                rays = vp.make_rays([[0.5, 0.5, 1.5], [0.5, 2.0, 1.5], [0.25, 0.5, -1.0], [1.2, 0.3, 0.3]],
+                                    [[0, -1, 0], [0, -1, 0], [0, 0, 1], [1, 0, 0]])
+                res.append((s.trace_primary(cam, fp), s.render(cam, fp)[0], s.find_nearest(rays), s.is_occluded(rays)))
+        assert_hits_equal(res[0][0], res[1][0], f"{len(vols)} volumes")
+        check_accum(res[1][1], res[0][1], f"{len(vols)} volumes")
+        assert_hits_equal(res[0][2], res[1][2], "axis rays")
+        assert np.array_equal(res[0][3], res[1][3])
+    with vp.Session(product) as s:
+        s.set_scene(vp.SceneDesc(volumes=[one], materials=mats))
+        acc = np.full((37, 61, 4), 0.5, np.float32)
+        out, _, st = s.render(cam, vp.frame_params(61, 37, spp=0), accum=acc.copy())
+        assert np.array_equal(out, acc) and st.primary_rays == 0
+
+
+def test_properties_fullsize(product):
+    """Size-independent properties at full resolution (cfg2, 1920x1080):
+    - tile sharding: rendering interleaved row tiles in separate calls == one call (image independent of #GPUs);
+    - spp splitting: 2 passes in one call == 2 calls with frame_index advanced (running average is sequential);
+    - host-buffer call == device-resident call; trace_primary is idempotent."""
+    sc, cam, fpd = scenes.config(2)
+    W, H = fpd["width"], fpd["height"]
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        whole, rgb_whole, st = s.render(cam, params(fpd, spp=2))
+        parts = np.zeros_like(whole)
+        for phase in range(4):
+            parts, _, _ = s.render(cam, params(fpd, spp=2, row_tile=8, row_tile_stride=4, row_tile_phase=phase), accum=parts)
+        assert np.array_equal(bits(whole), bits(parts))
+        seq, _, _ = s.render(cam, params(fpd, spp=1))
+        seq, rgb_seq, _ = s.render(cam, params(fpd, spp=1, frame_index=1), accum=seq)
+        assert np.array_equal(bits(whole), bits(seq)) and np.array_equal(rgb_whole, rgb_seq)
+        L = product
+        L.check(L.c_accum_reset(s.ctx, W, H), "accum_reset")
+        cc, fp = cam.to_c(), params(fpd, spp=2)
+        st2 = abi.VpStats()
+        L.check(L.c_render_resident(s.ctx, C.byref(cc), C.byref(fp), C.byref(st2)), "render_resident")
+        res = np.zeros_like(whole)
+        rgb = np.zeros((H, W), np.uint32)
+        L.check(L.c_accum_download(s.ctx, res.ctypes.data, rgb.ctypes.data), "accum_download")
+        assert np.array_equal(bits(whole), bits(res)) and np.array_equal(rgb, rgb_whole)
+        assert st2.rays == st.rays and st.rays > W * H
+        h1 = s.trace_primary(cam, params(fpd))
+        h2 = s.trace_primary(cam, params(fpd))
+        assert_hits_equal(h1, h2, "idempotence")
+        assert np.isfinite(whole).all() and (whole[..., :3] >= 0).all()
+
+
+def test_dirty_updates(product, oracle):
+    """vp_update_volume_grid / vp_update_volume_transform (Scene::Set + SetTransform between frames)."""
+    from _util import host
+    sc, cam, fpd = small_config(4, 96, 54)
+    fp = params(fpd, spp=1)
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        v = sc.volumes[4]
+        g = v.grid.copy()
+        g[1000:5000] = 3
+        product.check(product.c_update_volume_grid(s.ctx, 4, 1000, 4000, g[1000:5000].ctypes.data), "update_volume_grid")
+        M, iM, a, b = host.make_transform((-0.75, 0.25, 0.5), (0.1, 0.7, 0.0))
+        product.check(product.c_update_volume_transform(s.ctx, 6, M.ctypes.data, iM.ctypes.data, a.ctypes.data, b.ctypes.data),
+                      "update_volume_transform")
+        got_hits, got = s.trace_primary(cam, fp), s.render(cam, fp)[0]
+    sc.volumes[4].grid = g
+    sc.volumes[6].matrix, sc.volumes[6].inv_matrix, sc.volumes[6].cube_min, sc.volumes[6].cube_max = M, iM, a, b
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        want_hits, want = s.trace_primary(cam, fp), s.render(cam, fp)[0]
+    assert_hits_equal(want_hits, got_hits, "after dirty update")
+    check_accum(got, want, "after dirty update")
+
+
+def test_error_paths(product):
+    with vp.Session(product) as s:
+        sc, cam, fpd = small_config(1, 32, 18)
+        cc = cam.to_c()
+        fp = params(fpd)
+        acc = np.zeros((18, 32, 4), np.float32)
+        assert product.c_render(s.ctx, C.byref(cc), C.byref(fp), acc.ctypes.data, None, None) == abi.VP_ESTATE
+        assert b"vp_set_volumes" in product.c_last_error()
+        s.set_scene(sc)
+        bad = params(fpd, max_bounces=40)
+        assert product.c_render(s.ctx, C.byref(cc), C.byref(bad), acc.ctypes.data, None, None) == abi.VP_EINVAL
+        assert product.c_render(s.ctx, C.byref(cc), C.byref(fp), None, None, None) == abi.VP_EINVAL
+        info = C.create_string_buffer(1024)
+        product.check(product.c_info(s.ctx, info, 1024), "info")
+        meta = json.loads(info.value.decode())
+        assert meta["sm"] == "10.0" and meta["k_render_regs"] > 0
