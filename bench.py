@@ -47,37 +47,49 @@ def frame_params(fpd, **over):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled through NVML during the timed region
+    (same fields as the nvidia-smi clocks line of B200_PROFILING.md)."""
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.005):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
-        self.proc = None
+        self.gpu, self.period, self.stop_flag = gpu_index, period_s, False
+        self.sm, self.reasons, self.max_sm, self.err = [], set(), None, None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-                if self.stop_flag:
-                    break
-        except Exception:
-            pass
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self.stop_flag:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+                time.sleep(self.period)
+        except Exception as e:  # NVML unavailable: report it rather than invent numbers
+            self.err = repr(e)
+
+    def mark(self):
+        """start of the timed region: drop what was sampled before it"""
+        self.sm, self.reasons = [], set()
 
     def finish(self):
         self.stop_flag = True
-        if self.proc:
-            self.proc.terminate()
         self.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+               "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def load_checker():
@@ -134,7 +146,7 @@ def run_reference(args, cfg_idx):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, help="workload (SURVEY.md 8d); 2 = room.vox 1920x1080, the metric's config")
@@ -195,13 +207,14 @@ def main():
     # L2 flush between timed iterations (the frame's working set is far below the 126 MB L2)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize(dev)
 
     lib.check(lib.c_stats_begin(sess.ctx), "stats_begin")
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world > 1:
         dist.barrier()

@@ -101,6 +101,7 @@ typedef struct VpFrameParams {
 } VpFrameParams;
 
 #define VP_FLAG_COUNT_STEPS 1u /* also count DDA cell visits (instrumented kernel variant, slower) */
+#define VP_FLAG_MEGAKERNEL 2u  /* single-kernel path walk instead of the wavefront pipeline (A/B measurement) */
 
 /* Result of one Renderer::FindNearest call (renderer.cpp:946-1018). */
 typedef struct VpHit {

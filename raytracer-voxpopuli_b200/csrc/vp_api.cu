@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "vp_kernels.cuh"
+#include "vp_wavefront.cuh"
 
 using namespace vp;
 
@@ -82,6 +83,13 @@ struct vp_ctx {
   DScene sc{};
   bool have_volumes = false;
   int blocks_per_sm = 0;
+  // wavefront path state (HBM-resident, sized for the largest frame / depth seen)
+  WfState wf{};
+  DevBuf<unsigned char> d_wf;
+  uint32_t wf_cap = 0;
+  int wf_levels = 0, wf_samples = 0;
+  int wf_blocks_extend = 0, wf_blocks_shadow = 0;
+  unsigned long long host_launches = 0;
 };
 
 namespace {
@@ -179,6 +187,78 @@ int grid_blocks(const vp_ctx* c, long long work_warps)
   return (int)(need < full ? need : full);
 }
 
+int wf_reserve(vp_ctx* c, uint32_t cap, int levels, int samples)
+{
+  if (cap <= c->wf_cap && levels <= c->wf_levels && samples <= c->wf_samples && c->d_wf.p) return 0;
+  cap = cap > c->wf_cap ? cap : c->wf_cap;
+  levels = levels > c->wf_levels ? levels : c->wf_levels;
+  samples = samples > c->wf_samples ? samples : c->wf_samples;
+  const size_t f4 = sizeof(float4);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_r0 = take(cap * f4), o_r1 = take(cap * f4), o_h0 = take(cap * f4), o_h1 = take(cap * 4), o_term = take(cap * f4);
+  const size_t o_lm = take((size_t)levels * cap * f4), o_la = take((size_t)levels * cap * f4);
+  const size_t o_sq0 = take(cap * f4), o_sqd = take((size_t)samples * cap * f4), o_sql = take((size_t)samples * cap * f4);
+  const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_qs = take(cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
+  CU(cudaDeviceSynchronize());
+  CU(c->d_wf.reserve(off));
+  unsigned char* b = c->d_wf.p;
+  WfState& w = c->wf;
+  w.cap = cap;
+  w.r0 = (float4*)(b + o_r0); w.r1 = (float4*)(b + o_r1); w.h0 = (float4*)(b + o_h0); w.h1 = (uint32_t*)(b + o_h1);
+  w.term = (float4*)(b + o_term); w.lm = (float4*)(b + o_lm); w.la = (float4*)(b + o_la);
+  w.sq0 = (float4*)(b + o_sq0); w.sqd = (float4*)(b + o_sqd); w.sql = (float4*)(b + o_sql);
+  w.q[0] = (uint32_t*)(b + o_q0); w.q[1] = (uint32_t*)(b + o_q1); w.qs = (uint32_t*)(b + o_qs); w.counts = (uint32_t*)(b + o_cnt);
+  c->wf_cap = cap; c->wf_levels = levels; c->wf_samples = samples;
+  return 0;
+}
+
+// wavefront formulation: per pass  generate -> (extend, shade, shadow) x (max_bounces + 1) -> resolve
+template <bool CS>
+int launch_wavefront_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
+{
+  const size_t sm = smem_bytes(c);
+  CU(cudaMemsetAsync(p.st.counts, 0, (size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t), stream));
+  const int wide = c->sm_count * 8;
+  k_wf_generate<<<wide, kWfBlock, 0, stream>>>(p);
+  c->host_launches++;
+  for (int it = 0; it <= p.max_bounces; it++) {
+    p.iter = it;
+    k_wf_extend<CS><<<c->wf_blocks_extend, kWfBlock, sm, stream>>>(p);
+    k_wf_shade<CS><<<wide, kWfBlock, sm, stream>>>(p);
+    k_wf_shadow<CS><<<c->wf_blocks_shadow, kWfBlock, sm, stream>>>(p);
+    c->host_launches += 3;
+  }
+  k_wf_resolve<<<wide, kWfBlock, 0, stream>>>(p);
+  c->host_launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream)
+{
+  const uint32_t tiles = (uint32_t)((fp->width + 7) / 8) * (uint32_t)((fp->height + 3) / 4);
+  const int levels = fp->max_bounces + 1 > 1 ? fp->max_bounces + 1 : 1;
+  const int samples = c->sc.area_samples > 1 ? c->sc.area_samples : 1;
+  if (int rc = wf_reserve(c, tiles * 32u, levels, samples)) return rc;
+  WfParams p;
+  p.sc = c->sc; p.cam = *cam; p.st = c->wf;
+  p.st.cap = tiles * 32u;  // paths of this frame (strides use the frame's own cap)
+  p.W = fp->width; p.H = fp->height; p.max_bounces = fp->max_bounces;
+  p.seed = fp->seed; p.aa = fp->aa_strength;
+  p.row_begin = fp->row_begin; p.row_end = fp->row_end;
+  if (p.row_begin == 0 && p.row_end == 0) p.row_end = fp->height;
+  p.row_tile = fp->row_tile; p.row_tile_stride = fp->row_tile_stride; p.row_tile_phase = fp->row_tile_phase;
+  p.accum = accum; p.rgb8 = rgb8; p.counters = c->d_counters.p; p.iter = 0;
+  for (int s = 0; s < fp->spp; s++) {
+    p.frame = fp->frame_index + (uint32_t)s;
+    p.write_rgb8 = (s == fp->spp - 1);
+    const int rc = (fp->flags & VP_FLAG_COUNT_STEPS) ? launch_wavefront_pass<true>(c, p, stream) : launch_wavefront_pass<false>(c, p, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 // core: enqueue the render kernel on `stream` for device buffers
 int launch_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream,
                   VpStats* stats)
@@ -194,9 +274,16 @@ int launch_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float
   CU(cudaMemsetAsync(c->d_counters.p + 8, 0, sizeof(unsigned long long), stream));
   const long long tiles = (long long)((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
   const int blocks = grid_blocks(c, tiles);
+  const unsigned long long launches_before = c->host_launches;
   if (stats) CU(cudaEventRecord(c->ev0, stream));
-  if (fp->flags & VP_FLAG_COUNT_STEPS) k_render<true><<<blocks, kBlock, smem_bytes(c), stream>>>(p);
-  else k_render<false><<<blocks, kBlock, smem_bytes(c), stream>>>(p);
+  const bool mega = (fp->flags & VP_FLAG_MEGAKERNEL) || c->sc.area_samples > kMaxAreaSamples || fp->max_bounces < 0;
+  if (!mega) {
+    if (int rc = launch_wavefront(c, cam, fp, accum, rgb8, stream)) return rc;
+  } else {
+    if (fp->flags & VP_FLAG_COUNT_STEPS) k_render<true><<<blocks, kBlock, smem_bytes(c), stream>>>(p);
+    else k_render<false><<<blocks, kBlock, smem_bytes(c), stream>>>(p);
+    c->host_launches++;
+  }
   CU(cudaGetLastError());
   if (stats) {
     CU(cudaEventRecord(c->ev1, stream));
@@ -213,7 +300,7 @@ int launch_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float
     stats->dda_steps = h[3];
     stats->sky_samples = h[6];
     stats->device_ms = ms;
-    stats->kernel_launches = h[7];
+    stats->kernel_launches = c->host_launches - launches_before;
   }
   return 0;
 }
@@ -268,6 +355,16 @@ vp_ctx* vp_create(int device)
   cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render<false>, kBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
   c->blocks_per_sm = occ;
+  cudaFuncSetAttribute(k_wf_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_extend<false>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
+  c->wf_blocks_extend = occ * c->sm_count;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shadow<false>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
+  c->wf_blocks_shadow = occ * c->sm_count;
   return c;
 }
 
@@ -278,6 +375,7 @@ void vp_destroy(vp_ctx* c)
   for (auto& v : c->vols) free_volume(v);
   c->d_vols.release(); c->d_mat.release(); c->d_pl.release(); c->d_al.release(); c->d_sl.release();
   c->d_sph.release(); c->d_tri.release(); c->d_sky.release(); c->d_counters.release(); c->d_accum.release();
+  c->d_wf.release();
   c->d_rgb8.release(); c->d_scratch_in.release(); c->d_scratch_out.release(); c->d_scratch_aux.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -533,6 +631,7 @@ int vp_stats_begin(vp_ctx* c)
   if (bind(c)) return VP_ECUDA;
   CU(cudaDeviceSynchronize());
   CU(cudaMemset(c->d_counters.p, 0, 8 * sizeof(unsigned long long)));
+  c->host_launches = 0;
   return 0;
 }
 
@@ -550,7 +649,7 @@ int vp_stats_end(vp_ctx* c, VpStats* stats)
   stats->dda_steps = h[3];
   stats->sky_samples = h[6];
   stats->device_ms = 0;
-  stats->kernel_launches = h[7];
+  stats->kernel_launches = c->host_launches;
   return 0;
 }
 

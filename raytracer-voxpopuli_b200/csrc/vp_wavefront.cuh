@@ -1,0 +1,601 @@
+// vp_wavefront.cuh - wavefront formulation of Renderer::Update for sm_100a.
+//
+// The single-kernel walk (vp_kernels.cuh k_render) keeps 5.8 of 32 lanes busy on room.vox
+// (ncu, profiles/r1a_*): path lengths (1..15 segments), DDA trip counts, material branches
+// and the optional shadow ray all diverge inside one warp.  Here every pixel-sample is a
+// "path" whose state lives in HBM (SoA, 128-bit records) and each stage is its own kernel:
+//
+//   K1 wf_generate : seed, AA jitter, primary ray                     (1 lane per path)
+//   K2 wf_extend   : Renderer::FindNearest over all volumes            (persistent warps, lane refill)
+//   K3 wf_shade    : material switch, RNG, next ray, light sample      (1 lane per active path)
+//   K4 wf_shadow   : Renderer::IsOccluded for the light samples        (persistent warps, lane refill)
+//   K6 wf_resolve  : exact back-to-front colour fold, accumulate, tonemap, RGB8
+//
+// K2/K4 are the hot loops: a warp keeps all lanes inside the DDA stepping loop and, when
+// fewer than kRefill lanes are still walking, idle lanes pull the next ray from the stage
+// queue (one warp-aggregated atomicAdd) instead of waiting for the slowest lane.
+// Queues are plain arrays of path ids appended with ballot/popc warp aggregation.
+// The arithmetic of every stage is the same device code the single-kernel path uses
+// (vp_device.cuh), so results are bit-identical between the two formulations.
+#pragma once
+#include "vp_device.cuh"
+
+namespace vp {
+
+constexpr int kWfBlock = 128;
+constexpr int kRefill = 22;           // refill when fewer lanes than this are still stepping
+constexpr int kMaxAreaSamples = 8;    // numCheckShadowsAreaLight supported by the wavefront path (reference default 3)
+
+// Per-path state, structure of arrays over `cap` paths.
+struct WfState {
+  uint32_t cap;
+  float4* r0;    // O.xyz, w = bits: inside(1) | depth+1 (8 bits << 8) | top (8 bits << 16)
+  float4* r1;    // D.xyz (normalised), w = RNG state bits
+  float4* h0;    // hit: t, N.xyz
+  uint32_t* h1;  // hit: mat (8) | (vol + 2) << 8
+  float4* term;  // terminal radiance (sky / emissive / 0)
+  float4* lm;    // [level][path]: M.xyz, w = type bits
+  float4* la;    // [level][path]: A.xyz
+  float4* sq0;   // shadow request: origin.xyz, w = bits nsamp(8) | level(8) << 8 | area(1) << 16 | mat(8) << 24
+  float4* sqd;   // [sample][path]: dir.xyz, w = dist
+  float4* sql;   // [sample][path]: li.xyz (single lights: final contribution), w = valid
+  uint32_t* q[2];       // active-path queues (ping-pong)
+  uint32_t* qs;         // shadow-request queue
+  uint32_t* counts;     // [iter][4]: 0 = active count entering iter, 1 = shadow count of iter, 2 = extend cursor, 3 = shadow cursor
+};
+
+struct WfParams {
+  DScene sc;
+  VpCamera cam;
+  WfState st;
+  int W, H;
+  int max_bounces;
+  uint32_t frame;
+  uint32_t seed;
+  float aa;
+  int row_begin, row_end, row_tile, row_tile_stride, row_tile_phase;
+  int iter;              // bounce iteration of this launch
+  int write_rgb8;
+  float4* accum;
+  uint32_t* rgb8;
+  unsigned long long* counters;  // same slots as RenderParams
+};
+
+__device__ __forceinline__ bool wf_row_selected(const WfParams& p, int y)
+{
+  if (y < p.row_begin || y >= p.row_end) return false;
+  if (p.row_tile > 0 && ((y / p.row_tile) % p.row_tile_stride) != p.row_tile_phase) return false;
+  return true;
+}
+// path id <-> pixel: 8x4 tiles in row-major tile order, lane = position inside the tile
+__device__ __forceinline__ bool wf_pixel_of(const WfParams& p, uint32_t path, int& x, int& y)
+{
+  const uint32_t tiles_x = (uint32_t)(p.W + 7) / 8u;
+  const uint32_t tile = path >> 5, lane = path & 31u;
+  x = (int)((tile % tiles_x) * 8u + (lane & 7u));
+  y = (int)((tile / tiles_x) * 4u + (lane >> 3));
+  return x < p.W && y < p.H && wf_row_selected(p, y);
+}
+__device__ __forceinline__ const DVolume* wf_stage_volumes(const DScene& sc, unsigned char* smem)
+{
+  DVolume* sv = reinterpret_cast<DVolume*>(smem);
+  const int words = sc.nvol * (int)(sizeof(DVolume) / 4);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(sc.vol);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(sv);
+  for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+  __syncthreads();
+  return sv;
+}
+// warp-aggregated append of one id per participating lane
+__device__ __forceinline__ void wf_push(uint32_t* queue, uint32_t* counter, bool want, uint32_t id)
+{
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
+  if (!m) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  if (want) queue[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = id;
+}
+__device__ __forceinline__ void wf_add_counter(unsigned long long* slot, unsigned long long v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(slot, v);
+}
+__device__ __forceinline__ uint32_t pack_r0w(int inside, int depth, int top) { return (uint32_t)(inside & 1) | ((uint32_t)((depth + 1) & 0xFF) << 8) | ((uint32_t)(top & 0xFF) << 16); }
+
+// ---- K1: primary rays (Renderer::Update pixel loop head, renderer.cpp:1858-1866) --------------------
+__global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant__ WfParams p)
+{
+  const uint32_t npix = (uint32_t)p.W * (uint32_t)p.H;
+  unsigned long long launched = 0;
+  for (uint32_t path = blockIdx.x * blockDim.x + threadIdx.x; path < p.st.cap; path += gridDim.x * blockDim.x) {
+    int x, y;
+    const bool on = wf_pixel_of(p, path, x, y);
+    bool active = false;
+    if (on) {
+      const uint32_t px = (uint32_t)y * (uint32_t)p.W + (uint32_t)x;
+      uint32_t seed = pixel_seed(px, p.frame, npix, p.seed);
+      const float rx = rnd(seed) * p.aa;
+      const float ry = rnd(seed) * p.aa;
+      const Ray pr = primary_ray(p.cam, (float)x + rx, (float)y + ry, p.W, p.H, seed);
+      p.st.r0[path] = make_float4(pr.O.x, pr.O.y, pr.O.z, __uint_as_float(pack_r0w(0, p.max_bounces, 0)));
+      p.st.r1[path] = make_float4(pr.D.x, pr.D.y, pr.D.z, __uint_as_float(seed));
+      p.st.term[path] = make_float4(0, 0, 0, 0);
+      active = p.max_bounces >= 0;  // Trace(depth < 0) returns before FindNearest, renderer.cpp:1080
+      if (active) launched++;
+    }
+    wf_push(p.st.q[0], p.st.counts + 0, active, path);
+  }
+  wf_add_counter(p.counters + 4, launched);
+}
+
+// ---- K2: extend = Renderer::FindNearest (renderer.cpp:946-1018), persistent warps with lane refill ----
+template <bool CS>
+__global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ WfParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DVolume* svol = wf_stage_volumes(p.sc, smem);
+  const int lane = threadIdx.x & 31;
+  const uint32_t* queue = p.st.q[p.iter & 1];
+  uint32_t* cnt = p.st.counts + 4 * p.iter;
+  const uint32_t n = cnt[0];
+  const int nvol = p.sc.nvol;
+  // lane state
+  bool has_ray = false, in_dda = false, exhausted = false;
+  uint32_t path = 0;
+  f3 O = v3s(0), D = v3s(0);
+  float tbest = 0; f3 nbest = v3s(0); int matbest = VP_MAT_NONE, volbest = -2, inside = 0;
+  int vi = 0;
+  ORay r; r.O = r.D = r.rD = v3s(0); r.neg = 0;
+  DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.X = s.Y = s.Z = 0; s.sx = s.sy = s.sz = 0;
+  Occ o; o.key = 0xFFFFFFFFu; o.m = 0;
+  unsigned long long steps = 0;
+  unsigned int nrays = 0;
+  for (;;) {
+    // 1. refill idle lanes from the queue
+    const bool need = !has_ray && !exhausted;
+    const unsigned nm = __ballot_sync(0xFFFFFFFFu, need);
+    if (nm) {
+      const int leader = __ffs(nm) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(cnt + 2, (uint32_t)__popc(nm));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (need) {
+        const uint32_t qi = base + (uint32_t)__popc(nm & ((1u << lane) - 1u));
+        if (qi < n) {
+          path = queue[qi];
+          const float4 a = p.st.r0[path], b = p.st.r1[path];
+          O = v3(a.x, a.y, a.z); D = v3(b.x, b.y, b.z);
+          inside = (int)(__float_as_uint(a.w) & 1u);
+          tbest = 1e34f; nbest = v3s(0); matbest = VP_MAT_NONE; volbest = -2;
+          vi = 0; has_ray = true; in_dda = false;
+          nrays++;
+        } else exhausted = true;
+      }
+    }
+    if (!__any_sync(0xFFFFFFFFu, has_ray)) break;
+    // 2. lanes between volumes: set up the next volume the ray enters, or finish the ray
+    if (has_ray && !in_dda) {
+      while (vi < nvol) {
+        const DVolume& v = svol[vi];
+        r = make_oray(xform_pos_sse(O, v.iM), xform_vec_sse(D, v.iM));
+        vi++;
+        if (setup_dda(v, r, s)) { in_dda = true; o.key = 0xFFFFFFFFu; o.m = 0; break; }
+      }
+      if (!in_dda) {
+        if (p.sc.nsph + p.sc.ntri > 0) {
+          PrimHit h; h.t = 1e34f; h.N = v3s(0); h.mat = VP_MAT_NONE; h.inside = 0;
+          prims_nearest(p.sc, O, normalize3(D), h);
+          if (tbest > h.t) { tbest = h.t; matbest = h.mat; nbest = h.N; inside = h.inside; volbest = -1; }
+        }
+        p.st.h0[path] = make_float4(tbest, nbest.x, nbest.y, nbest.z);
+        p.st.h1[path] = (uint32_t)(matbest & 255) | ((uint32_t)(volbest + 2) << 8) | ((uint32_t)(inside & 1) << 31);
+        has_ray = false;
+      }
+    }
+    // 3. DDA stepping (Scene::FindNearest loop, scene.cpp:763-804) until too few lanes are walking
+    const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)kRefill;  // queue drained: run to completion
+    for (;;) {
+      if (in_dda) {
+        const DVolume& v = svol[vi - 1];
+        if (!(s.t < tbest)) in_dda = false;
+        else {
+          if (CS) steps++;
+          if (occ_test(v, o, s.X, s.Y, s.Z)) {
+            const uint32_t cell = s.X + (s.Y + s.Z * v.n) * v.n;
+            matbest = __ldg(v.grid + cell);
+            tbest = s.t;
+            nbest = normal_voxel(v, r, tbest, nullptr);
+            volbest = vi - 1;
+            in_dda = false;
+          } else if (!dda_step(s, v.n)) in_dda = false;
+        }
+      }
+      if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, in_dda)) < thr) break;
+    }
+  }
+  wf_add_counter(p.counters + 0, nrays);
+  if (CS) wf_add_counter(p.counters + 3, steps);
+}
+
+// ---- K3: shade = the material switch of Renderer::Trace (renderer.cpp:1092-1327) -------------------
+// One lane per path of the iteration's queue.  Emits the next ray, the fold level and, where
+// Illumination() would run, a shadow request (the RNG draws of the light sample happen here, in
+// the reference's order; only the occlusion tests are deferred to K4).
+template <bool CS>
+__device__ __forceinline__ void wf_light_request(const WfParams& p, const DVolume* svol, uint32_t path, int level, const Ray& ray, uint32_t& seed,
+                                                 bool& queued, f3& A_now)
+{
+  const DScene& sc = p.sc;
+  const uint32_t lightCount = (uint32_t)(sc.npl + sc.nsl + sc.nal + 1);
+  const float pick = rnd(seed) * (float)lightCount;
+  const uint32_t idx = (uint32_t)pick;
+  const f3 ip = isect(ray);
+  const f3 n = ray.N;
+  const f3 k = albedo_of(sc, ray.mat);
+  queued = false;
+  A_now = muls(v3s(0), (float)lightCount);
+  const uint32_t cap = p.st.cap;
+  if (idx >= (uint32_t)sc.npl && idx < (uint32_t)(sc.nal + sc.npl)) {
+    const VpAreaLight L = sc.al[idx - sc.npl];
+    const f3 center = ld3(L.position);
+    const float radius = L.radius;
+    const f3 point = offset_ray(ip, n);
+    int nvalid = 0;
+    for (int i = 0; i < sc.area_samples; i++) {
+      f3 rp = random_direction(seed);
+      rp = muls(rp, radius);
+      rp = add(rp, center);
+      const f3 dir = sub(rp, ip);
+      const float dst = sqrtf(dot3(dir, dir));
+      const f3 dn = muls(dir, 1 / dst);
+      const float ct = dot3(dn, n);
+      f3 li = muls(ld3(L.color), ct);
+      li = muls(li, L.color_multiplier);
+      li = muls(li, radius * radius);
+      li = muls(li, VP_PI);
+      li = muls(li, 4.0f);
+      li = divs(li, dst * dst);
+      const bool valid = !(ct <= 0);
+      nvalid += valid;
+      p.st.sqd[(size_t)i * cap + path] = make_float4(dn.x, dn.y, dn.z, dst);
+      p.st.sql[(size_t)i * cap + path] = make_float4(li.x, li.y, li.z, valid ? 1.0f : 0.0f);
+    }
+    if (nvalid > 0) {
+      p.st.sq0[path] = make_float4(point.x, point.y, point.z,
+                                   __uint_as_float((uint32_t)sc.area_samples | ((uint32_t)level << 8) | (1u << 16) | ((uint32_t)(ray.mat & 255) << 24)));
+      queued = true;
+    } else {
+      // inc = (0 / n) * k * lightCount, as the reference computes it
+      f3 inc = divs(v3s(0), (float)sc.area_samples);
+      inc = mul(inc, k);
+      A_now = muls(inc, (float)lightCount);
+    }
+  } else {
+    f3 dirn, contrib; float tshadow; bool lit;
+    if (idx < (uint32_t)sc.npl) {
+      const VpPointLight L = sc.pl[idx];
+      const f3 dir = sub(ld3(L.position), ip);
+      const float dst = sqrtf(dot3(dir, dir));
+      dirn = muls(dir, 1.0f / dst);
+      const float ct = dot3(dirn, n);
+      lit = !(ct <= 0.0f);
+      contrib = mul(muls(muls(ld3(L.color), stdmax(0.0f, ct)), 1.0f / (dst * dst)), k);
+      tshadow = dst;
+    } else if (idx < (uint32_t)(sc.nal + sc.nsl + sc.npl)) {
+      const VpSpotLight L = sc.sl[idx - sc.nal - sc.npl];
+      const f3 dir = sub(ld3(L.position), ip);
+      const float dst = sqrtf(dot3(dir, dir));
+      dirn = divs(dir, dst);
+      const float ct = dot3(dirn, ld3(L.direction));
+      lit = !(ct <= L.angle);
+      const float alpha = 1.0f - (1.0f - ct) * 1.0f / (1.0f - L.angle);
+      const f3 li = divs(muls(ld3(L.color), stdmax(0.0f, ct)), dst * dst);
+      contrib = muls(mul(li, k), alpha);
+      tshadow = dst;
+    } else {
+      dirn = neg(ld3(sc.dl.direction));
+      const float ct = dot3(dirn, n);
+      lit = !(ct <= 0);
+      contrib = mul(muls(ld3(sc.dl.color), stdmax(0.0f, ct)), k);
+      tshadow = 1e34f;
+    }
+    if (lit) {
+      const f3 org = offset_ray(ip, n);
+      p.st.sq0[path] = make_float4(org.x, org.y, org.z, __uint_as_float(1u | ((uint32_t)level << 8) | ((uint32_t)(ray.mat & 255) << 24)));
+      p.st.sqd[path] = make_float4(dirn.x, dirn.y, dirn.z, tshadow);
+      p.st.sql[path] = make_float4(contrib.x, contrib.y, contrib.z, 1.0f);
+      queued = true;
+    }
+  }
+}
+
+template <bool CS>
+__global__ void __launch_bounds__(kWfBlock) k_wf_shade(const __grid_constant__ WfParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DVolume* svol = wf_stage_volumes(p.sc, smem);
+  const DScene& sc = p.sc;
+  const uint32_t* queue = p.st.q[p.iter & 1];
+  uint32_t* qnext = p.st.q[(p.iter + 1) & 1];
+  uint32_t* cnt = p.st.counts + 4 * p.iter;
+  const uint32_t n = cnt[0];
+  const uint32_t cap = p.st.cap;
+  Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
+  int in_light = 0;
+  const uint32_t nround = (n + 31u) & ~31u;  // whole warps so the aggregated pushes stay convergent
+  for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < nround; qi += gridDim.x * blockDim.x) {
+    bool cont = false, want_shadow = false;
+    uint32_t path = 0;
+    if (qi < n) {
+      path = queue[qi];
+      const float4 a = p.st.r0[path], b = p.st.r1[path], h = p.st.h0[path];
+      const uint32_t hb = p.st.h1[path], rb = __float_as_uint(a.w);
+      Ray ray;
+      ray.O = v3(a.x, a.y, a.z); ray.D = v3(b.x, b.y, b.z);
+      ray.t = h.x; ray.N = v3(h.y, h.z, h.w);
+      ray.mat = (int)(hb & 255u);
+      ray.inside = (int)(hb >> 31);  // FindNearest may overwrite isInsideGlass on a sphere hit (renderer.cpp:1012)
+      const int voxIndex = (int)((hb >> 8) & 0x7FFFFFu) - 2;
+      uint32_t seed = __float_as_uint(b.w);
+      int depth = (int)((rb >> 8) & 0xFFu) - 1;
+      int top = (int)((rb >> 16) & 0xFFu);
+      const int m = ray.mat;
+      if (m == VP_MAT_NONE) {
+        cn.sky++;
+        const f3 t = sample_sky(sc, ray.D);
+        p.st.term[path] = make_float4(t.x, t.y, t.z, 0);
+      } else if (m == 15) {
+        const f3 t = muls(albedo_of(sc, m), sc.mat[m].emissive);
+        p.st.term[path] = make_float4(t.x, t.y, t.z, 0);
+      } else {
+        Level L; L.pad = 0; L.ax = L.ay = L.az = 0;
+        Ray nr;
+        bool illum = false;
+        if (m >= 5 && m <= 7) {
+          const f3 refl = reflect3(ray.D, ray.N);
+          const float rough = sc.mat[m].roughness;
+          nr = spawn(offset_ray(isect(ray), ray.N), add(refl, muls(random_sphere_sample(seed), rough)), 0);
+          const f3 al = albedo_of(sc, m);
+          L.type = 0; L.mx = al.x; L.my = al.y; L.mz = al.z;
+        } else if (m <= 4) {
+          if (rnd(seed) > schlick_nonmetal(dot3(neg(ray.D), ray.N))) {
+            const f3 rdir = add(ray.N, random_sphere_sample(seed));
+            illum = true;
+            nr = spawn(offset_ray(isect(ray), ray.N), rdir, 0);
+            const f3 al = albedo_of(sc, m);
+            L.type = 1; L.mx = al.x; L.my = al.y; L.mz = al.z;
+          } else {
+            const f3 refl = reflect3(ray.D, ray.N);
+            const float rough = sc.mat[m].roughness;
+            nr = spawn(offset_ray(isect(ray), ray.N), add(refl, muls(random_sphere_sample(seed), rough)), 0);
+            L.type = 3; L.mx = L.my = L.mz = 1.0f;
+          }
+        } else if (m == 8) {
+          f3 color = v3s(1.0f);
+          int inGlass = ray.inside;
+          const float ior = sc.mat[m].ior;
+          const float ratio = inGlass ? ior : 1.0f / ior;
+          bool insideVolume = true;
+          if (inGlass) {
+            color = albedo_of(sc, m);
+            if (voxIndex >= 0) insideVolume = medium_exit<CS>(svol[voxIndex], ray, 0, cn);
+          }
+          if (!insideVolume) { ray.O = add(ray.O, muls(ray.D, ray.t)); ray.t = 0; }
+          const float ct = stdmin(dot3(neg(ray.D), ray.N), 1.0f);
+          const float st = sqrtf(1.0f - ct * ct);
+          const bool cannot = ratio * st > 1.0f;
+          f3 rdir, rn;
+          if (cannot || schlick(ct, ratio) > rnd(seed)) { rdir = reflect3(ray.D, ray.N); rn = ray.N; }
+          else { rdir = refract3(ray.D, ray.N, ratio); inGlass = !inGlass; rn = neg(ray.N); }
+          nr = spawn(offset_ray(isect(ray), rn), rdir, inGlass);
+          L.type = 0; L.mx = color.x; L.my = color.y; L.mz = color.z;
+        } else if (m >= 9 && m <= 14) {
+          f3 color = v3s(1.0f);
+          int inGlass = ray.inside;
+          bool insideVolume = true;
+          float intensity = 0, dist = 0;
+          if (voxIndex == 0) {  // player-volume side channel: evaluated in place (rare), result only feeds inLight
+            const f3 inc = illumination<CS>(sc, svol, ray, seed, cn);
+            if (dot3(inc, inc) > 16.0f) in_light = 1;
+          }
+          if (inGlass) {
+            intensity = sc.mat[m].emissive;
+            color = albedo_of(sc, m);
+            if (voxIndex >= 0) insideVolume = medium_exit<CS>(svol[voxIndex], ray, 1, cn);
+            dist = ray.t;
+          }
+          const float threshold = rnd(seed) * 100 - intensity;
+          if (rnd(seed) * dist > threshold) {
+            const float lo = ray.t * .45f;
+            const float rr = lo + rnd(seed) * (ray.t - lo);
+            ray.O = add(ray.O, muls(ray.D, rr));
+            ray.D = random_direction(seed);
+            ray.t = 0;
+          }
+          color = absorption(color, intensity, dist);
+          if (!insideVolume) { ray.O = add(ray.O, muls(ray.D, ray.t)); ray.t = 0; }
+          const f3 rdir = refract3(ray.D, ray.N, 1.0f);
+          inGlass = !inGlass;
+          nr = spawn(offset_ray(isect(ray), neg(ray.N)), rdir, inGlass);
+          L.type = 0; L.mx = color.x; L.my = color.y; L.mz = color.z;
+        } else {
+          const f3 rdir = diffuse_reflection(seed, ray.N);
+          illum = true;
+          nr = spawn(offset_ray(isect(ray), ray.N), rdir, 0);
+          const f3 al = albedo_of(sc, m);
+          L.type = 2; L.mx = al.x; L.my = al.y; L.mz = al.z;
+        }
+        f3 A = v3s(0);
+        if (illum) wf_light_request<CS>(p, svol, path, top, ray, seed, want_shadow, A);
+        p.st.lm[(size_t)top * cap + path] = make_float4(L.mx, L.my, L.mz, __int_as_float(L.type));
+        p.st.la[(size_t)top * cap + path] = make_float4(A.x, A.y, A.z, 0);
+        top++; depth--;
+        cont = depth >= 0 && top < VP_MAX_LEVELS;  // Trace(depth < 0) returns 0: term stays 0
+        if (cont) {
+          p.st.r0[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, __uint_as_float(pack_r0w(nr.inside, depth, top)));
+          p.st.r1[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, __uint_as_float(seed));
+        } else {
+          p.st.r0[path].w = __uint_as_float(pack_r0w(nr.inside, depth, top));
+        }
+      }
+    }
+    wf_push(qnext, cnt + 4, cont, path);          // counts[iter+1][0]
+    wf_push(p.st.qs, cnt + 1, want_shadow, path);  // counts[iter][1]
+  }
+  wf_add_counter(p.counters + 6, cn.sky);
+  wf_add_counter(p.counters + 2, cn.exitray);
+  wf_add_counter(p.counters + 1, cn.shadow);
+  wf_add_counter(p.counters + 5, (unsigned long long)in_light);
+  if (CS) wf_add_counter(p.counters + 3, cn.steps);
+}
+
+// ---- K4: shadow = Renderer::IsOccluded per light sample (renderer.cpp:209-243), lane refill -------
+template <bool CS>
+__global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ WfParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DVolume* svol = wf_stage_volumes(p.sc, smem);
+  const int lane = threadIdx.x & 31;
+  const DScene& sc = p.sc;
+  uint32_t* cnt = p.st.counts + 4 * p.iter;
+  const uint32_t n = cnt[1];
+  const uint32_t cap = p.st.cap;
+  const int nvol = sc.nvol;
+  const float lightCount = (float)(uint32_t)(sc.npl + sc.nsl + sc.nal + 1);
+  bool has_req = false, has_ray = false, in_dda = false, exhausted = false;
+  uint32_t path = 0, bits = 0;
+  int nsamp = 0, sample = 0, vi = 0;
+  f3 org = v3s(0), D = v3s(0), inc = v3s(0), li = v3s(0);
+  float tmaxray = 0;
+  ORay r; r.O = r.D = r.rD = v3s(0); r.neg = 0;
+  DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.X = s.Y = s.Z = 0; s.sx = s.sy = s.sz = 0;
+  Occ o; o.key = 0xFFFFFFFFu; o.m = 0;
+  unsigned long long steps = 0;
+  unsigned int nrays = 0;
+  for (;;) {
+    const bool need = !has_req && !exhausted;
+    const unsigned nm = __ballot_sync(0xFFFFFFFFu, need);
+    if (nm) {
+      const int leader = __ffs(nm) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(cnt + 3, (uint32_t)__popc(nm));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (need) {
+        const uint32_t qi = base + (uint32_t)__popc(nm & ((1u << lane) - 1u));
+        if (qi < n) {
+          path = p.st.qs[qi];
+          const float4 q0 = p.st.sq0[path];
+          org = v3(q0.x, q0.y, q0.z);
+          bits = __float_as_uint(q0.w);
+          nsamp = (int)(bits & 255u);
+          sample = 0; inc = v3s(0);
+          has_req = true; has_ray = false; in_dda = false;
+        } else exhausted = true;
+      }
+    }
+    if (!__any_sync(0xFFFFFFFFu, has_req)) break;
+    if (has_req && !in_dda) {
+      // finish the previous sample's volume loop / start the next sample
+      for (;;) {
+        if (has_ray) {
+          bool entered = false;
+          while (vi < nvol) {
+            const DVolume& v = svol[vi];
+            r = make_oray(xform_scalar(org, 1.0f, v.iM), xform_scalar(D, 0.0f, v.iM));
+            vi++;
+            if (setup_dda(v, r, s)) { entered = true; o.key = 0xFFFFFFFFu; o.m = 0; break; }
+          }
+          if (entered) { in_dda = true; break; }
+          // all volumes passed unoccluded: analytic primitives, then accept the sample
+          bool occluded = false;
+          if (sc.nsph + sc.ntri > 0) occluded = prims_any(sc, org, D, tmaxray);
+          if (!occluded) inc = (bits & (1u << 16)) ? add(inc, li) : li;
+          has_ray = false;
+          sample++;
+        }
+        // next sample that needs a ray
+        bool found = false;
+        while (sample < nsamp) {
+          const float4 l4 = p.st.sql[(size_t)sample * cap + path];
+          if (l4.w != 0.0f) {
+            const float4 d4 = p.st.sqd[(size_t)sample * cap + path];
+            D = normalize3(v3(d4.x, d4.y, d4.z));  // normalising Ray ctor of the shadow ray
+            tmaxray = d4.w;
+            li = v3(l4.x, l4.y, l4.z);
+            vi = 0; has_ray = true; found = true;
+            nrays++;
+            break;
+          }
+          sample++;
+        }
+        if (!found) {
+          // request complete: write A of the level it belongs to
+          f3 A;
+          if (bits & (1u << 16)) {
+            f3 t = divs(inc, (float)nsamp);
+            t = mul(t, albedo_of(sc, (int)(bits >> 24)));
+            A = muls(t, lightCount);
+          } else A = muls(inc, lightCount);
+          const uint32_t level = (bits >> 8) & 255u;
+          p.st.la[(size_t)level * cap + path] = make_float4(A.x, A.y, A.z, 0);
+          has_req = false;
+          break;
+        }
+      }
+    }
+    const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)kRefill;
+    for (;;) {
+      if (in_dda) {
+        const DVolume& v = svol[vi - 1];
+        if (!(s.t < tmaxray)) in_dda = false;  // this volume does not occlude: continue with the next one
+        else {
+          if (CS) steps++;
+          if (occ_test(v, o, s.X, s.Y, s.Z)) { in_dda = false; has_ray = false; sample++; }  // occluded: sample contributes nothing
+          else if (!dda_step(s, v.n)) in_dda = false;
+        }
+      }
+      if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, in_dda)) < thr) break;
+    }
+  }
+  wf_add_counter(p.counters + 1, nrays);
+  if (CS) wf_add_counter(p.counters + 3, steps);
+}
+
+// ---- K6: resolve = fold the levels in the recursion's order, BlendColor, tonemap, RGB8 ------------
+__global__ void __launch_bounds__(kWfBlock) k_wf_resolve(const __grid_constant__ WfParams p)
+{
+  const uint32_t cap = p.st.cap;
+  for (uint32_t path = blockIdx.x * blockDim.x + threadIdx.x; path < cap; path += gridDim.x * blockDim.x) {
+    int x, y;
+    if (!wf_pixel_of(p, path, x, y)) continue;
+    const uint32_t px = (uint32_t)y * (uint32_t)p.W + (uint32_t)x;
+    const int top = (int)((__float_as_uint(p.st.r0[path].w) >> 16) & 0xFFu);
+    const float4 t4 = p.st.term[path];
+    f3 R = v3(t4.x, t4.y, t4.z);
+    for (int l = top - 1; l >= 0; l--) {
+      const float4 m4 = p.st.lm[(size_t)l * cap + path];
+      const float4 a4 = p.st.la[(size_t)l * cap + path];
+      const int type = __float_as_int(m4.w);
+      const f3 M = v3(m4.x, m4.y, m4.z), A = v3(a4.x, a4.y, a4.z);
+      if (type == 0) R = mul(R, M);
+      else if (type == 1) R = add(add(v3s(0), A), mul(R, M));
+      else if (type == 2) R = mul(add(R, A), M);
+    }
+    float4 acc = p.accum[px];
+    const float weight = 1.0f / ((float)p.frame + 1.0f);
+    const float invWeight = 1.0f - weight;
+    const float w1 = 1.0f - invWeight;
+    acc.x = R.x * w1 + acc.x * invWeight;
+    acc.y = R.y * w1 + acc.y * invWeight;
+    acc.z = R.z * w1 + acc.z * invWeight;
+    acc.w = 0.0f * w1 + acc.w * invWeight;
+    p.accum[px] = acc;
+    if (p.write_rgb8 && p.rgb8) p.rgb8[px] = rgb8(reinhard_jodie(v3(acc.x, acc.y, acc.z)));
+  }
+}
+
+}  // namespace vp

@@ -48,15 +48,18 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("pipeline", ["wavefront", "megakernel"])
 @pytest.mark.parametrize("idx,w,h,over", CASES)
-def test_config_vs_oracle(product, oracle, idx, w, h, over):
+def test_config_vs_oracle(product, oracle, idx, w, h, over, pipeline):
+    """Both formulations of the path (wavefront stages = default, single-kernel walk) against the oracle."""
     sc, cam, fpd = small_config(idx, w, h, **over)
+    flags = abi.VP_FLAG_COUNT_STEPS | (abi.VP_FLAG_MEGAKERNEL if pipeline == "megakernel" else 0)
     res = []
     for lib in (oracle, product):
         with vp.Session(lib) as s:
             s.set_scene(sc)
             hits = s.trace_primary(cam, params(fpd))
-            acc, rgb8, st = s.render(cam, params(fpd, flags=abi.VP_FLAG_COUNT_STEPS))
+            acc, rgb8, st = s.render(cam, params(fpd, flags=flags))
             res.append((hits, acc, rgb8, st))
     assert_hits_equal(res[0][0], res[1][0], f"cfg{idx}")
     check_accum(res[1][1], res[0][1], f"cfg{idx} accum")
