@@ -40,7 +40,7 @@ extern "C" {
  * cube_min/cube_max = Scene::cube.b[0..1].  The library copies everything at upload. */
 typedef struct VpVolume {
   const uint8_t* grid;
-  uint32_t n;            /* gridsize (== worldsize), any value 1..1024 */
+  uint32_t n;            /* gridsize (== worldsize), any value 1..512 (reference template/scene.h:253: "max 512") */
   float cube_min[3];
   float cube_max[3];
   float matrix[16];

@@ -35,11 +35,10 @@ int fail(int code, const char* fmt, ...)
   } while (0)
 
 struct HostVolume {
-  uint32_t n = 0, nb = 0, nc = 0;
+  uint32_t n = 0, jr = 0;
   uint8_t* grid = nullptr;
-  unsigned long long* fine = nullptr;
-  uint32_t* coarse = nullptr;
-  size_t coarse_words = 0;
+  unsigned long long* fine = nullptr;  // 64 << 3*jr brick masks
+  uint32_t region_off = 0;             // offset of this volume's 1 << 3*jr region masks in ctx->d_regions
   DVolume d{};
 };
 
@@ -75,6 +74,8 @@ struct vp_ctx {
   DevBuf<VpSphere> d_sph;
   DevBuf<VpTriangle> d_tri;
   DevBuf<float> d_sky;
+  DevBuf<unsigned long long> d_regions;  // region masks of all volumes, contiguous (staged to shared memory by the kernels)
+  size_t region_words = 0;
   DevBuf<unsigned long long> d_counters;  // 8 counters + tile counter slot
   DevBuf<float4> d_accum;                 // library-owned resident accumulator / staging for vp_render
   DevBuf<uint32_t> d_rgb8;
@@ -104,16 +105,14 @@ void free_volume(HostVolume& v)
 {
   if (v.grid) cudaFree(v.grid);
   if (v.fine) cudaFree(v.fine);
-  if (v.coarse) cudaFree(v.coarse);
   v = HostVolume();
 }
 
 int build_masks(vp_ctx* c, HostVolume& v)
 {
-  const uint32_t nbricks = v.nb * v.nb * v.nb, ncoarse = v.nc * v.nc * v.nc;
-  CU(cudaMemsetAsync(v.coarse, 0, v.coarse_words * sizeof(uint32_t), c->stream));
-  k_fine<<<(nbricks + 127) / 128, 128, 0, c->stream>>>(v.grid, v.n, v.nb, v.fine);
-  k_coarse<<<(ncoarse + 127) / 128, 128, 0, c->stream>>>(v.fine, v.nb, v.nc, v.coarse);
+  const uint32_t nbricks = 64u << (3 * v.jr), nregions = 1u << (3 * v.jr);
+  k_fine<<<(nbricks + 127) / 128, 128, 0, c->stream>>>(v.grid, v.n, v.jr, v.fine);
+  k_region<<<(nregions + 127) / 128, 128, 0, c->stream>>>(v.fine, v.jr, c->d_regions.p + v.region_off);
   CU(cudaGetLastError());
   return 0;
 }
@@ -124,14 +123,17 @@ void fill_dvolume(HostVolume& v, const float* M, const float* iM, const float* b
   memcpy(v.d.M, M, 12 * sizeof(float));
   memcpy(v.d.bmin, bmin, 12);
   memcpy(v.d.bmax, bmax, 12);
-  v.d.n = v.n; v.d.nb = v.nb; v.d.nc = v.nc; v.d.pad = 0;
-  v.d.grid = v.grid; v.d.fine = v.fine; v.d.coarse = v.coarse;
+  v.d.n = v.n; v.d.jr = v.jr; v.d.region_off = v.region_off; v.d.pad = 0;
+  v.d.grid = v.grid; v.d.fine = v.fine; v.d.region = nullptr;  // region pointer patched in upload_volume_table
 }
 
 int upload_volume_table(vp_ctx* c)
 {
   std::vector<DVolume> tab(c->vols.size());
-  for (size_t i = 0; i < c->vols.size(); i++) tab[i] = c->vols[i].d;
+  for (size_t i = 0; i < c->vols.size(); i++) {
+    tab[i] = c->vols[i].d;
+    tab[i].region = c->d_regions.p + c->vols[i].region_off;
+  }
   CU(c->d_vols.reserve(tab.size()));
   if (!tab.empty()) CU(cudaMemcpyAsync(c->d_vols.p, tab.data(), tab.size() * sizeof(DVolume), cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -149,7 +151,7 @@ int upload_array(vp_ctx* c, DevBuf<T>& buf, const T* src, int n)
   return 0;
 }
 
-size_t smem_bytes(const vp_ctx* c) { return (size_t)c->sc.nvol * sizeof(DVolume) + 16; }
+size_t smem_bytes(const vp_ctx* c) { return (size_t)c->sc.nvol * sizeof(DVolume) + 16 + (size_t)c->sc.region_words * 8; }
 
 int check_frame(const vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp)
 {
@@ -196,7 +198,7 @@ int wf_reserve(vp_ctx* c, uint32_t cap, int levels, int samples)
   const size_t f4 = sizeof(float4);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  const size_t o_r0 = take(cap * f4), o_r1 = take(cap * f4), o_h0 = take(cap * f4), o_h1 = take(cap * 4), o_term = take(cap * f4);
+  const size_t o_r0 = take(cap * f4), o_r1 = take(cap * f4), o_h0 = take(cap * 8), o_h1 = take(cap * 4), o_hn = take(cap * f4), o_term = take(cap * f4);
   const size_t o_lm = take((size_t)levels * cap * f4), o_la = take((size_t)levels * cap * f4);
   const size_t o_sq0 = take(cap * f4), o_sqd = take((size_t)samples * cap * f4), o_sql = take((size_t)samples * cap * f4);
   const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_qs = take(cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
@@ -205,7 +207,7 @@ int wf_reserve(vp_ctx* c, uint32_t cap, int levels, int samples)
   unsigned char* b = c->d_wf.p;
   WfState& w = c->wf;
   w.cap = cap;
-  w.r0 = (float4*)(b + o_r0); w.r1 = (float4*)(b + o_r1); w.h0 = (float4*)(b + o_h0); w.h1 = (uint32_t*)(b + o_h1);
+  w.r0 = (float4*)(b + o_r0); w.r1 = (float4*)(b + o_r1); w.h0 = (float2*)(b + o_h0); w.h1 = (uint32_t*)(b + o_h1); w.hn = (float4*)(b + o_hn);
   w.term = (float4*)(b + o_term); w.lm = (float4*)(b + o_lm); w.la = (float4*)(b + o_la);
   w.sq0 = (float4*)(b + o_sq0); w.sqd = (float4*)(b + o_sqd); w.sql = (float4*)(b + o_sql);
   w.q[0] = (uint32_t*)(b + o_q0); w.q[1] = (uint32_t*)(b + o_q1); w.qs = (uint32_t*)(b + o_qs); w.counts = (uint32_t*)(b + o_cnt);
@@ -374,7 +376,7 @@ void vp_destroy(vp_ctx* c)
   cudaSetDevice(c->device);
   for (auto& v : c->vols) free_volume(v);
   c->d_vols.release(); c->d_mat.release(); c->d_pl.release(); c->d_al.release(); c->d_sl.release();
-  c->d_sph.release(); c->d_tri.release(); c->d_sky.release(); c->d_counters.release(); c->d_accum.release();
+  c->d_sph.release(); c->d_tri.release(); c->d_sky.release(); c->d_regions.release(); c->d_counters.release(); c->d_accum.release();
   c->d_wf.release();
   c->d_rgb8.release(); c->d_scratch_in.release(); c->d_scratch_out.release(); c->d_scratch_aux.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -389,21 +391,35 @@ int vp_set_volumes(vp_ctx* c, const VpVolume* vols, int n)
   if ((size_t)n * sizeof(DVolume) + 16 > 64 * 1024) return fail(VP_EINVAL, "too many volumes (%d)", n);
   if (bind(c)) return VP_ECUDA;
   for (int i = 0; i < n; i++)
-    if (!vols[i].grid || vols[i].n == 0 || vols[i].n > 1024) return fail(VP_EINVAL, "volume %d: bad grid pointer or size %u", i, vols[i].n);
+    if (!vols[i].grid || vols[i].n == 0 || vols[i].n > 512) return fail(VP_EINVAL, "volume %d: bad grid pointer or size %u", i, vols[i].n);
   for (auto& v : c->vols) free_volume(v);
   c->vols.assign((size_t)n, HostVolume());
+  size_t rwords = 0;
   for (int i = 0; i < n; i++) {
     HostVolume& v = c->vols[i];
-    v.n = vols[i].n; v.nb = (v.n + 3) / 4; v.nc = (v.n + 15) / 16;
+    v.n = vols[i].n;
+    uint32_t npad = 16;
+    while (npad < v.n) npad <<= 1;
+    v.jr = 0;
+    while ((16u << v.jr) < npad) v.jr++;
+    v.region_off = (uint32_t)rwords;
+    rwords += (size_t)1 << (3 * v.jr);
+  }
+  c->region_words = rwords;
+  CU(c->d_regions.reserve(rwords ? rwords : 1));
+  for (int i = 0; i < n; i++) {
+    HostVolume& v = c->vols[i];
     const size_t bytes = (size_t)v.n * v.n * v.n;
-    v.coarse_words = ((size_t)v.nc * v.nc * v.nc + 31) / 32;
     CU(cudaMalloc(&v.grid, bytes));
-    CU(cudaMalloc(&v.fine, (size_t)v.nb * v.nb * v.nb * sizeof(unsigned long long)));
-    CU(cudaMalloc(&v.coarse, v.coarse_words * sizeof(uint32_t)));
+    CU(cudaMalloc(&v.fine, ((size_t)64 << (3 * v.jr)) * sizeof(unsigned long long)));
     CU(cudaMemcpyAsync(v.grid, vols[i].grid, bytes, cudaMemcpyHostToDevice, c->stream));
     if (build_masks(c, v)) return VP_ECUDA;
     fill_dvolume(v, vols[i].matrix, vols[i].inv_matrix, vols[i].cube_min, vols[i].cube_max);
   }
+  c->sc.regions = c->d_regions.p;
+  // stage the region masks in shared memory when table + masks fit the 64 KB the kernels opt into
+  const size_t budget = 64 * 1024 - 64;
+  c->sc.region_words = ((size_t)n * sizeof(DVolume) + 16 + rwords * 8 <= budget) ? (int)rwords : 0;
   if (upload_volume_table(c)) return VP_ECUDA;
   c->have_volumes = true;
   return 0;

@@ -37,16 +37,22 @@ __device__ __forceinline__ bool row_selected(const RenderParams& p, int y)
   return true;
 }
 
-// stage the volume table into shared memory (read by every ray of the block)
-__device__ __forceinline__ const DVolume* stage_volumes(const DScene& sc, unsigned char* smem)
+// stage the volume table and (when they fit) the region masks into shared memory
+__device__ __forceinline__ Staged stage_scene(const DScene& sc, unsigned char* smem)
 {
   DVolume* sv = reinterpret_cast<DVolume*>(smem);
   const int words = sc.nvol * (int)(sizeof(DVolume) / 4);
   const uint32_t* src = reinterpret_cast<const uint32_t*>(sc.vol);
   uint32_t* dst = reinterpret_cast<uint32_t*>(sv);
   for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+  Staged st; st.vol = sv; st.regions = nullptr;
+  if (sc.region_words > 0) {
+    unsigned long long* rg = reinterpret_cast<unsigned long long*>(smem + (((size_t)words * 4 + 15) & ~(size_t)15));
+    for (int i = threadIdx.x; i < sc.region_words; i += blockDim.x) rg[i] = __ldg(sc.regions + i);
+    st.regions = rg;
+  }
   __syncthreads();
-  return sv;
+  return st;
 }
 
 __device__ __forceinline__ void flush_counters(const RenderParams& p, const Counters& cn, unsigned int primary, int in_light)
@@ -65,7 +71,7 @@ template <bool kCountSteps>
 __global__ void __launch_bounds__(kBlock) k_render(const __grid_constant__ RenderParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  const DVolume* svol = stage_volumes(p.sc, smem);
+  const Staged svol = stage_scene(p.sc, smem);
   const int lane = threadIdx.x & 31;
   const int tiles_x = (p.W + kTileW - 1) / kTileW;
   const int tiles_y = (p.H + kTileH - 1) / kTileH;
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(kBlock) k_render(const __grid_constant__ Rende
 __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ RenderParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  const DVolume* svol = stage_volumes(p.sc, smem);
+  const Staged svol = stage_scene(p.sc, smem);
   const int lane = threadIdx.x & 31;
   const int tiles_x = (p.W + kTileW - 1) / kTileW;
   const int tiles_y = (p.H + kTileH - 1) / kTileH;
@@ -160,7 +166,7 @@ struct BatchParams {
 __global__ void __launch_bounds__(kBlock) k_nearest(const __grid_constant__ BatchParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  const DVolume* svol = stage_volumes(p.sc, smem);
+  const Staged svol = stage_scene(p.sc, smem);
   Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
     const VpRay r = p.rays[i];
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(kBlock) k_nearest(const __grid_constant__ Batc
 __global__ void __launch_bounds__(kBlock) k_occluded(const __grid_constant__ BatchParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  const DVolume* svol = stage_volumes(p.sc, smem);
+  const Staged svol = stage_scene(p.sc, smem);
   Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
     const VpRay r = p.rays[i];
@@ -191,7 +197,7 @@ __global__ void __launch_bounds__(kBlock) k_occluded(const __grid_constant__ Bat
 __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ BatchParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  const DVolume* svol = stage_volumes(p.sc, smem);
+  const Staged svol = stage_scene(p.sc, smem);
   Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
   Level stack[VP_MAX_LEVELS];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
@@ -204,12 +210,17 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ BatchP
 }
 
 // ---- occupancy hierarchy build ----------------------------------------------------------
-// one thread per 4x4x4 brick: 16 row reads of 4 bytes (edge bricks of non-multiple-of-4 grids clamp)
-__global__ void k_fine(const uint8_t* __restrict__ grid, uint32_t n, uint32_t nb, unsigned long long* __restrict__ fine)
+// one thread per 4x4x4 brick in brick-major order (index = P >> 6, see struct DDA); cells outside
+// the n^3 grid (padding up to the power-of-two domain) read as empty
+__global__ void k_fine(const uint8_t* __restrict__ grid, uint32_t n, uint32_t jr, unsigned long long* __restrict__ fine)
 {
-  const uint32_t total = nb * nb * nb;
+  const uint32_t total = 64u << (3 * jr);
+  const uint32_t rmask = (1u << jr) - 1u;
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < total; b += gridDim.x * blockDim.x) {
-    const uint32_t bx = b % nb, by = (b / nb) % nb, bz = b / (nb * nb);
+    const uint32_t rg = b >> 6;
+    const uint32_t bx = (b & 3u) | ((rg & rmask) << 2);
+    const uint32_t by = ((b >> 2) & 3u) | (((rg >> jr) & rmask) << 2);
+    const uint32_t bz = ((b >> 4) & 3u) | (((rg >> (2 * jr)) & rmask) << 2);
     unsigned long long m = 0;
     for (uint32_t z = 0; z < 4; z++)
       for (uint32_t y = 0; y < 4; y++)
@@ -220,20 +231,15 @@ __global__ void k_fine(const uint8_t* __restrict__ grid, uint32_t n, uint32_t nb
     fine[b] = m;
   }
 }
-// one thread per 16^3 region: OR of its 4x4x4 bricks
-__global__ void k_coarse(const unsigned long long* __restrict__ fine, uint32_t nb, uint32_t nc, uint32_t* __restrict__ coarse)
+// one thread per 16^3 region: bit j <=> brick (region << 6 | j) holds a voxel
+__global__ void k_region(const unsigned long long* __restrict__ fine, uint32_t jr, unsigned long long* __restrict__ region)
 {
-  const uint32_t total = nc * nc * nc;
-  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
-    const uint32_t cx = c % nc, cy = (c / nc) % nc, cz = c / (nc * nc);
-    unsigned long long any = 0;
-    for (uint32_t z = 0; z < 4; z++)
-      for (uint32_t y = 0; y < 4; y++)
-        for (uint32_t x = 0; x < 4; x++) {
-          const uint32_t bx = cx * 4 + x, by = cy * 4 + y, bz = cz * 4 + z;
-          if (bx < nb && by < nb && bz < nb) any |= fine[bx + (by + bz * nb) * nb];
-        }
-    if (any) atomicOr(coarse + (c >> 5), 1u << (c & 31u));
+  const uint32_t total = 1u << (3 * jr);
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < total; r += gridDim.x * blockDim.x) {
+    unsigned long long m = 0;
+    for (uint32_t j = 0; j < 64; j++)
+      if (fine[(r << 6) | j]) m |= 1ull << j;
+    region[r] = m;
   }
 }
 

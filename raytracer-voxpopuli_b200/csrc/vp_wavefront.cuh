@@ -31,8 +31,9 @@ struct WfState {
   uint32_t cap;
   float4* r0;    // O.xyz, w = bits: inside(1) | depth+1 (8 bits << 8) | top (8 bits << 16)
   float4* r1;    // D.xyz (normalised), w = RNG state bits
-  float4* h0;    // hit: t, N.xyz
-  uint32_t* h1;  // hit: mat (8) | (vol + 2) << 8
+  float2* h0;    // hit: t, P bits (cell of the hit inside volume `vol`, brick-major)
+  uint32_t* h1;  // hit: (vol + 2) << 8; primitive hits: mat (8) | 1 << 8 | inside << 30 | 1 << 31
+  float4* hn;    // primitive hits only: normal
   float4* term;  // terminal radiance (sky / emissive / 0)
   float4* lm;    // [level][path]: M.xyz, w = type bits
   float4* la;    // [level][path]: A.xyz
@@ -76,15 +77,21 @@ __device__ __forceinline__ bool wf_pixel_of(const WfParams& p, uint32_t path, in
   y = (int)((tile / tiles_x) * 4u + (lane >> 3));
   return x < p.W && y < p.H && wf_row_selected(p, y);
 }
-__device__ __forceinline__ const DVolume* wf_stage_volumes(const DScene& sc, unsigned char* smem)
+__device__ __forceinline__ Staged wf_stage_scene(const DScene& sc, unsigned char* smem)
 {
   DVolume* sv = reinterpret_cast<DVolume*>(smem);
   const int words = sc.nvol * (int)(sizeof(DVolume) / 4);
   const uint32_t* src = reinterpret_cast<const uint32_t*>(sc.vol);
   uint32_t* dst = reinterpret_cast<uint32_t*>(sv);
   for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+  Staged st; st.vol = sv; st.regions = nullptr;
+  if (sc.region_words > 0) {
+    unsigned long long* rg = reinterpret_cast<unsigned long long*>(smem + (((size_t)words * 4 + 15) & ~(size_t)15));
+    for (int i = threadIdx.x; i < sc.region_words; i += blockDim.x) rg[i] = __ldg(sc.regions + i);
+    st.regions = rg;
+  }
   __syncthreads();
-  return sv;
+  return st;
 }
 // warp-aggregated append of one id per participating lane
 __device__ __forceinline__ void wf_push(uint32_t* queue, uint32_t* counter, bool want, uint32_t id)
@@ -133,25 +140,29 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant_
 }
 
 // ---- K2: extend = Renderer::FindNearest (renderer.cpp:946-1018), persistent warps with lane refill ----
+// Writes per path: t, the winning volume and the hit cell (as P).  The face normal and the
+// material byte are produced by the shade stage where all 32 lanes are busy, not here where
+// a hit is a single-lane event inside the stepping loop.
 template <bool CS>
 __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  const DVolume* svol = wf_stage_volumes(p.sc, smem);
+  const Staged stg = wf_stage_scene(p.sc, smem);
+  const DVolume* svol = stg.vol;
   const int lane = threadIdx.x & 31;
   const uint32_t* queue = p.st.q[p.iter & 1];
   uint32_t* cnt = p.st.counts + 4 * p.iter;
   const uint32_t n = cnt[0];
   const int nvol = p.sc.nvol;
-  // lane state
   bool has_ray = false, in_dda = false, exhausted = false;
   uint32_t path = 0;
   f3 O = v3s(0), D = v3s(0);
-  float tbest = 0; f3 nbest = v3s(0); int matbest = VP_MAT_NONE, volbest = -2, inside = 0;
+  float tbest = 0; uint32_t pbest = 0; int volbest = -2;
   int vi = 0;
-  ORay r; r.O = r.D = r.rD = v3s(0); r.neg = 0;
-  DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.X = s.Y = s.Z = 0; s.sx = s.sy = s.sz = 0;
-  Occ o; o.key = 0xFFFFFFFFu; o.m = 0;
+  const unsigned long long* region = nullptr;
+  const unsigned long long* fine = nullptr;
+  DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
+  Occ o; occ_reset(o);
   unsigned long long steps = 0;
   unsigned int nrays = 0;
   for (;;) {
@@ -169,8 +180,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
           path = queue[qi];
           const float4 a = p.st.r0[path], b = p.st.r1[path];
           O = v3(a.x, a.y, a.z); D = v3(b.x, b.y, b.z);
-          inside = (int)(__float_as_uint(a.w) & 1u);
-          tbest = 1e34f; nbest = v3s(0); matbest = VP_MAT_NONE; volbest = -2;
+          tbest = 1e34f; pbest = 0; volbest = -2;
           vi = 0; has_ray = true; in_dda = false;
           nrays++;
         } else exhausted = true;
@@ -181,37 +191,45 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
     if (has_ray && !in_dda) {
       while (vi < nvol) {
         const DVolume& v = svol[vi];
-        r = make_oray(xform_pos_sse(O, v.iM), xform_vec_sse(D, v.iM));
+        const ORay r = make_oray(xform_pos_sse(O, v.iM), xform_vec_sse(D, v.iM));
         vi++;
-        if (setup_dda(v, r, s)) { in_dda = true; o.key = 0xFFFFFFFFu; o.m = 0; break; }
+        if (setup_dda(v, r, s)) { in_dda = true; occ_reset(o); region = region_of(stg, v); fine = v.fine; break; }
       }
       if (!in_dda) {
+        uint32_t hb = (uint32_t)(volbest + 2) << 8;
         if (p.sc.nsph + p.sc.ntri > 0) {
           PrimHit h; h.t = 1e34f; h.N = v3s(0); h.mat = VP_MAT_NONE; h.inside = 0;
           prims_nearest(p.sc, O, normalize3(D), h);
-          if (tbest > h.t) { tbest = h.t; matbest = h.mat; nbest = h.N; inside = h.inside; volbest = -1; }
+          if (tbest > h.t) {
+            tbest = h.t;
+            hb = (uint32_t)(h.mat & 255) | (1u << 8) | ((uint32_t)(h.inside & 1) << 30) | (1u << 31);  // vol = -1, bit 31: inside flag valid
+            p.st.hn[path] = make_float4(h.N.x, h.N.y, h.N.z, 0);
+          }
         }
-        p.st.h0[path] = make_float4(tbest, nbest.x, nbest.y, nbest.z);
-        p.st.h1[path] = (uint32_t)(matbest & 255) | ((uint32_t)(volbest + 2) << 8) | ((uint32_t)(inside & 1) << 31);
+        p.st.h0[path] = make_float2(tbest, __uint_as_float(pbest));
+        p.st.h1[path] = hb;
         has_ray = false;
       }
     }
     // 3. DDA stepping (Scene::FindNearest loop, scene.cpp:763-804) until too few lanes are walking
     const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)kRefill;  // queue drained: run to completion
     for (;;) {
-      if (in_dda) {
-        const DVolume& v = svol[vi - 1];
-        if (!(s.t < tbest)) in_dda = false;
-        else {
-          if (CS) steps++;
-          if (occ_test(v, o, s.X, s.Y, s.Z)) {
-            const uint32_t cell = s.X + (s.Y + s.Z * v.n) * v.n;
-            matbest = __ldg(v.grid + cell);
-            tbest = s.t;
-            nbest = normal_voxel(v, r, tbest, nullptr);
-            volbest = vi - 1;
-            in_dda = false;
-          } else if (!dda_step(s, v.n)) in_dda = false;
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (in_dda) {
+          if (!(s.t < tbest)) in_dda = false;
+          else {
+            if (CS) steps++;
+            // occupancy of the current cell (inline occ_test with the lane's cached mask pointers)
+            const uint32_t ch = s.P ^ o.key;
+            if (ch >> 6) {
+              if (ch >> 12) o.rm = region[s.P >> 12];
+              o.key = s.P;
+              o.m = ((o.rm >> ((s.P >> 6) & 63u)) & 1ull) ? __ldg(fine + (s.P >> 6)) : 0ull;
+            }
+            if ((o.m >> (s.P & 63u)) & 1ull) { tbest = s.t; pbest = s.P; volbest = vi - 1; in_dda = false; }
+            else if (!dda_step(s)) in_dda = false;
+          }
         }
       }
       if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, in_dda)) < thr) break;
@@ -226,7 +244,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
 // Illumination() would run, a shadow request (the RNG draws of the light sample happen here, in
 // the reference's order; only the occlusion tests are deferred to K4).
 template <bool CS>
-__device__ __forceinline__ void wf_light_request(const WfParams& p, const DVolume* svol, uint32_t path, int level, const Ray& ray, uint32_t& seed,
+__device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t path, int level, const Ray& ray, uint32_t& seed,
                                                  bool& queued, f3& A_now)
 {
   const DScene& sc = p.sc;
@@ -317,7 +335,8 @@ template <bool CS>
 __global__ void __launch_bounds__(kWfBlock) k_wf_shade(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  const DVolume* svol = wf_stage_volumes(p.sc, smem);
+  const Staged stg = wf_stage_scene(p.sc, smem);
+  const DVolume* svol = stg.vol;
   const DScene& sc = p.sc;
   const uint32_t* queue = p.st.q[p.iter & 1];
   uint32_t* qnext = p.st.q[(p.iter + 1) & 1];
@@ -332,14 +351,26 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shade(const __grid_constant__ W
     uint32_t path = 0;
     if (qi < n) {
       path = queue[qi];
-      const float4 a = p.st.r0[path], b = p.st.r1[path], h = p.st.h0[path];
+      const float4 a = p.st.r0[path], b = p.st.r1[path];
+      const float2 h = p.st.h0[path];
       const uint32_t hb = p.st.h1[path], rb = __float_as_uint(a.w);
       Ray ray;
       ray.O = v3(a.x, a.y, a.z); ray.D = v3(b.x, b.y, b.z);
-      ray.t = h.x; ray.N = v3(h.y, h.z, h.w);
-      ray.mat = (int)(hb & 255u);
-      ray.inside = (int)(hb >> 31);  // FindNearest may overwrite isInsideGlass on a sphere hit (renderer.cpp:1012)
-      const int voxIndex = (int)((hb >> 8) & 0x7FFFFFu) - 2;
+      ray.t = h.x; ray.N = v3s(0); ray.mat = VP_MAT_NONE;
+      ray.inside = (int)(rb & 1u);
+      const int voxIndex = (int)((hb >> 8) & 0x3FFFFFu) - 2;
+      if (voxIndex >= 0) {
+        // finish Scene::FindNearest's hit block here (scene.cpp:766-773): material byte + Ray::GetNormalVoxel
+        const DVolume& v = svol[voxIndex];
+        const f3 oO = xform_pos_sse(ray.O, v.iM), oD = xform_vec_sse(ray.D, v.iM);
+        ray.mat = __ldg(v.grid + cell_of(v, __float_as_uint(h.y)));
+        ray.N = normal_voxel(v, oO, oD, neg_bits(oD), ray.t, nullptr);
+      } else if (voxIndex == -1) {
+        const float4 nn = p.st.hn[path];
+        ray.N = v3(nn.x, nn.y, nn.z);
+        ray.mat = (int)(hb & 255u);
+        ray.inside = (int)((hb >> 30) & 1u);  // FindNearest overwrites isInsideGlass on a sphere/triangle hit (renderer.cpp:1012)
+      }
       uint32_t seed = __float_as_uint(b.w);
       int depth = (int)((rb >> 8) & 0xFFu) - 1;
       int top = (int)((rb >> 16) & 0xFFu);
@@ -399,7 +430,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shade(const __grid_constant__ W
           bool insideVolume = true;
           float intensity = 0, dist = 0;
           if (voxIndex == 0) {  // player-volume side channel: evaluated in place (rare), result only feeds inLight
-            const f3 inc = illumination<CS>(sc, svol, ray, seed, cn);
+            const f3 inc = illumination<CS>(sc, stg, ray, seed, cn);
             if (dot3(inc, inc) > 16.0f) in_light = 1;
           }
           if (inGlass) {
@@ -430,7 +461,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shade(const __grid_constant__ W
           L.type = 2; L.mx = al.x; L.my = al.y; L.mz = al.z;
         }
         f3 A = v3s(0);
-        if (illum) wf_light_request<CS>(p, svol, path, top, ray, seed, want_shadow, A);
+        if (illum) wf_light_request<CS>(p, path, top, ray, seed, want_shadow, A);
         p.st.lm[(size_t)top * cap + path] = make_float4(L.mx, L.my, L.mz, __int_as_float(L.type));
         p.st.la[(size_t)top * cap + path] = make_float4(A.x, A.y, A.z, 0);
         top++; depth--;
@@ -458,7 +489,8 @@ template <bool CS>
 __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  const DVolume* svol = wf_stage_volumes(p.sc, smem);
+  const Staged stg = wf_stage_scene(p.sc, smem);
+  const DVolume* svol = stg.vol;
   const int lane = threadIdx.x & 31;
   const DScene& sc = p.sc;
   uint32_t* cnt = p.st.counts + 4 * p.iter;
@@ -471,9 +503,10 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
   int nsamp = 0, sample = 0, vi = 0;
   f3 org = v3s(0), D = v3s(0), inc = v3s(0), li = v3s(0);
   float tmaxray = 0;
-  ORay r; r.O = r.D = r.rD = v3s(0); r.neg = 0;
-  DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.X = s.Y = s.Z = 0; s.sx = s.sy = s.sz = 0;
-  Occ o; o.key = 0xFFFFFFFFu; o.m = 0;
+  const unsigned long long* region = nullptr;
+  const unsigned long long* fine = nullptr;
+  DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
+  Occ o; occ_reset(o);
   unsigned long long steps = 0;
   unsigned int nrays = 0;
   for (;;) {
@@ -505,9 +538,9 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
           bool entered = false;
           while (vi < nvol) {
             const DVolume& v = svol[vi];
-            r = make_oray(xform_scalar(org, 1.0f, v.iM), xform_scalar(D, 0.0f, v.iM));
+            const ORay r = make_oray(xform_scalar(org, 1.0f, v.iM), xform_scalar(D, 0.0f, v.iM));
             vi++;
-            if (setup_dda(v, r, s)) { entered = true; o.key = 0xFFFFFFFFu; o.m = 0; break; }
+            if (setup_dda(v, r, s)) { entered = true; occ_reset(o); region = region_of(stg, v); fine = v.fine; break; }
           }
           if (entered) { in_dda = true; break; }
           // all volumes passed unoccluded: analytic primitives, then accept the sample
@@ -549,13 +582,21 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
     }
     const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)kRefill;
     for (;;) {
-      if (in_dda) {
-        const DVolume& v = svol[vi - 1];
-        if (!(s.t < tmaxray)) in_dda = false;  // this volume does not occlude: continue with the next one
-        else {
-          if (CS) steps++;
-          if (occ_test(v, o, s.X, s.Y, s.Z)) { in_dda = false; has_ray = false; sample++; }  // occluded: sample contributes nothing
-          else if (!dda_step(s, v.n)) in_dda = false;
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (in_dda) {
+          if (!(s.t < tmaxray)) in_dda = false;  // this volume does not occlude: continue with the next one
+          else {
+            if (CS) steps++;
+            const uint32_t ch = s.P ^ o.key;
+            if (ch >> 6) {
+              if (ch >> 12) o.rm = region[s.P >> 12];
+              o.key = s.P;
+              o.m = ((o.rm >> ((s.P >> 6) & 63u)) & 1ull) ? __ldg(fine + (s.P >> 6)) : 0ull;
+            }
+            if ((o.m >> (s.P & 63u)) & 1ull) { in_dda = false; has_ray = false; sample++; }  // occluded: sample contributes nothing
+            else if (!dda_step(s)) in_dda = false;
+          }
         }
       }
       if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, in_dda)) < thr) break;
