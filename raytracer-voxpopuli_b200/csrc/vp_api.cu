@@ -646,7 +646,7 @@ int vp_stats_begin(vp_ctx* c)
   if (!c) return fail(VP_EINVAL, "null context");
   if (bind(c)) return VP_ECUDA;
   CU(cudaDeviceSynchronize());
-  CU(cudaMemset(c->d_counters.p, 0, 8 * sizeof(unsigned long long)));
+  CU(cudaMemset(c->d_counters.p, 0, 16 * sizeof(unsigned long long)));
   c->host_launches = 0;
   return 0;
 }
@@ -674,13 +674,22 @@ int vp_info(vp_ctx* c, char* buf, int cap)
   if (!c || !buf || cap <= 0) return fail(VP_EINVAL, "bad arguments to vp_info");
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) return fail(VP_ECUDA, "cudaGetDeviceProperties failed");
-  cudaFuncAttributes fa;
+  cudaFuncAttributes fa, fe, fs, fh;
   cudaFuncGetAttributes(&fa, k_render<false>);
+  cudaFuncGetAttributes(&fe, k_wf_extend<false>);
+  cudaFuncGetAttributes(&fs, k_wf_shadow<false>);
+  cudaFuncGetAttributes(&fh, k_wf_shade<false>);
+  unsigned long long dbg[16] = {0};
+  cudaDeviceSynchronize();
+  cudaMemcpy(dbg, c->d_counters.p, sizeof(dbg), cudaMemcpyDeviceToHost);
   snprintf(buf, (size_t)cap,
            "{\"device\": %d, \"name\": \"%s\", \"sm\": \"%d.%d\", \"sm_count\": %d, \"blocks_per_sm\": %d, \"block\": %d, "
-           "\"k_render_regs\": %d, \"k_render_local_bytes\": %zu, \"volumes\": %d, \"max_levels\": %d}",
+           "\"k_render_regs\": %d, \"k_render_local_bytes\": %zu, \"k_wf_extend_regs\": %d, \"k_wf_shadow_regs\": %d, "
+           "\"k_wf_shade_regs\": %d, \"wf_blocks_extend\": %d, \"wf_blocks_shadow\": %d, \"volumes\": %d, \"max_levels\": %d, "
+           "\"region_words_staged\": %d, \"dbg_extend_steps_in_empty_region\": %llu, \"dbg_extend_steps_in_empty_brick\": %llu}",
            c->device, prop.name, prop.major, prop.minor, c->sm_count, c->blocks_per_sm, kBlock, fa.numRegs, fa.localSizeBytes,
-           c->sc.nvol, VP_MAX_LEVELS);
+           fe.numRegs, fs.numRegs, fh.numRegs, c->wf_blocks_extend, c->wf_blocks_shadow, c->sc.nvol, VP_MAX_LEVELS,
+           c->sc.region_words, dbg[9], dbg[10]);
   return 0;
 }
 

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
   const unsigned long long* fine = nullptr;
   DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
   Occ o; occ_reset(o);
-  unsigned long long steps = 0;
+  unsigned long long steps = 0, steps_er = 0, steps_eb = 0;
   unsigned int nrays = 0;
   for (;;) {
     // 1. refill idle lanes from the queue
@@ -211,32 +211,32 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
         has_ray = false;
       }
     }
-    // 3. DDA stepping (Scene::FindNearest loop, scene.cpp:763-804) until too few lanes are walking
+    // 3. DDA stepping (Scene::FindNearest loop, scene.cpp:763-804) until too few lanes are walking.
+    //    A lane walks while s.t < tbest: a hit sets tbest = s.t, leaving the grid sets s.t = inf.
+    if (!in_dda) s.t = 3.0e38f;
     const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)kRefill;  // queue drained: run to completion
     for (;;) {
 #pragma unroll
       for (int u = 0; u < 2; u++) {
-        if (in_dda) {
-          if (!(s.t < tbest)) in_dda = false;
-          else {
-            if (CS) steps++;
-            // occupancy of the current cell (inline occ_test with the lane's cached mask pointers)
-            const uint32_t ch = s.P ^ o.key;
-            if (ch >> 6) {
-              if (ch >> 12) o.rm = region[s.P >> 12];
-              o.key = s.P;
-              o.m = ((o.rm >> ((s.P >> 6) & 63u)) & 1ull) ? __ldg(fine + (s.P >> 6)) : 0ull;
-            }
-            if ((o.m >> (s.P & 63u)) & 1ull) { tbest = s.t; pbest = s.P; volbest = vi - 1; in_dda = false; }
-            else if (!dda_step(s)) in_dda = false;
+        if (s.t < tbest) {
+          if (CS) steps++;
+          const uint32_t ch = s.P ^ o.key;
+          if (ch >> 6) {
+            if (ch >> 12) o.rm = region[s.P >> 12];
+            o.key = s.P;
+            o.m = ((uint32_t)(o.rm >> ((s.P >> 6) & 63u)) & 1u) ? __ldg(fine + (s.P >> 6)) : 0ull;
           }
+          if (CS) { if (o.rm == 0ull) steps_er++; if (o.m == 0ull) steps_eb++; }
+          if ((uint32_t)(o.m >> (s.P & 63u)) & 1u) { tbest = s.t; pbest = s.P; volbest = vi - 1; }
+          else if (!dda_step(s)) s.t = 3.0e38f;
         }
       }
-      if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, in_dda)) < thr) break;
+      if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) < thr) break;
     }
+    in_dda = s.t < tbest;
   }
   wf_add_counter(p.counters + 0, nrays);
-  if (CS) wf_add_counter(p.counters + 3, steps);
+  if (CS) { wf_add_counter(p.counters + 3, steps); wf_add_counter(p.counters + 9, steps_er); wf_add_counter(p.counters + 10, steps_eb); }
 }
 
 // ---- K3: shade = the material switch of Renderer::Trace (renderer.cpp:1092-1327) -------------------
@@ -580,26 +580,30 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
         }
       }
     }
+    // walk while s.t < tlim: tlim = tmaxray while a volume is being traversed, -inf otherwise
+    if (!in_dda) s.t = 3.0e38f;
     const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)kRefill;
+    bool occluded = false;
     for (;;) {
 #pragma unroll
       for (int u = 0; u < 2; u++) {
-        if (in_dda) {
-          if (!(s.t < tmaxray)) in_dda = false;  // this volume does not occlude: continue with the next one
-          else {
-            if (CS) steps++;
-            const uint32_t ch = s.P ^ o.key;
-            if (ch >> 6) {
-              if (ch >> 12) o.rm = region[s.P >> 12];
-              o.key = s.P;
-              o.m = ((o.rm >> ((s.P >> 6) & 63u)) & 1ull) ? __ldg(fine + (s.P >> 6)) : 0ull;
-            }
-            if ((o.m >> (s.P & 63u)) & 1ull) { in_dda = false; has_ray = false; sample++; }  // occluded: sample contributes nothing
-            else if (!dda_step(s)) in_dda = false;
+        if (s.t < tmaxray) {
+          if (CS) steps++;
+          const uint32_t ch = s.P ^ o.key;
+          if (ch >> 6) {
+            if (ch >> 12) o.rm = region[s.P >> 12];
+            o.key = s.P;
+            o.m = ((uint32_t)(o.rm >> ((s.P >> 6) & 63u)) & 1u) ? __ldg(fine + (s.P >> 6)) : 0ull;
           }
+          if ((uint32_t)(o.m >> (s.P & 63u)) & 1u) { occluded = true; s.t = 3.0e38f; }
+          else if (!dda_step(s)) s.t = 3.0e38f;
         }
       }
-      if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, in_dda)) < thr) break;
+      if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) < thr) break;
+    }
+    if (in_dda) {
+      in_dda = s.t < tmaxray;
+      if (occluded) { has_ray = false; sample++; }  // occluded: the sample contributes nothing
     }
   }
   wf_add_counter(p.counters + 1, nrays);
