@@ -31,10 +31,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 vp = importlib.import_module("raytracer-voxpopuli_b200")
 scenes = importlib.import_module("raytracer-voxpopuli_b200.scenes")
+sharding = importlib.import_module("raytracer-voxpopuli_b200.sharding")
 abi = vp.abi
 
 METRIC = "Mrays/s (primary+shadow+secondary)"
-ROW_TILE = 8
+ROW_TILE = sharding.ROW_TILE
 
 
 def frame_params(fpd, **over):
@@ -172,37 +173,22 @@ def main():
     lib = vp.load_product()
     sc, cam, fpd = scenes.config(args.config)
     W, H = fpd["width"], fpd["height"]
-    shard = dict(row_tile=ROW_TILE, row_tile_stride=world, row_tile_phase=rank) if world > 1 else {}
+    shard = sharding.shard_params(world, rank)
     sess = vp.Session(lib, local)
     sess.set_scene(sc)
     cc = cam.to_c()
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     rgb8 = torch.zeros((H, W), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev)
-    # rows owned by each rank (interleaved 8-row tiles) for the gather
-    ntile = (H + ROW_TILE - 1) // ROW_TILE
-    tiles_r = [list(range(r, ntile, world)) for r in range(world)]
-    max_tiles = max(len(t) for t in tiles_r)
-    rgb_tiles = rgb8.view(-1)[: ntile * ROW_TILE * W] if H % ROW_TILE == 0 else None
-    gather_out = torch.zeros((world, max_tiles, ROW_TILE, W), dtype=torch.int32, device=dev) if world > 1 else None
-    my_pack = torch.zeros((max_tiles, ROW_TILE, W), dtype=torch.int32, device=dev) if world > 1 else None
-    my_idx = torch.tensor(tiles_r[rank], device=dev, dtype=torch.long) if world > 1 else None
+    tiles_r = [sharding.tiles_of_rank(H, world, r) for r in range(world)]
+    gather = sharding.FrameGather(rgb8, world, rank) if world > 1 else None
 
     def step(i, stats=None):
         fp = frame_params(fpd, frame_index=i, **shard)
         lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp), accum.data_ptr(), rgb8.data_ptr(), stream.cuda_stream,
                                       C.byref(stats) if stats is not None else None), "render_device")
         if world > 1:
-            # pack own tiles -> one NCCL all_gather -> de-interleave into the full frame (every rank ends with the image)
-            v = rgb8.view(ntile, ROW_TILE, W) if H % ROW_TILE == 0 else None
-            my_pack[: len(tiles_r[rank])] = v[my_idx]
-            dist.all_gather_into_tensor(gather_out.view(-1), my_pack.view(-1))
-            for r in range(world):
-                if r != rank:
-                    v[r::world] = gather_out[r, : len(tiles_r[r])]
-
-    if world > 1:
-        assert H % ROW_TILE == 0, "sharded bench expects H to be a multiple of the row tile"
+            gather(rgb8)  # pack own tiles -> one NCCL all_gather -> de-interleave: every rank ends with the image
 
     # L2 flush between timed iterations (the frame's working set is far below the 126 MB L2)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)

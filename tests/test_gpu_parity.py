@@ -228,3 +228,29 @@ def test_error_paths(product):
         product.check(product.c_info(s.ctx, info, 1024), "info")
         meta = json.loads(info.value.decode())
         assert meta["sm"] == "10.0" and meta["k_render_regs"] > 0
+
+
+def test_cpp_renderer_mirror(product, oracle):
+    """The C++ host mirror (voxpop::Renderer / Scene / Camera over the C ABI) driven like reference
+    host code: Scene + SetTransform, lights, camera.LookAt, UploadScene, Update() x frames."""
+    import ctypes as C
+    from _util import host
+    so = os.path.join(os.path.dirname(vp.PRODUCT_SO), "libvoxpop_renderer.so")
+    dll = C.CDLL(so)
+    dll.vphr_demo_render.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.POINTER(C.c_ulonglong)]
+    grid, n, _ = scenes.load_grid("teapot")
+    W, H, frames, mb = 96, 54, 3, 5
+    acc = np.zeros((H, W, 4), np.float32)
+    rgb = np.zeros((H, W), np.uint32)
+    rays = C.c_ulonglong()
+    assert dll.vphr_demo_render(None, grid.ctypes.data, n, W, H, frames, mb, acc.ctypes.data, rgb.ctypes.data, C.byref(rays)) == 0
+    M, iM, a, b = host.make_transform((0, 0, 0), (0, 0.3, 0))
+    sc = vp.SceneDesc(volumes=[vp.Volume(grid, n, a, b, M, iM)], materials=host.default_materials(),
+                      point_lights=[((0.5, 1.6, -0.6), (4, 4, 4))])
+    cam = host.look_at((0.5, 0.55, -0.75), (0.5, 0.3, 0.5), W, H)
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        want, want_rgb, st = s.render(cam, vp.frame_params(W, H, max_bounces=mb, spp=frames))
+    check_accum(acc, want, "C++ mirror")
+    assert np.count_nonzero(rgb != want_rgb) == 0 and rays.value == st.rays

@@ -1,0 +1,63 @@
+"""N > 1 host path on CPU: two gloo ranks each render their interleaved row tiles with the
+oracle, exchange them with one all_gather and must reproduce the single-rank frame exactly."""
+import importlib
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from _util import oracle_lib, params, small_config, vp
+
+sharding = importlib.import_module("raytracer-voxpopuli_b200.sharding")
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = oracle_lib()
+        sc, cam, fpd = small_config(4, 64, 48, spp=2)
+        with vp.Session(lib) as s:
+            s.set_scene(sc)
+            acc, rgb8, st = s.render(cam, params(fpd, **sharding.shard_params(world, rank)))
+        frame = torch.from_numpy(rgb8.astype(np.int32))
+        accum = torch.from_numpy(acc)
+        sharding.FrameGather(frame, world, rank)(frame)
+        sharding.FrameGather(accum, world, rank)(accum)
+        rays = torch.tensor([st.rays], dtype=torch.int64)
+        dist.all_reduce(rays)
+        if rank == 0:
+            q.put((frame.numpy().copy(), accum.numpy().copy(), int(rays[0])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_tile_sharding_matches_single_rank():
+    world, port = 2, 29500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    frame, accum, rays = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sc, cam, fpd = small_config(4, 64, 48, spp=2)
+    with vp.Session(oracle_lib()) as s:
+        s.set_scene(sc)
+        want_acc, want_rgb8, st = s.render(cam, params(fpd))
+    assert np.array_equal(frame.astype(np.uint32), want_rgb8)
+    assert np.array_equal(accum.view(np.uint32), want_acc.view(np.uint32))
+    assert rays == st.rays
+
+
+def test_tile_ownership_partitions_the_frame():
+    for H in (48, 1080, 2160):
+        for world in (1, 2, 4, 8):
+            owned = sorted(t for r in range(world) for t in sharding.tiles_of_rank(H, world, r))
+            assert owned == list(range((H + sharding.ROW_TILE - 1) // sharding.ROW_TILE))
+            sizes = [len(sharding.tiles_of_rank(H, world, r)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
