@@ -64,7 +64,9 @@ struct vp_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;  // shadow stage of the wavefront pipeline
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_shade[VP_MAX_LEVELS] = {}, ev_shadow[VP_MAX_LEVELS] = {};
   std::vector<HostVolume> vols;
   DevBuf<DVolume> d_vols;
   DevBuf<VpMaterial> d_mat;
@@ -200,8 +202,8 @@ int wf_reserve(vp_ctx* c, uint32_t cap, int levels, int samples)
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_r0 = take(cap * f4), o_r1 = take(cap * f4), o_h0 = take(cap * 8), o_h1 = take(cap * 4), o_hn = take(cap * f4), o_term = take(cap * f4);
   const size_t o_lm = take((size_t)levels * cap * f4), o_la = take((size_t)levels * cap * f4);
-  const size_t o_sq0 = take(cap * f4), o_sqd = take((size_t)samples * cap * f4), o_sql = take((size_t)samples * cap * f4);
-  const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_qs = take(cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
+  const size_t o_sq0 = take(2 * cap * f4), o_sqd = take((size_t)2 * samples * cap * f4), o_sql = take((size_t)2 * samples * cap * f4);
+  const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_qs = take(2 * cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
   CU(cudaDeviceSynchronize());
   CU(c->d_wf.reserve(off));
   unsigned char* b = c->d_wf.p;
@@ -209,13 +211,22 @@ int wf_reserve(vp_ctx* c, uint32_t cap, int levels, int samples)
   w.cap = cap;
   w.r0 = (float4*)(b + o_r0); w.r1 = (float4*)(b + o_r1); w.h0 = (float2*)(b + o_h0); w.h1 = (uint32_t*)(b + o_h1); w.hn = (float4*)(b + o_hn);
   w.term = (float4*)(b + o_term); w.lm = (float4*)(b + o_lm); w.la = (float4*)(b + o_la);
-  w.sq0 = (float4*)(b + o_sq0); w.sqd = (float4*)(b + o_sqd); w.sql = (float4*)(b + o_sql);
-  w.q[0] = (uint32_t*)(b + o_q0); w.q[1] = (uint32_t*)(b + o_q1); w.qs = (uint32_t*)(b + o_qs); w.counts = (uint32_t*)(b + o_cnt);
+  for (int k = 0; k < 2; k++) {
+    w.sq0[k] = (float4*)(b + o_sq0) + (size_t)k * cap;
+    w.sqd[k] = (float4*)(b + o_sqd) + (size_t)k * samples * cap;
+    w.sql[k] = (float4*)(b + o_sql) + (size_t)k * samples * cap;
+    w.qs[k] = (uint32_t*)(b + o_qs) + (size_t)k * cap;
+  }
+  w.q[0] = (uint32_t*)(b + o_q0); w.q[1] = (uint32_t*)(b + o_q1); w.counts = (uint32_t*)(b + o_cnt);
   c->wf_cap = cap; c->wf_levels = levels; c->wf_samples = samples;
   return 0;
 }
 
 // wavefront formulation: per pass  generate -> (extend, shade, shadow) x (max_bounces + 1) -> resolve
+// One Update() pass.  Main chain on `stream`: generate, then extend(k) -> shade(k) per bounce, resolve.
+// The shadow stage of bounce k only feeds the fold (level k's light term), so it runs on the context's
+// side stream, overlapping the tails of the next bounce's extend/shade; shade(k+2) waits for shadow(k)
+// before reusing its request buffer and resolve waits for all of them.
 template <bool CS>
 int launch_wavefront_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
 {
@@ -227,10 +238,15 @@ int launch_wavefront_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
   for (int it = 0; it <= p.max_bounces; it++) {
     p.iter = it;
     k_wf_extend<CS><<<c->wf_blocks_extend, kWfBlock, sm, stream>>>(p);
+    if (it >= 2) CU(cudaStreamWaitEvent(stream, c->ev_shadow[it - 2], 0));
     k_wf_shade<CS><<<wide, kWfBlock, sm, stream>>>(p);
-    k_wf_shadow<CS><<<c->wf_blocks_shadow, kWfBlock, sm, stream>>>(p);
+    CU(cudaEventRecord(c->ev_shade[it], stream));
+    CU(cudaStreamWaitEvent(c->side, c->ev_shade[it], 0));
+    k_wf_shadow<CS><<<c->wf_blocks_shadow, kWfBlock, sm, c->side>>>(p);
+    CU(cudaEventRecord(c->ev_shadow[it], c->side));
     c->host_launches += 3;
   }
+  for (int it = (p.max_bounces >= 1 ? p.max_bounces - 1 : 0); it <= p.max_bounces; it++) CU(cudaStreamWaitEvent(stream, c->ev_shadow[it], 0));
   k_wf_resolve<<<wide, kWfBlock, 0, stream>>>(p);
   c->host_launches++;
   CU(cudaGetLastError());
@@ -332,7 +348,11 @@ vp_ctx* vp_create(int device)
   vp_ctx* c = new vp_ctx;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+  bool evok = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < VP_MAX_LEVELS && evok; i++)
+    evok = cudaEventCreateWithFlags(&c->ev_shade[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&c->ev_shadow[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!evok || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
       cudaEventCreate(&c->ev1) != cudaSuccess || c->d_counters.reserve(16) != cudaSuccess ||
       cudaMemset(c->d_counters.p, 0, 16 * sizeof(unsigned long long)) != cudaSuccess) {
     fail(VP_ENODEVICE, "CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -379,6 +399,11 @@ void vp_destroy(vp_ctx* c)
   c->d_sph.release(); c->d_tri.release(); c->d_sky.release(); c->d_regions.release(); c->d_counters.release(); c->d_accum.release();
   c->d_wf.release();
   c->d_rgb8.release(); c->d_scratch_in.release(); c->d_scratch_out.release(); c->d_scratch_aux.release();
+  for (int i = 0; i < VP_MAX_LEVELS; i++) {
+    if (c->ev_shade[i]) cudaEventDestroy(c->ev_shade[i]);
+    if (c->ev_shadow[i]) cudaEventDestroy(c->ev_shadow[i]);
+  }
+  if (c->side) cudaStreamDestroy(c->side);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);

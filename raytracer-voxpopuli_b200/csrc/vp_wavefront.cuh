@@ -37,11 +37,13 @@ struct WfState {
   float4* term;  // terminal radiance (sky / emissive / 0)
   float4* lm;    // [level][path]: M.xyz, w = type bits
   float4* la;    // [level][path]: A.xyz
-  float4* sq0;   // shadow request: origin.xyz, w = bits nsamp(8) | level(8) << 8 | area(1) << 16 | mat(8) << 24
-  float4* sqd;   // [sample][path]: dir.xyz, w = dist
-  float4* sql;   // [sample][path]: li.xyz (single lights: final contribution), w = valid
+  // shadow requests, double-buffered by bounce parity (the shadow stage of bounce k runs on a second
+  // stream while bounce k+1 is extended and shaded; shade k+2 waits for it before reusing the buffer)
+  float4* sq0[2];   // origin.xyz, w = bits nsamp(8) | level(8) << 8 | area(1) << 16 | mat(8) << 24
+  float4* sqd[2];   // [sample][path]: dir.xyz, w = dist
+  float4* sql[2];   // [sample][path]: li.xyz (single lights: final contribution), w = valid
   uint32_t* q[2];       // active-path queues (ping-pong)
-  uint32_t* qs;         // shadow-request queue
+  uint32_t* qs[2];      // shadow-request queues (bounce parity)
   uint32_t* counts;     // [iter][4]: 0 = active count entering iter, 1 = shadow count of iter, 2 = extend cursor, 3 = shadow cursor
 };
 
@@ -257,6 +259,7 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
   queued = false;
   A_now = muls(v3s(0), (float)lightCount);
   const uint32_t cap = p.st.cap;
+  const int par = p.iter & 1;
   if (idx >= (uint32_t)sc.npl && idx < (uint32_t)(sc.nal + sc.npl)) {
     const VpAreaLight L = sc.al[idx - sc.npl];
     const f3 center = ld3(L.position);
@@ -279,11 +282,11 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
       li = divs(li, dst * dst);
       const bool valid = !(ct <= 0);
       nvalid += valid;
-      p.st.sqd[(size_t)i * cap + path] = make_float4(dn.x, dn.y, dn.z, dst);
-      p.st.sql[(size_t)i * cap + path] = make_float4(li.x, li.y, li.z, valid ? 1.0f : 0.0f);
+      p.st.sqd[par][(size_t)i * cap + path] = make_float4(dn.x, dn.y, dn.z, dst);
+      p.st.sql[par][(size_t)i * cap + path] = make_float4(li.x, li.y, li.z, valid ? 1.0f : 0.0f);
     }
     if (nvalid > 0) {
-      p.st.sq0[path] = make_float4(point.x, point.y, point.z,
+      p.st.sq0[par][path] = make_float4(point.x, point.y, point.z,
                                    __uint_as_float((uint32_t)sc.area_samples | ((uint32_t)level << 8) | (1u << 16) | ((uint32_t)(ray.mat & 255) << 24)));
       queued = true;
     } else {
@@ -323,9 +326,9 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
     }
     if (lit) {
       const f3 org = offset_ray(ip, n);
-      p.st.sq0[path] = make_float4(org.x, org.y, org.z, __uint_as_float(1u | ((uint32_t)level << 8) | ((uint32_t)(ray.mat & 255) << 24)));
-      p.st.sqd[path] = make_float4(dirn.x, dirn.y, dirn.z, tshadow);
-      p.st.sql[path] = make_float4(contrib.x, contrib.y, contrib.z, 1.0f);
+      p.st.sq0[par][path] = make_float4(org.x, org.y, org.z, __uint_as_float(1u | ((uint32_t)level << 8) | ((uint32_t)(ray.mat & 255) << 24)));
+      p.st.sqd[par][path] = make_float4(dirn.x, dirn.y, dirn.z, tshadow);
+      p.st.sql[par][path] = make_float4(contrib.x, contrib.y, contrib.z, 1.0f);
       queued = true;
     }
   }
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shade(const __grid_constant__ W
       }
     }
     wf_push(qnext, cnt + 4, cont, path);          // counts[iter+1][0]
-    wf_push(p.st.qs, cnt + 1, want_shadow, path);  // counts[iter][1]
+    wf_push(p.st.qs[p.iter & 1], cnt + 1, want_shadow, path);  // counts[iter][1]
   }
   wf_add_counter(p.counters + 6, cn.sky);
   wf_add_counter(p.counters + 2, cn.exitray);
@@ -498,6 +501,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
   const uint32_t cap = p.st.cap;
   const int nvol = sc.nvol;
   const float lightCount = (float)(uint32_t)(sc.npl + sc.nsl + sc.nal + 1);
+  const int par = p.iter & 1;
   bool has_req = false, has_ray = false, in_dda = false, exhausted = false;
   uint32_t path = 0, bits = 0;
   int nsamp = 0, sample = 0, vi = 0;
@@ -520,8 +524,8 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
       if (need) {
         const uint32_t qi = base + (uint32_t)__popc(nm & ((1u << lane) - 1u));
         if (qi < n) {
-          path = p.st.qs[qi];
-          const float4 q0 = p.st.sq0[path];
+          path = p.st.qs[par][qi];
+          const float4 q0 = p.st.sq0[par][path];
           org = v3(q0.x, q0.y, q0.z);
           bits = __float_as_uint(q0.w);
           nsamp = (int)(bits & 255u);
@@ -553,9 +557,9 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
         // next sample that needs a ray
         bool found = false;
         while (sample < nsamp) {
-          const float4 l4 = p.st.sql[(size_t)sample * cap + path];
+          const float4 l4 = p.st.sql[par][(size_t)sample * cap + path];
           if (l4.w != 0.0f) {
-            const float4 d4 = p.st.sqd[(size_t)sample * cap + path];
+            const float4 d4 = p.st.sqd[par][(size_t)sample * cap + path];
             D = normalize3(v3(d4.x, d4.y, d4.z));  // normalising Ray ctor of the shadow ray
             tmaxray = d4.w;
             li = v3(l4.x, l4.y, l4.z);
