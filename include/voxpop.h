@@ -102,6 +102,8 @@ typedef struct VpFrameParams {
 
 #define VP_FLAG_COUNT_STEPS 1u /* also count DDA cell visits (instrumented kernel variant, slower) */
 #define VP_FLAG_MEGAKERNEL 2u  /* single-kernel path walk instead of the wavefront pipeline (A/B measurement) */
+#define VP_FLAG_PERSISTENT 4u  /* all stages of a pass inside ONE persistent kernel with device-side queues instead of one
+                                  kernel per stage and bounce (lower fixed latency on very small frames, slower at full load) */
 
 /* Result of one Renderer::FindNearest call (renderer.cpp:946-1018). */
 typedef struct VpHit {

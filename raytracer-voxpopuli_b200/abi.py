@@ -75,6 +75,7 @@ class VpStats(C.Structure):
 VP_OK, VP_EINVAL, VP_ENODEVICE, VP_ECUDA, VP_ENOMEM, VP_ESTATE = 0, -1, -2, -3, -4, -5
 VP_FLAG_COUNT_STEPS = 1
 VP_FLAG_MEGAKERNEL = 2
+VP_FLAG_PERSISTENT = 4
 
 HIT_DTYPE = np.dtype([("volume", "<i4"), ("cell", "<u4"), ("t", "<f4"), ("normal", "<f4", (3,)),
                       ("material", "u1"), ("face", "i1"), ("inside", "u1"), ("pad", "u1")])

@@ -30,7 +30,7 @@ def _run(cmd):
 def build(force=False, verbose_ptxas=False):
     csrc = os.path.join(PKG, "csrc")
     hdr = os.path.join(os.path.dirname(PKG), "include", "voxpop.h")
-    cu = [os.path.join(csrc, f) for f in ("vp_api.cu", "vp_kernels.cuh", "vp_device.cuh")] + [hdr]
+    cu = [os.path.join(csrc, "vp_api.cu")] + sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")) + [hdr]
     so = os.path.join(PKG, "libvoxpop_b200.so")
     if force or _stale(so, cu):
         _run(["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + ["-o", so, cu[0]])

@@ -4,12 +4,14 @@
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "vp_kernels.cuh"
 #include "vp_wavefront.cuh"
+#include "vp_persistent.cuh"
 
 using namespace vp;
 
@@ -93,6 +95,10 @@ struct vp_ctx {
   int wf_levels = 0, wf_samples = 0;
   int wf_blocks_extend = 0, wf_blocks_shadow = 0;
   unsigned long long host_launches = 0;
+  int tune_refill = kRefill;  // VP_REFILL
+  int tune_persistent = 0;    // VP_PERSISTENT=1: persistent kernel instead of per-stage kernels
+  int wf_blocks_persistent = 0;
+  uint32_t last_error_word = 0;  // error word of the last persistent launch (valid after a stream sync)
 };
 
 namespace {
@@ -202,7 +208,9 @@ int wf_reserve(vp_ctx* c, uint32_t cap, int levels, int samples)
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_r0 = take(cap * f4), o_r1 = take(cap * f4), o_h0 = take(cap * 8), o_h1 = take(cap * 4), o_hn = take(cap * f4), o_term = take(cap * f4);
   const size_t o_lm = take((size_t)levels * cap * f4), o_la = take((size_t)levels * cap * f4);
-  const size_t o_sq0 = take(2 * cap * f4), o_sqd = take((size_t)2 * samples * cap * f4), o_sql = take((size_t)2 * samples * cap * f4);
+  const size_t o_sq0 = take((size_t)levels * cap * f4), o_sqd = take((size_t)levels * samples * cap * f4), o_sql = take((size_t)levels * samples * cap * f4);
+  const size_t pq_len = (size_t)levels * cap + (size_t)64 * 1024 * 32;  // + one window per warp that may be handed out past the last id
+  const size_t o_pq = take(3 * pq_len * 4), o_pctl = take(kCtlWords * 4);
   const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_qs = take(2 * cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
   CU(cudaDeviceSynchronize());
   CU(c->d_wf.reserve(off));
@@ -211,13 +219,13 @@ int wf_reserve(vp_ctx* c, uint32_t cap, int levels, int samples)
   w.cap = cap;
   w.r0 = (float4*)(b + o_r0); w.r1 = (float4*)(b + o_r1); w.h0 = (float2*)(b + o_h0); w.h1 = (uint32_t*)(b + o_h1); w.hn = (float4*)(b + o_hn);
   w.term = (float4*)(b + o_term); w.lm = (float4*)(b + o_lm); w.la = (float4*)(b + o_la);
-  for (int k = 0; k < 2; k++) {
-    w.sq0[k] = (float4*)(b + o_sq0) + (size_t)k * cap;
-    w.sqd[k] = (float4*)(b + o_sqd) + (size_t)k * samples * cap;
-    w.sql[k] = (float4*)(b + o_sql) + (size_t)k * samples * cap;
-    w.qs[k] = (uint32_t*)(b + o_qs) + (size_t)k * cap;
-  }
+  w.sq0 = (float4*)(b + o_sq0); w.sqd = (float4*)(b + o_sqd); w.sql = (float4*)(b + o_sql); w.nsamp = (uint32_t)samples;
+  for (int k = 0; k < 2; k++) w.qs[k] = (uint32_t*)(b + o_qs) + (size_t)k * cap;
   w.q[0] = (uint32_t*)(b + o_q0); w.q[1] = (uint32_t*)(b + o_q1); w.counts = (uint32_t*)(b + o_cnt);
+  for (int k = 0; k < 3; k++) w.pq[k] = (uint32_t*)(b + o_pq) + (size_t)k * pq_len;
+  w.pctl = (uint32_t*)(b + o_pctl);
+  CU(cudaMemset(b + o_pq, 0xFF, 3 * pq_len * 4));  // all slots empty
+  CU(cudaMemset(w.pctl, 0, kCtlWords * 4));
   c->wf_cap = cap; c->wf_levels = levels; c->wf_samples = samples;
   return 0;
 }
@@ -238,7 +246,7 @@ int launch_wavefront_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
   for (int it = 0; it <= p.max_bounces; it++) {
     p.iter = it;
     k_wf_extend<CS><<<c->wf_blocks_extend, kWfBlock, sm, stream>>>(p);
-    if (it >= 2) CU(cudaStreamWaitEvent(stream, c->ev_shadow[it - 2], 0));
+    if (it >= 2) CU(cudaStreamWaitEvent(stream, c->ev_shadow[it - 2], 0));  // shade(k) reuses the id queue of shadow(k-2)
     k_wf_shade<CS><<<wide, kWfBlock, sm, stream>>>(p);
     CU(cudaEventRecord(c->ev_shade[it], stream));
     CU(cudaStreamWaitEvent(c->side, c->ev_shade[it], 0));
@@ -249,6 +257,23 @@ int launch_wavefront_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
   for (int it = (p.max_bounces >= 1 ? p.max_bounces - 1 : 0); it <= p.max_bounces; it++) CU(cudaStreamWaitEvent(stream, c->ev_shadow[it], 0));
   k_wf_resolve<<<wide, kWfBlock, 0, stream>>>(p);
   c->host_launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// One Update() pass with the persistent kernel: clear the queues, generate, one persistent launch, resolve.
+template <bool CS>
+int launch_persistent_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
+{
+  const size_t sm = smem_bytes(c);
+  const int wide = c->sm_count * 8;
+  p.persistent = 1;
+  k_wf_pclear<<<wide, 256, 0, stream>>>(p);
+  CU(cudaMemsetAsync(p.st.pctl, 0, 256 * sizeof(uint32_t), stream));  // heads, tails, pending, error (kPrevTails kept for the clear above)
+  k_wf_generate<<<wide, kWfBlock, 0, stream>>>(p);
+  k_wf_persistent<CS><<<c->wf_blocks_persistent, kWfBlock, sm, stream>>>(p);
+  k_wf_resolve<<<wide, kWfBlock, 0, stream>>>(p);
+  c->host_launches += 4;
   CU(cudaGetLastError());
   return 0;
 }
@@ -268,12 +293,19 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   if (p.row_begin == 0 && p.row_end == 0) p.row_end = fp->height;
   p.row_tile = fp->row_tile; p.row_tile_stride = fp->row_tile_stride; p.row_tile_phase = fp->row_tile_phase;
   p.accum = accum; p.rgb8 = rgb8; p.counters = c->d_counters.p; p.iter = 0;
+  p.refill = c->tune_refill;
+  p.persistent = 0;
+  const bool staged = !((fp->flags & VP_FLAG_PERSISTENT) != 0 || c->tune_persistent);
   for (int s = 0; s < fp->spp; s++) {
     p.frame = fp->frame_index + (uint32_t)s;
     p.write_rgb8 = (s == fp->spp - 1);
-    const int rc = (fp->flags & VP_FLAG_COUNT_STEPS) ? launch_wavefront_pass<true>(c, p, stream) : launch_wavefront_pass<false>(c, p, stream);
+    const bool cs = (fp->flags & VP_FLAG_COUNT_STEPS) != 0;
+    int rc;
+    if (staged) rc = cs ? launch_wavefront_pass<true>(c, p, stream) : launch_wavefront_pass<false>(c, p, stream);
+    else rc = cs ? launch_persistent_pass<true>(c, p, stream) : launch_persistent_pass<false>(c, p, stream);
     if (rc) return rc;
   }
+  if (!staged) CU(cudaMemcpyAsync(&c->last_error_word, c->wf.pctl + kError, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   return 0;
 }
 
@@ -310,6 +342,7 @@ int launch_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float
     CU(cudaStreamSynchronize(stream));
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (c->last_error_word) { const uint32_t e = c->last_error_word; c->last_error_word = 0; return fail(VP_ECUDA, "persistent render kernel gave up waiting (code %u)", e); }
     for (int k = 0; k < 8; k++) h[k] -= before[k];
     stats->primary_rays = h[4];
     stats->secondary_rays = h[0] - h[4];
@@ -387,6 +420,16 @@ vp_ctx* vp_create(int device)
   c->wf_blocks_extend = occ * c->sm_count;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shadow<false>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
   c->wf_blocks_shadow = occ * c->sm_count;
+  // tuning knobs for experiments (defaults are the shipped values)
+  cudaFuncSetAttribute(k_wf_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_persistent<false>, kWfBlock, 8 * 1024) != cudaSuccess || occ < 1) occ = 3;
+  c->wf_blocks_persistent = occ * c->sm_count;
+  if (const char* e = getenv("VP_PERSISTENT")) c->tune_persistent = atoi(e);
+  if (const char* e = getenv("VP_BLOCKS_PERSISTENT")) c->wf_blocks_persistent = atoi(e) * c->sm_count;
+  if (const char* e = getenv("VP_REFILL")) c->tune_refill = atoi(e);
+  if (const char* e = getenv("VP_BLOCKS_EXTEND")) c->wf_blocks_extend = atoi(e) * c->sm_count;
+  if (const char* e = getenv("VP_BLOCKS_SHADOW")) c->wf_blocks_shadow = atoi(e) * c->sm_count;
   return c;
 }
 

@@ -23,7 +23,8 @@
 namespace vp {
 
 constexpr int kWfBlock = 128;
-constexpr int kRefill = 22;           // refill when fewer lanes than this are still stepping
+constexpr int kRefill = 20;           // refill when fewer lanes than this are still stepping
+constexpr int kBulkLanes = 12;        // with at most this many lanes walking, lanes in empty 8^3/16^3 blocks bulk-advance
 constexpr int kMaxAreaSamples = 8;    // numCheckShadowsAreaLight supported by the wavefront path (reference default 3)
 
 // Per-path state, structure of arrays over `cap` paths.
@@ -37,14 +38,18 @@ struct WfState {
   float4* term;  // terminal radiance (sky / emissive / 0)
   float4* lm;    // [level][path]: M.xyz, w = type bits
   float4* la;    // [level][path]: A.xyz
-  // shadow requests, double-buffered by bounce parity (the shadow stage of bounce k runs on a second
-  // stream while bounce k+1 is extended and shaded; shade k+2 waits for it before reusing the buffer)
-  float4* sq0[2];   // origin.xyz, w = bits nsamp(8) | level(8) << 8 | area(1) << 16 | mat(8) << 24
-  float4* sqd[2];   // [sample][path]: dir.xyz, w = dist
-  float4* sql[2];   // [sample][path]: li.xyz (single lights: final contribution), w = valid
+  // shadow requests, one slot per (level, path): the shadow stage of a bounce may run long after the
+  // path has been extended and shaded again (side stream / persistent kernel)
+  uint32_t nsamp;   // samples allocated per request (>= area_samples)
+  float4* sq0;      // [level][path]: origin.xyz, w = bits nsamp(8) | level(8) << 8 | area(1) << 16 | mat(8) << 24
+  float4* sqd;      // [level][sample][path]: dir.xyz, w = dist
+  float4* sql;      // [level][sample][path]: li.xyz (single lights: final contribution), w = valid
   uint32_t* q[2];       // active-path queues (ping-pong)
   uint32_t* qs[2];      // shadow-request queues (bounce parity)
   uint32_t* counts;     // [iter][4]: 0 = active count entering iter, 1 = shadow count of iter, 2 = extend cursor, 3 = shadow cursor
+  // persistent pipeline (vp_persistent.cuh): append-only queues 0 extend / 1 shade / 2 shadow + control block
+  uint32_t* pq[3];
+  uint32_t* pctl;
 };
 
 struct WfParams {
@@ -58,6 +63,8 @@ struct WfParams {
   float aa;
   int row_begin, row_end, row_tile, row_tile_stride, row_tile_phase;
   int iter;              // bounce iteration of this launch
+  int refill;            // lanes still walking below which idle lanes refill from the queue
+  int persistent;        // 1: generate feeds the persistent kernel's extend queue
   int write_rgb8;
   float4* accum;
   uint32_t* rgb8;
@@ -136,7 +143,17 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant_
       active = p.max_bounces >= 0;  // Trace(depth < 0) returns before FindNearest, renderer.cpp:1080
       if (active) launched++;
     }
-    wf_push(p.st.q[0], p.st.counts + 0, active, path);
+    if (p.persistent) {
+      // extend queue of the persistent kernel (slot 0 = tail word of the control block); every path is pending work
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, active);
+      if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) { atomicAdd(p.st.pctl + 192, (uint32_t)__popc(m)); base = atomicAdd(p.st.pctl + 0, (uint32_t)__popc(m)); }
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (active) p.st.pq[0][base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = path;
+      }
+    } else wf_push(p.st.q[0], p.st.counts + 0, active, path);
   }
   wf_add_counter(p.counters + 4, launched);
 }
@@ -216,24 +233,25 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
     // 3. DDA stepping (Scene::FindNearest loop, scene.cpp:763-804) until too few lanes are walking.
     //    A lane walks while s.t < tbest: a hit sets tbest = s.t, leaving the grid sets s.t = inf.
     if (!in_dda) s.t = 3.0e38f;
-    const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)kRefill;  // queue drained: run to completion
+    const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)p.refill;  // queue drained: run to completion
+    const bool drained = thr == 1u;  // no more work to pull: latency of the remaining rays is all that matters
+    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) <= (unsigned)kBulkLanes;
     for (;;) {
 #pragma unroll
       for (int u = 0; u < 2; u++) {
         if (s.t < tbest) {
           if (CS) steps++;
-          const uint32_t ch = s.P ^ o.key;
-          if (ch >> 6) {
-            if (ch >> 12) o.rm = region[s.P >> 12];
-            o.key = s.P;
-            o.m = ((uint32_t)(o.rm >> ((s.P >> 6) & 63u)) & 1u) ? __ldg(fine + (s.P >> 6)) : 0ull;
-          }
-          if (CS) { if (o.rm == 0ull) steps_er++; if (o.m == 0ull) steps_eb++; }
-          if ((uint32_t)(o.m >> (s.P & 63u)) & 1u) { tbest = s.t; pbest = s.P; volbest = vi - 1; }
+          uint32_t skipped = 0;
+          const bool solid = occ_visit(region, fine, o, s, tbest, sparse, skipped);
+          if (CS) steps += skipped;
+          if (CS) { if (o.rm == 0ull) steps_er += 1 + skipped; if (o.m == 0ull) steps_eb += 1 + skipped; }
+          if (solid) { tbest = s.t; pbest = s.P; volbest = vi - 1; }
           else if (!dda_step(s)) s.t = 3.0e38f;
         }
       }
-      if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) < thr) break;
+      const unsigned act = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest));
+      sparse = drained || act <= (unsigned)kBulkLanes;
+      if (act < thr) break;
     }
     in_dda = s.t < tbest;
   }
@@ -259,7 +277,9 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
   queued = false;
   A_now = muls(v3s(0), (float)lightCount);
   const uint32_t cap = p.st.cap;
-  const int par = p.iter & 1;
+  float4* const sq0 = p.st.sq0 + (size_t)level * cap;
+  float4* const sqd = p.st.sqd + (size_t)level * p.st.nsamp * cap;
+  float4* const sql = p.st.sql + (size_t)level * p.st.nsamp * cap;
   if (idx >= (uint32_t)sc.npl && idx < (uint32_t)(sc.nal + sc.npl)) {
     const VpAreaLight L = sc.al[idx - sc.npl];
     const f3 center = ld3(L.position);
@@ -282,11 +302,11 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
       li = divs(li, dst * dst);
       const bool valid = !(ct <= 0);
       nvalid += valid;
-      p.st.sqd[par][(size_t)i * cap + path] = make_float4(dn.x, dn.y, dn.z, dst);
-      p.st.sql[par][(size_t)i * cap + path] = make_float4(li.x, li.y, li.z, valid ? 1.0f : 0.0f);
+      sqd[(size_t)i * cap + path] = make_float4(dn.x, dn.y, dn.z, dst);
+      sql[(size_t)i * cap + path] = make_float4(li.x, li.y, li.z, valid ? 1.0f : 0.0f);
     }
     if (nvalid > 0) {
-      p.st.sq0[par][path] = make_float4(point.x, point.y, point.z,
+      sq0[path] = make_float4(point.x, point.y, point.z,
                                    __uint_as_float((uint32_t)sc.area_samples | ((uint32_t)level << 8) | (1u << 16) | ((uint32_t)(ray.mat & 255) << 24)));
       queued = true;
     } else {
@@ -326,12 +346,148 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
     }
     if (lit) {
       const f3 org = offset_ray(ip, n);
-      p.st.sq0[par][path] = make_float4(org.x, org.y, org.z, __uint_as_float(1u | ((uint32_t)level << 8) | ((uint32_t)(ray.mat & 255) << 24)));
-      p.st.sqd[par][path] = make_float4(dirn.x, dirn.y, dirn.z, tshadow);
-      p.st.sql[par][path] = make_float4(contrib.x, contrib.y, contrib.z, 1.0f);
+      sq0[path] = make_float4(org.x, org.y, org.z, __uint_as_float(1u | ((uint32_t)level << 8) | ((uint32_t)(ray.mat & 255) << 24)));
+      sqd[path] = make_float4(dirn.x, dirn.y, dirn.z, tshadow);
+      sql[path] = make_float4(contrib.x, contrib.y, contrib.z, 1.0f);
       queued = true;
     }
   }
+}
+
+// Shade one path (the body of Trace's switch for the hit the extend stage recorded).  Outputs:
+// cont = the path continues with the ray now stored in r0/r1; want_shadow = a light sample was
+// written to the request slot [level][path] and needs its occlusion test.
+template <bool CS>
+__device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& stg, uint32_t path, Counters& cn, int& in_light,
+                                             bool& cont, bool& want_shadow, int& level)
+{
+  const DVolume* svol = stg.vol;
+  const DScene& sc = p.sc;
+  const uint32_t cap = p.st.cap;
+  cont = false; want_shadow = false; level = 0;
+  const float4 a = __ldcg(p.st.r0 + path), b = __ldcg(p.st.r1 + path);
+  const float2 h = __ldcg(p.st.h0 + path);
+  const uint32_t hb = __ldcg(p.st.h1 + path), rb = __float_as_uint(a.w);
+  Ray ray;
+  ray.O = v3(a.x, a.y, a.z); ray.D = v3(b.x, b.y, b.z);
+  ray.t = h.x; ray.N = v3s(0); ray.mat = VP_MAT_NONE;
+  ray.inside = (int)(rb & 1u);
+  const int voxIndex = (int)((hb >> 8) & 0x3FFFFFu) - 2;
+  if (voxIndex >= 0) {
+    // finish Scene::FindNearest's hit block here (scene.cpp:766-773): material byte + Ray::GetNormalVoxel
+    const DVolume& v = svol[voxIndex];
+    const f3 oO = xform_pos_sse(ray.O, v.iM), oD = xform_vec_sse(ray.D, v.iM);
+    ray.mat = __ldg(v.grid + cell_of(v, __float_as_uint(h.y)));
+    ray.N = normal_voxel(v, oO, oD, neg_bits(oD), ray.t, nullptr);
+  } else if (voxIndex == -1) {
+    const float4 nn = __ldcg(p.st.hn + path);
+    ray.N = v3(nn.x, nn.y, nn.z);
+    ray.mat = (int)(hb & 255u);
+    ray.inside = (int)((hb >> 30) & 1u);  // FindNearest overwrites isInsideGlass on a sphere/triangle hit (renderer.cpp:1012)
+  }
+  uint32_t seed = __float_as_uint(b.w);
+  int depth = (int)((rb >> 8) & 0xFFu) - 1;
+  int top = (int)((rb >> 16) & 0xFFu);
+  const int m = ray.mat;
+  if (m == VP_MAT_NONE) {
+    cn.sky++;
+    const f3 t = sample_sky(sc, ray.D);
+    __stcg(p.st.term + path, make_float4(t.x, t.y, t.z, 0));
+  } else if (m == 15) {
+    const f3 t = muls(albedo_of(sc, m), sc.mat[m].emissive);
+    __stcg(p.st.term + path, make_float4(t.x, t.y, t.z, 0));
+  } else {
+    Level L; L.pad = 0; L.ax = L.ay = L.az = 0;
+    Ray nr;
+    bool illum = false;
+    if (m >= 5 && m <= 7) {
+      const f3 refl = reflect3(ray.D, ray.N);
+      const float rough = sc.mat[m].roughness;
+      nr = spawn(offset_ray(isect(ray), ray.N), add(refl, muls(random_sphere_sample(seed), rough)), 0);
+      const f3 al = albedo_of(sc, m);
+      L.type = 0; L.mx = al.x; L.my = al.y; L.mz = al.z;
+    } else if (m <= 4) {
+      if (rnd(seed) > schlick_nonmetal(dot3(neg(ray.D), ray.N))) {
+        const f3 rdir = add(ray.N, random_sphere_sample(seed));
+        illum = true;
+        nr = spawn(offset_ray(isect(ray), ray.N), rdir, 0);
+        const f3 al = albedo_of(sc, m);
+        L.type = 1; L.mx = al.x; L.my = al.y; L.mz = al.z;
+      } else {
+        const f3 refl = reflect3(ray.D, ray.N);
+        const float rough = sc.mat[m].roughness;
+        nr = spawn(offset_ray(isect(ray), ray.N), add(refl, muls(random_sphere_sample(seed), rough)), 0);
+        L.type = 3; L.mx = L.my = L.mz = 1.0f;
+      }
+    } else if (m == 8) {
+      f3 color = v3s(1.0f);
+      int inGlass = ray.inside;
+      const float ior = sc.mat[m].ior;
+      const float ratio = inGlass ? ior : 1.0f / ior;
+      bool insideVolume = true;
+      if (inGlass) {
+        color = albedo_of(sc, m);
+        if (voxIndex >= 0) insideVolume = medium_exit<CS>(svol[voxIndex], ray, 0, cn);
+      }
+      if (!insideVolume) { ray.O = add(ray.O, muls(ray.D, ray.t)); ray.t = 0; }
+      const float ct = stdmin(dot3(neg(ray.D), ray.N), 1.0f);
+      const float st = sqrtf(1.0f - ct * ct);
+      const bool cannot = ratio * st > 1.0f;
+      f3 rdir, rn;
+      if (cannot || schlick(ct, ratio) > rnd(seed)) { rdir = reflect3(ray.D, ray.N); rn = ray.N; }
+      else { rdir = refract3(ray.D, ray.N, ratio); inGlass = !inGlass; rn = neg(ray.N); }
+      nr = spawn(offset_ray(isect(ray), rn), rdir, inGlass);
+      L.type = 0; L.mx = color.x; L.my = color.y; L.mz = color.z;
+    } else if (m >= 9 && m <= 14) {
+      f3 color = v3s(1.0f);
+      int inGlass = ray.inside;
+      bool insideVolume = true;
+      float intensity = 0, dist = 0;
+      if (voxIndex == 0) {  // player-volume side channel: evaluated in place (rare), result only feeds inLight
+        const f3 inc = illumination<CS>(sc, stg, ray, seed, cn);
+        if (dot3(inc, inc) > 16.0f) in_light = 1;
+      }
+      if (inGlass) {
+        intensity = sc.mat[m].emissive;
+        color = albedo_of(sc, m);
+        if (voxIndex >= 0) insideVolume = medium_exit<CS>(svol[voxIndex], ray, 1, cn);
+        dist = ray.t;
+      }
+      const float threshold = rnd(seed) * 100 - intensity;
+      if (rnd(seed) * dist > threshold) {
+        const float lo = ray.t * .45f;
+        const float rr = lo + rnd(seed) * (ray.t - lo);
+        ray.O = add(ray.O, muls(ray.D, rr));
+        ray.D = random_direction(seed);
+        ray.t = 0;
+      }
+      color = absorption(color, intensity, dist);
+      if (!insideVolume) { ray.O = add(ray.O, muls(ray.D, ray.t)); ray.t = 0; }
+      const f3 rdir = refract3(ray.D, ray.N, 1.0f);
+      inGlass = !inGlass;
+      nr = spawn(offset_ray(isect(ray), neg(ray.N)), rdir, inGlass);
+      L.type = 0; L.mx = color.x; L.my = color.y; L.mz = color.z;
+    } else {
+      const f3 rdir = diffuse_reflection(seed, ray.N);
+      illum = true;
+      nr = spawn(offset_ray(isect(ray), ray.N), rdir, 0);
+      const f3 al = albedo_of(sc, m);
+      L.type = 2; L.mx = al.x; L.my = al.y; L.mz = al.z;
+    }
+    f3 A = v3s(0);
+    if (illum) { wf_light_request<CS>(p, path, top, ray, seed, want_shadow, A); level = top; }
+    __stcg(p.st.lm + (size_t)top * cap + path, make_float4(L.mx, L.my, L.mz, __int_as_float(L.type)));
+    __stcg(p.st.la + (size_t)top * cap + path, make_float4(A.x, A.y, A.z, 0));
+    top++; depth--;
+    cont = depth >= 0 && top < VP_MAX_LEVELS;  // Trace(depth < 0) returns 0: term stays 0
+    if (cont) {
+      __stcg(p.st.r0 + path, make_float4(nr.O.x, nr.O.y, nr.O.z, __uint_as_float(pack_r0w(nr.inside, depth, top))));
+      __stcg(p.st.r1 + path, make_float4(nr.D.x, nr.D.y, nr.D.z, __uint_as_float(seed)));
+    } else {
+      __stcg(&p.st.r0[path].w, __uint_as_float(pack_r0w(nr.inside, depth, top)));
+    }
+  }
+
 }
 
 template <bool CS>
@@ -354,131 +510,11 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shade(const __grid_constant__ W
     uint32_t path = 0;
     if (qi < n) {
       path = queue[qi];
-      const float4 a = p.st.r0[path], b = p.st.r1[path];
-      const float2 h = p.st.h0[path];
-      const uint32_t hb = p.st.h1[path], rb = __float_as_uint(a.w);
-      Ray ray;
-      ray.O = v3(a.x, a.y, a.z); ray.D = v3(b.x, b.y, b.z);
-      ray.t = h.x; ray.N = v3s(0); ray.mat = VP_MAT_NONE;
-      ray.inside = (int)(rb & 1u);
-      const int voxIndex = (int)((hb >> 8) & 0x3FFFFFu) - 2;
-      if (voxIndex >= 0) {
-        // finish Scene::FindNearest's hit block here (scene.cpp:766-773): material byte + Ray::GetNormalVoxel
-        const DVolume& v = svol[voxIndex];
-        const f3 oO = xform_pos_sse(ray.O, v.iM), oD = xform_vec_sse(ray.D, v.iM);
-        ray.mat = __ldg(v.grid + cell_of(v, __float_as_uint(h.y)));
-        ray.N = normal_voxel(v, oO, oD, neg_bits(oD), ray.t, nullptr);
-      } else if (voxIndex == -1) {
-        const float4 nn = p.st.hn[path];
-        ray.N = v3(nn.x, nn.y, nn.z);
-        ray.mat = (int)(hb & 255u);
-        ray.inside = (int)((hb >> 30) & 1u);  // FindNearest overwrites isInsideGlass on a sphere/triangle hit (renderer.cpp:1012)
-      }
-      uint32_t seed = __float_as_uint(b.w);
-      int depth = (int)((rb >> 8) & 0xFFu) - 1;
-      int top = (int)((rb >> 16) & 0xFFu);
-      const int m = ray.mat;
-      if (m == VP_MAT_NONE) {
-        cn.sky++;
-        const f3 t = sample_sky(sc, ray.D);
-        p.st.term[path] = make_float4(t.x, t.y, t.z, 0);
-      } else if (m == 15) {
-        const f3 t = muls(albedo_of(sc, m), sc.mat[m].emissive);
-        p.st.term[path] = make_float4(t.x, t.y, t.z, 0);
-      } else {
-        Level L; L.pad = 0; L.ax = L.ay = L.az = 0;
-        Ray nr;
-        bool illum = false;
-        if (m >= 5 && m <= 7) {
-          const f3 refl = reflect3(ray.D, ray.N);
-          const float rough = sc.mat[m].roughness;
-          nr = spawn(offset_ray(isect(ray), ray.N), add(refl, muls(random_sphere_sample(seed), rough)), 0);
-          const f3 al = albedo_of(sc, m);
-          L.type = 0; L.mx = al.x; L.my = al.y; L.mz = al.z;
-        } else if (m <= 4) {
-          if (rnd(seed) > schlick_nonmetal(dot3(neg(ray.D), ray.N))) {
-            const f3 rdir = add(ray.N, random_sphere_sample(seed));
-            illum = true;
-            nr = spawn(offset_ray(isect(ray), ray.N), rdir, 0);
-            const f3 al = albedo_of(sc, m);
-            L.type = 1; L.mx = al.x; L.my = al.y; L.mz = al.z;
-          } else {
-            const f3 refl = reflect3(ray.D, ray.N);
-            const float rough = sc.mat[m].roughness;
-            nr = spawn(offset_ray(isect(ray), ray.N), add(refl, muls(random_sphere_sample(seed), rough)), 0);
-            L.type = 3; L.mx = L.my = L.mz = 1.0f;
-          }
-        } else if (m == 8) {
-          f3 color = v3s(1.0f);
-          int inGlass = ray.inside;
-          const float ior = sc.mat[m].ior;
-          const float ratio = inGlass ? ior : 1.0f / ior;
-          bool insideVolume = true;
-          if (inGlass) {
-            color = albedo_of(sc, m);
-            if (voxIndex >= 0) insideVolume = medium_exit<CS>(svol[voxIndex], ray, 0, cn);
-          }
-          if (!insideVolume) { ray.O = add(ray.O, muls(ray.D, ray.t)); ray.t = 0; }
-          const float ct = stdmin(dot3(neg(ray.D), ray.N), 1.0f);
-          const float st = sqrtf(1.0f - ct * ct);
-          const bool cannot = ratio * st > 1.0f;
-          f3 rdir, rn;
-          if (cannot || schlick(ct, ratio) > rnd(seed)) { rdir = reflect3(ray.D, ray.N); rn = ray.N; }
-          else { rdir = refract3(ray.D, ray.N, ratio); inGlass = !inGlass; rn = neg(ray.N); }
-          nr = spawn(offset_ray(isect(ray), rn), rdir, inGlass);
-          L.type = 0; L.mx = color.x; L.my = color.y; L.mz = color.z;
-        } else if (m >= 9 && m <= 14) {
-          f3 color = v3s(1.0f);
-          int inGlass = ray.inside;
-          bool insideVolume = true;
-          float intensity = 0, dist = 0;
-          if (voxIndex == 0) {  // player-volume side channel: evaluated in place (rare), result only feeds inLight
-            const f3 inc = illumination<CS>(sc, stg, ray, seed, cn);
-            if (dot3(inc, inc) > 16.0f) in_light = 1;
-          }
-          if (inGlass) {
-            intensity = sc.mat[m].emissive;
-            color = albedo_of(sc, m);
-            if (voxIndex >= 0) insideVolume = medium_exit<CS>(svol[voxIndex], ray, 1, cn);
-            dist = ray.t;
-          }
-          const float threshold = rnd(seed) * 100 - intensity;
-          if (rnd(seed) * dist > threshold) {
-            const float lo = ray.t * .45f;
-            const float rr = lo + rnd(seed) * (ray.t - lo);
-            ray.O = add(ray.O, muls(ray.D, rr));
-            ray.D = random_direction(seed);
-            ray.t = 0;
-          }
-          color = absorption(color, intensity, dist);
-          if (!insideVolume) { ray.O = add(ray.O, muls(ray.D, ray.t)); ray.t = 0; }
-          const f3 rdir = refract3(ray.D, ray.N, 1.0f);
-          inGlass = !inGlass;
-          nr = spawn(offset_ray(isect(ray), neg(ray.N)), rdir, inGlass);
-          L.type = 0; L.mx = color.x; L.my = color.y; L.mz = color.z;
-        } else {
-          const f3 rdir = diffuse_reflection(seed, ray.N);
-          illum = true;
-          nr = spawn(offset_ray(isect(ray), ray.N), rdir, 0);
-          const f3 al = albedo_of(sc, m);
-          L.type = 2; L.mx = al.x; L.my = al.y; L.mz = al.z;
-        }
-        f3 A = v3s(0);
-        if (illum) wf_light_request<CS>(p, path, top, ray, seed, want_shadow, A);
-        p.st.lm[(size_t)top * cap + path] = make_float4(L.mx, L.my, L.mz, __int_as_float(L.type));
-        p.st.la[(size_t)top * cap + path] = make_float4(A.x, A.y, A.z, 0);
-        top++; depth--;
-        cont = depth >= 0 && top < VP_MAX_LEVELS;  // Trace(depth < 0) returns 0: term stays 0
-        if (cont) {
-          p.st.r0[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, __uint_as_float(pack_r0w(nr.inside, depth, top)));
-          p.st.r1[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, __uint_as_float(seed));
-        } else {
-          p.st.r0[path].w = __uint_as_float(pack_r0w(nr.inside, depth, top));
-        }
-      }
+      int level;
+      wf_shade_one<CS>(p, stg, path, cn, in_light, cont, want_shadow, level);
     }
     wf_push(qnext, cnt + 4, cont, path);          // counts[iter+1][0]
-    wf_push(p.st.qs[p.iter & 1], cnt + 1, want_shadow, path);  // counts[iter][1]
+    wf_push(p.st.qs[p.iter & 1], cnt + 1, want_shadow, path);  // counts[iter][1]; the request's level == iter
   }
   wf_add_counter(p.counters + 6, cn.sky);
   wf_add_counter(p.counters + 2, cn.exitray);
@@ -502,6 +538,9 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
   const int nvol = sc.nvol;
   const float lightCount = (float)(uint32_t)(sc.npl + sc.nsl + sc.nal + 1);
   const int par = p.iter & 1;
+  const float4* const sq0 = p.st.sq0 + (size_t)p.iter * cap;  // staged pipeline: the request level is the bounce index
+  const float4* const sqd = p.st.sqd + (size_t)p.iter * p.st.nsamp * cap;
+  const float4* const sql = p.st.sql + (size_t)p.iter * p.st.nsamp * cap;
   bool has_req = false, has_ray = false, in_dda = false, exhausted = false;
   uint32_t path = 0, bits = 0;
   int nsamp = 0, sample = 0, vi = 0;
@@ -525,7 +564,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
         const uint32_t qi = base + (uint32_t)__popc(nm & ((1u << lane) - 1u));
         if (qi < n) {
           path = p.st.qs[par][qi];
-          const float4 q0 = p.st.sq0[par][path];
+          const float4 q0 = sq0[path];
           org = v3(q0.x, q0.y, q0.z);
           bits = __float_as_uint(q0.w);
           nsamp = (int)(bits & 255u);
@@ -557,9 +596,9 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
         // next sample that needs a ray
         bool found = false;
         while (sample < nsamp) {
-          const float4 l4 = p.st.sql[par][(size_t)sample * cap + path];
+          const float4 l4 = sql[(size_t)sample * cap + path];
           if (l4.w != 0.0f) {
-            const float4 d4 = p.st.sqd[par][(size_t)sample * cap + path];
+            const float4 d4 = sqd[(size_t)sample * cap + path];
             D = normalize3(v3(d4.x, d4.y, d4.z));  // normalising Ray ctor of the shadow ray
             tmaxray = d4.w;
             li = v3(l4.x, l4.y, l4.z);
@@ -586,24 +625,25 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
     }
     // walk while s.t < tlim: tlim = tmaxray while a volume is being traversed, -inf otherwise
     if (!in_dda) s.t = 3.0e38f;
-    const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)kRefill;
+    const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)p.refill;
     bool occluded = false;
+    const bool drained = thr == 1u;
+    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) <= (unsigned)kBulkLanes;
     for (;;) {
 #pragma unroll
       for (int u = 0; u < 2; u++) {
         if (s.t < tmaxray) {
           if (CS) steps++;
-          const uint32_t ch = s.P ^ o.key;
-          if (ch >> 6) {
-            if (ch >> 12) o.rm = region[s.P >> 12];
-            o.key = s.P;
-            o.m = ((uint32_t)(o.rm >> ((s.P >> 6) & 63u)) & 1u) ? __ldg(fine + (s.P >> 6)) : 0ull;
-          }
-          if ((uint32_t)(o.m >> (s.P & 63u)) & 1u) { occluded = true; s.t = 3.0e38f; }
+          uint32_t skipped = 0;
+          const bool solid = occ_visit(region, fine, o, s, tmaxray, sparse, skipped);
+          if (CS) steps += skipped;
+          if (solid) { occluded = true; s.t = 3.0e38f; }
           else if (!dda_step(s)) s.t = 3.0e38f;
         }
       }
-      if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) < thr) break;
+      const unsigned act = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray));
+      sparse = drained || act <= (unsigned)kBulkLanes;
+      if (act < thr) break;
     }
     if (in_dda) {
       in_dda = s.t < tmaxray;
@@ -618,6 +658,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
 __global__ void __launch_bounds__(kWfBlock) k_wf_resolve(const __grid_constant__ WfParams p)
 {
   const uint32_t cap = p.st.cap;
+  if (p.persistent && blockIdx.x == 0 && threadIdx.x < 3) p.st.pctl[256 + threadIdx.x] = p.st.pctl[64 * threadIdx.x];  // tails -> kPrevTails
   for (uint32_t path = blockIdx.x * blockDim.x + threadIdx.x; path < cap; path += gridDim.x * blockDim.x) {
     int x, y;
     if (!wf_pixel_of(p, path, x, y)) continue;

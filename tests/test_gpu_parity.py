@@ -48,12 +48,13 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("pipeline", ["wavefront", "megakernel"])
+@pytest.mark.parametrize("pipeline", ["persistent", "staged", "megakernel"])
 @pytest.mark.parametrize("idx,w,h,over", CASES)
 def test_config_vs_oracle(product, oracle, idx, w, h, over, pipeline):
-    """Both formulations of the path (wavefront stages = default, single-kernel walk) against the oracle."""
+    """All formulations of the path against the oracle: wavefront stages as kernels (default), the same
+    stages inside one persistent kernel, single-kernel walk."""
     sc, cam, fpd = small_config(idx, w, h, **over)
-    flags = abi.VP_FLAG_COUNT_STEPS | (abi.VP_FLAG_MEGAKERNEL if pipeline == "megakernel" else 0)
+    flags = abi.VP_FLAG_COUNT_STEPS | {"persistent": abi.VP_FLAG_PERSISTENT, "staged": 0, "megakernel": abi.VP_FLAG_MEGAKERNEL}[pipeline]
     res = []
     for lib in (oracle, product):
         with vp.Session(lib) as s:
