@@ -183,8 +183,8 @@ def main():
     tiles_r = [sharding.tiles_of_rank(H, world, r) for r in range(world)]
     gather = sharding.FrameGather(rgb8, world, rank) if world > 1 else None
 
-    def step(i, stats=None):
-        fp = frame_params(fpd, frame_index=i, **shard)
+    def step(i, stats=None, flags=0):
+        fp = frame_params(fpd, frame_index=i, flags=flags, **shard)
         lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp), accum.data_ptr(), rgb8.data_ptr(), stream.cuda_stream,
                                       C.byref(stats) if stats is not None else None), "render_device")
         if world > 1:
@@ -208,7 +208,9 @@ def main():
     for i in range(args.steps):
         flush.fill_(float(i))
         ev[i][0].record(stream)
-        step(args.warmup + i)
+        # every 10th step also records CUDA events around its extend-stage launches (kept sparse: the extra
+        # event records cost ~6 % of a step when enabled on all of them)
+        step(args.warmup + i, flags=abi.VP_FLAG_TIME_STAGES if i % 10 == 0 else 0)
         ev[i][1].record(stream)
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -217,6 +219,8 @@ def main():
     clocks = sampler.finish()
     st = abi.VpStats()
     lib.check(lib.c_stats_end(sess.ctx, C.byref(st)), "stats_end")
+    ext_ms, ext_n = C.c_double(), C.c_uint64()
+    lib.check(lib.c_stage_times(sess.ctx, C.byref(ext_ms), C.byref(ext_n)), "stage_times")
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms, float(st.rays), float(st.kernel_launches)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -261,33 +265,50 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_render), single-GPU algorithmic bytes per launch ----
+    # ---- roofline of the dominant kernel: k_wf_extend (Renderer::FindNearest stage) -----------------------
+    # duration: CUDA events recorded by the library around every extend launch of the timed region, on the
+    # stream they were launched on; algorithmic bytes (SURVEY.md 8d terms of this stage): one byte per DDA cell
+    # visit + 128 B of volume transform per ray and volume, counted by an instrumented (untimed) pass.
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     inst = abi.VpStats()
     acc2 = torch.zeros_like(accum)
+    lib.check(lib.c_stats_begin(sess.ctx), "stats_begin")
     fp = frame_params(fpd, frame_index=args.warmup, flags=abi.VP_FLAG_COUNT_STEPS, **shard)
     lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp), acc2.data_ptr(), rgb8.data_ptr(), stream.cuda_stream, C.byref(inst)),
               "render_device(count steps)")
+    info = C.create_string_buffer(4096)
+    lib.check(lib.c_info(sess.ctx, info, 4096), "info")
+    meta = json.loads(info.value.decode())
     nvol = len(sc.volumes)
+    own_rows = sum(min(ROW_TILE, H - k * ROW_TILE) for k in tiles_r[rank])
     px_rank = own_rows * W if world > 1 else W * H
-    alg_bytes = inst.dda_steps * 1 + (inst.rays + inst.exit_rays) * nvol * 128 + px_rank * 32 + px_rank * 4 + inst.sky_samples * 12
-    kernel_ms = total_ms / args.steps  # one k_render launch per step dominates the step (see profiles/)
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    ext_rays = inst.primary_rays + inst.secondary_rays
+    timed_steps = len(range(0, args.steps, 10))
+    ext_launches_per_frame = max(1, ext_n.value // max(1, timed_steps))
+    ext_bytes_frame = meta["extend_steps"] * 1 + ext_rays * nvol * 128
+    frame_bytes = inst.dda_steps * 1 + (inst.rays + inst.exit_rays) * nvol * 128 + px_rank * 32 + px_rank * 4 + inst.sky_samples * 12
+    ext_ms_frame = ext_ms.value / max(1, timed_steps)
+    achieved = ext_bytes_frame / (ext_ms_frame * 1e-3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "k_render_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "k_wf_extend_traffic.json")
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_render", "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
-                "dda_steps_per_launch": int(inst.dda_steps),
-                "note": "latency/divergence-bound traversal of an L2-resident grid: the HBM fraction is expected to be ~1%"}
+                "kernel": "k_wf_extend", "peak_source": peak_src,
+                "launches_per_step": int(ext_launches_per_frame), "kernel_ms_per_step": ext_ms_frame, "steps_with_stage_events": timed_steps,
+                "kernel_share_of_step": ext_ms_frame / (total_ms / args.steps),
+                "algorithmic_bytes_per_launch": int(ext_bytes_frame / ext_launches_per_frame),
+                "algorithmic_bytes_per_step_all_stages": int(frame_bytes),
+                "dda_steps_per_step": int(inst.dda_steps),
+                "note": "traversal of an L2-resident grid, bound by issue slots / divergence / latency, not by HBM: the HBM "
+                        "fraction is a few percent by construction (DESIGN.md section 4)"}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

@@ -102,6 +102,7 @@ typedef struct VpFrameParams {
 
 #define VP_FLAG_COUNT_STEPS 1u /* also count DDA cell visits (instrumented kernel variant, slower) */
 #define VP_FLAG_MEGAKERNEL 2u  /* single-kernel path walk instead of the wavefront pipeline (A/B measurement) */
+#define VP_FLAG_TIME_STAGES 8u /* record CUDA events around every extend-stage launch (read with vp_stage_times) */
 #define VP_FLAG_PERSISTENT 4u  /* all stages of a pass inside ONE persistent kernel with device-side queues instead of one
                                   kernel per stage and bounce (lower fixed latency on very small frames, slower at full load) */
 
@@ -197,6 +198,10 @@ int vp_trace(vp_ctx* ctx, const VpRay* rays, const uint32_t* seeds, int n, int d
  * filled - time with CUDA events on the stream you passed). */
 int vp_stats_begin(vp_ctx* ctx);
 int vp_stats_end(vp_ctx* ctx, VpStats* stats);
+
+/* Sum of the device time of the extend-stage (k_wf_extend) launches made with VP_FLAG_TIME_STAGES since
+ * the previous call, and their number; synchronises the device. */
+int vp_stage_times(vp_ctx* ctx, double* extend_ms, uint64_t* extend_launches);
 
 /* Build/runtime facts for the harness: fills up to `cap` bytes of a JSON string. */
 int vp_info(vp_ctx* ctx, char* buf, int cap);

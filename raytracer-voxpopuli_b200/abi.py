@@ -76,6 +76,7 @@ VP_OK, VP_EINVAL, VP_ENODEVICE, VP_ECUDA, VP_ENOMEM, VP_ESTATE = 0, -1, -2, -3, 
 VP_FLAG_COUNT_STEPS = 1
 VP_FLAG_MEGAKERNEL = 2
 VP_FLAG_PERSISTENT = 4
+VP_FLAG_TIME_STAGES = 8
 
 HIT_DTYPE = np.dtype([("volume", "<i4"), ("cell", "<u4"), ("t", "<f4"), ("normal", "<f4", (3,)),
                       ("material", "u1"), ("face", "i1"), ("inside", "u1"), ("pad", "u1")])
@@ -86,7 +87,7 @@ assert HIT_DTYPE.itemsize == 28 and RAY_DTYPE.itemsize == 32
 ABI_SYMBOLS = [
     "create", "destroy", "last_error", "set_volumes", "update_volume_grid", "update_volume_transform",
     "set_materials", "set_lights", "set_prims", "set_sky", "render", "render_resident", "accum_reset",
-    "accum_download", "render_device", "trace_primary", "find_nearest", "is_occluded", "trace", "info", "stats_begin", "stats_end",
+    "accum_download", "render_device", "trace_primary", "find_nearest", "is_occluded", "trace", "info", "stats_begin", "stats_end", "stage_times",
 ]
 
 
@@ -136,6 +137,7 @@ class Lib:
         f("info", C.c_int, [C.c_void_p, C.c_char_p, C.c_int], optional=True)
         f("stats_begin", C.c_int, [C.c_void_p], optional=True)
         f("stats_end", C.c_int, [C.c_void_p, C.POINTER(VpStats)], optional=True)
+        f("stage_times", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)], optional=True)
 
     def _f(self, name, restype, argtypes, optional=False):
         try:

@@ -99,6 +99,10 @@ struct vp_ctx {
   int tune_persistent = 0;    // VP_PERSISTENT=1: persistent kernel instead of per-stage kernels
   int wf_blocks_persistent = 0;
   uint32_t last_error_word = 0;  // error word of the last persistent launch (valid after a stream sync)
+  // VP_FLAG_TIME_STAGES: CUDA-event pairs around every k_wf_extend launch, summed by vp_stage_times
+  std::vector<cudaEvent_t> tev;
+  size_t tev_used = 0;
+  bool time_stages_now = false;
 };
 
 namespace {
@@ -245,7 +249,16 @@ int launch_wavefront_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
   c->host_launches++;
   for (int it = 0; it <= p.max_bounces; it++) {
     p.iter = it;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->time_stages_now) {
+      if (c->tev_used + 2 > c->tev.size()) {
+        for (int k = 0; k < 64; k++) { cudaEvent_t e; CU(cudaEventCreate(&e)); c->tev.push_back(e); }
+      }
+      e0 = c->tev[c->tev_used++]; e1 = c->tev[c->tev_used++];
+      CU(cudaEventRecord(e0, stream));
+    }
     k_wf_extend<CS><<<c->wf_blocks_extend, kWfBlock, sm, stream>>>(p);
+    if (e1) CU(cudaEventRecord(e1, stream));
     if (it >= 2) CU(cudaStreamWaitEvent(stream, c->ev_shadow[it - 2], 0));  // shade(k) reuses the id queue of shadow(k-2)
     k_wf_shade<CS><<<wide, kWfBlock, sm, stream>>>(p);
     CU(cudaEventRecord(c->ev_shade[it], stream));
@@ -295,6 +308,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   p.accum = accum; p.rgb8 = rgb8; p.counters = c->d_counters.p; p.iter = 0;
   p.refill = c->tune_refill;
   p.persistent = 0;
+  c->time_stages_now = (fp->flags & VP_FLAG_TIME_STAGES) != 0;
   const bool staged = !((fp->flags & VP_FLAG_PERSISTENT) != 0 || c->tune_persistent);
   for (int s = 0; s < fp->spp; s++) {
     p.frame = fp->frame_index + (uint32_t)s;
@@ -442,6 +456,7 @@ void vp_destroy(vp_ctx* c)
   c->d_sph.release(); c->d_tri.release(); c->d_sky.release(); c->d_regions.release(); c->d_counters.release(); c->d_accum.release();
   c->d_wf.release();
   c->d_rgb8.release(); c->d_scratch_in.release(); c->d_scratch_out.release(); c->d_scratch_aux.release();
+  for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
   for (int i = 0; i < VP_MAX_LEVELS; i++) {
     if (c->ev_shade[i]) cudaEventDestroy(c->ev_shade[i]);
     if (c->ev_shadow[i]) cudaEventDestroy(c->ev_shadow[i]);
@@ -737,6 +752,23 @@ int vp_stats_end(vp_ctx* c, VpStats* stats)
   return 0;
 }
 
+int vp_stage_times(vp_ctx* c, double* extend_ms, uint64_t* extend_launches)
+{
+  if (!c || !extend_ms || !extend_launches) return fail(VP_EINVAL, "bad arguments to vp_stage_times");
+  if (bind(c)) return VP_ECUDA;
+  CU(cudaDeviceSynchronize());
+  double sum = 0;
+  for (size_t i = 0; i + 1 < c->tev_used; i += 2) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->tev[i], c->tev[i + 1]));
+    sum += ms;
+  }
+  *extend_ms = sum;
+  *extend_launches = c->tev_used / 2;
+  c->tev_used = 0;
+  return 0;
+}
+
 int vp_info(vp_ctx* c, char* buf, int cap)
 {
   if (!c || !buf || cap <= 0) return fail(VP_EINVAL, "bad arguments to vp_info");
@@ -754,10 +786,10 @@ int vp_info(vp_ctx* c, char* buf, int cap)
            "{\"device\": %d, \"name\": \"%s\", \"sm\": \"%d.%d\", \"sm_count\": %d, \"blocks_per_sm\": %d, \"block\": %d, "
            "\"k_render_regs\": %d, \"k_render_local_bytes\": %zu, \"k_wf_extend_regs\": %d, \"k_wf_shadow_regs\": %d, "
            "\"k_wf_shade_regs\": %d, \"wf_blocks_extend\": %d, \"wf_blocks_shadow\": %d, \"volumes\": %d, \"max_levels\": %d, "
-           "\"region_words_staged\": %d, \"dbg_extend_steps_in_empty_region\": %llu, \"dbg_extend_steps_in_empty_brick\": %llu}",
+           "\"region_words_staged\": %d, \"dbg_extend_steps_in_empty_region\": %llu, \"dbg_extend_steps_in_empty_brick\": %llu, \"extend_steps\": %llu}",
            c->device, prop.name, prop.major, prop.minor, c->sm_count, c->blocks_per_sm, kBlock, fa.numRegs, fa.localSizeBytes,
            fe.numRegs, fs.numRegs, fh.numRegs, c->wf_blocks_extend, c->wf_blocks_shadow, c->sc.nvol, VP_MAX_LEVELS,
-           c->sc.region_words, dbg[9], dbg[10]);
+           c->sc.region_words, dbg[9], dbg[10], dbg[11]);
   return 0;
 }
 

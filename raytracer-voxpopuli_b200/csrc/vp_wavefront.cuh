@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
     in_dda = s.t < tbest;
   }
   wf_add_counter(p.counters + 0, nrays);
-  if (CS) { wf_add_counter(p.counters + 3, steps); wf_add_counter(p.counters + 9, steps_er); wf_add_counter(p.counters + 10, steps_eb); }
+  if (CS) { wf_add_counter(p.counters + 3, steps); wf_add_counter(p.counters + 9, steps_er); wf_add_counter(p.counters + 10, steps_eb); wf_add_counter(p.counters + 11, steps); }
 }
 
 // ---- K3: shade = the material switch of Renderer::Trace (renderer.cpp:1092-1327) -------------------
