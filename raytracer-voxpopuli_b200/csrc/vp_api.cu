@@ -67,6 +67,9 @@ struct vp_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;  // shadow stage of the wavefront pipeline
+  cudaStream_t copy = nullptr;  // vp_render: accumulator upload, overlapped with the trace (only the resolve stage reads it)
+  cudaEvent_t ev_copy = nullptr;
+  bool wait_copy = false;       // the next resolve / k_render must wait for ev_copy
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_shade[VP_MAX_LEVELS] = {}, ev_shadow[VP_MAX_LEVELS] = {};
   std::vector<HostVolume> vols;
@@ -268,6 +271,7 @@ int launch_wavefront_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
     c->host_launches += 3;
   }
   for (int it = (p.max_bounces >= 1 ? p.max_bounces - 1 : 0); it <= p.max_bounces; it++) CU(cudaStreamWaitEvent(stream, c->ev_shadow[it], 0));
+  if (c->wait_copy) { CU(cudaStreamWaitEvent(stream, c->ev_copy, 0)); c->wait_copy = false; }
   k_wf_resolve<<<wide, kWfBlock, 0, stream>>>(p);
   c->host_launches++;
   CU(cudaGetLastError());
@@ -285,6 +289,7 @@ int launch_persistent_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
   CU(cudaMemsetAsync(p.st.pctl, 0, 256 * sizeof(uint32_t), stream));  // heads, tails, pending, error (kPrevTails kept for the clear above)
   k_wf_generate<<<wide, kWfBlock, 0, stream>>>(p);
   k_wf_persistent<CS><<<c->wf_blocks_persistent, kWfBlock, sm, stream>>>(p);
+  if (c->wait_copy) { CU(cudaStreamWaitEvent(stream, c->ev_copy, 0)); c->wait_copy = false; }
   k_wf_resolve<<<wide, kWfBlock, 0, stream>>>(p);
   c->host_launches += 4;
   CU(cudaGetLastError());
@@ -344,6 +349,7 @@ int launch_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float
   if (!mega) {
     if (int rc = launch_wavefront(c, cam, fp, accum, rgb8, stream)) return rc;
   } else {
+    if (c->wait_copy) { CU(cudaStreamWaitEvent(stream, c->ev_copy, 0)); c->wait_copy = false; }
     if (fp->flags & VP_FLAG_COUNT_STEPS) k_render<true><<<blocks, kBlock, smem_bytes(c), stream>>>(p);
     else k_render<false><<<blocks, kBlock, smem_bytes(c), stream>>>(p);
     c->host_launches++;
@@ -395,7 +401,9 @@ vp_ctx* vp_create(int device)
   vp_ctx* c = new vp_ctx;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  bool evok = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess;
+  bool evok = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < VP_MAX_LEVELS && evok; i++)
     evok = cudaEventCreateWithFlags(&c->ev_shade[i], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&c->ev_shadow[i], cudaEventDisableTiming) == cudaSuccess;
@@ -462,6 +470,8 @@ void vp_destroy(vp_ctx* c)
     if (c->ev_shadow[i]) cudaEventDestroy(c->ev_shadow[i]);
   }
   if (c->side) cudaStreamDestroy(c->side);
+  if (c->copy) cudaStreamDestroy(c->copy);
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -631,9 +641,13 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
   CU(c->d_accum.reserve(n));
   CU(c->d_rgb8.reserve(n));
   c->acc_w = fp->width; c->acc_h = fp->height;
-  CU(cudaMemcpyAsync(c->d_accum.p, accum, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  // the accumulator is only read by the resolve stage: upload it on the copy stream while the frame is traced
+  CU(cudaMemcpyAsync(c->d_accum.p, accum, n * sizeof(float4), cudaMemcpyHostToDevice, c->copy));
+  CU(cudaEventRecord(c->ev_copy, c->copy));
+  c->wait_copy = true;
   VpStats local;
   if (int rc = launch_render(c, cam, fp, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, stats ? stats : &local)) return rc;
+  if (c->wait_copy) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->wait_copy = false; }  // spp == 0: nothing consumed the upload
   CU(cudaMemcpyAsync(accum, c->d_accum.p, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
   if (rgb8) CU(cudaMemcpyAsync(rgb8, c->d_rgb8.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
