@@ -191,7 +191,7 @@ __device__ __forceinline__ void p_extend_session(const WfParams& p, const Staged
           uint32_t skipped = 0;
           const bool solid = occ_visit(region, fine, o, s, tbest, sparse, skipped);
           if (CS) steps += skipped;
-          if (solid) { tbest = s.t; pbest = s.P; volbest = vi - 1; }
+          if (solid) { tbest = s.t; s.t = __uint_as_float(kHitTag); }  // NaN tag: stops the walk, recovered below
           else if (!dda_step(s)) s.t = 3.0e38f;
         }
       }
@@ -199,6 +199,7 @@ __device__ __forceinline__ void p_extend_session(const WfParams& p, const Staged
       sparse = drained || act <= (unsigned)kBulkLanes;
       if (act < thr) break;
     }
+    if (__float_as_uint(s.t) == kHitTag) { pbest = s.P; volbest = vi - 1; s.t = 3.0e38f; }  // the cell the walk stopped on
     in_dda = s.t < tbest;
   }
   while (ring_n > 0u) {  // leaving the session: publish what is still in the ring

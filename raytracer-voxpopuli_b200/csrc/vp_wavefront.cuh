@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
           const bool solid = occ_visit(region, fine, o, s, tbest, sparse, skipped);
           if (CS) steps += skipped;
           if (CS) { if (o.rm == 0ull) steps_er += 1 + skipped; if (o.m == 0ull) steps_eb += 1 + skipped; }
-          if (solid) { tbest = s.t; pbest = s.P; volbest = vi - 1; }
+          if (solid) { tbest = s.t; s.t = __uint_as_float(kHitTag); }  // NaN tag: stops the walk, recovered below
           else if (!dda_step(s)) s.t = 3.0e38f;
         }
       }
@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
       sparse = drained || act <= (unsigned)kBulkLanes;
       if (act < thr) break;
     }
+    if (__float_as_uint(s.t) == kHitTag) { pbest = s.P; volbest = vi - 1; s.t = 3.0e38f; }  // the cell the walk stopped on
     in_dda = s.t < tbest;
   }
   wf_add_counter(p.counters + 0, nrays);
