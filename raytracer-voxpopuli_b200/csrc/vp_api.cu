@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -132,8 +133,35 @@ int build_masks(vp_ctx* c, HostVolume& v)
   return 0;
 }
 
+// world-space bounding sphere of the cube: corners mapped through the inverse of inv_matrix (fp64), 1 % + 1e-4 margin
+void bounding_sphere(const float* iM, const float* bmin, const float* bmax, float out[4])
+{
+  const double a = iM[0], b = iM[1], c = iM[2], d = iM[4], e = iM[5], f = iM[6], g = iM[8], h = iM[9], i = iM[10];
+  const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+  out[0] = out[1] = out[2] = 0.0f;
+  out[3] = INFINITY;
+  if (!(fabs(det) > 1e-30) || !std::isfinite(det)) return;
+  const double inv[9] = {(e * i - f * h) / det, (c * h - b * i) / det, (b * f - c * e) / det, (f * g - d * i) / det, (a * i - c * g) / det,
+                         (c * d - a * f) / det, (d * h - e * g) / det, (b * g - a * h) / det, (a * e - b * d) / det};
+  double P[8][3], ctr[3] = {0, 0, 0};
+  for (int k = 0; k < 8; k++) {
+    const double o[3] = {(k & 1 ? bmax[0] : bmin[0]) - iM[3], (k & 2 ? bmax[1] : bmin[1]) - iM[7], (k & 4 ? bmax[2] : bmin[2]) - iM[11]};
+    for (int r = 0; r < 3; r++) { P[k][r] = inv[3 * r] * o[0] + inv[3 * r + 1] * o[1] + inv[3 * r + 2] * o[2]; ctr[r] += P[k][r] / 8.0; }
+  }
+  double r2 = 0;
+  for (int k = 0; k < 8; k++) {
+    const double dx = P[k][0] - ctr[0], dy = P[k][1] - ctr[1], dz = P[k][2] - ctr[2];
+    r2 = fmax(r2, dx * dx + dy * dy + dz * dz);
+  }
+  const double r = sqrt(r2) * 1.01 + 1e-4;
+  if (!std::isfinite(r) || !std::isfinite(ctr[0] + ctr[1] + ctr[2])) return;
+  out[0] = (float)ctr[0]; out[1] = (float)ctr[1]; out[2] = (float)ctr[2];
+  out[3] = (float)(r * r);
+}
+
 void fill_dvolume(HostVolume& v, const float* M, const float* iM, const float* bmin, const float* bmax)
 {
+  bounding_sphere(iM, bmin, bmax, v.d.bsphere);
   memcpy(v.d.iM, iM, 12 * sizeof(float));
   memcpy(v.d.M, M, 12 * sizeof(float));
   memcpy(v.d.bmin, bmin, 12);

@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
     if (has_ray && !in_dda) {
       while (vi < nvol) {
         const DVolume& v = svol[vi];
+        if (nvol > 1 && !volume_may_hit(v, O, D)) { vi++; continue; }
         const ORay r = make_oray(xform_pos_sse(O, v.iM), xform_vec_sse(D, v.iM));
         vi++;
         if (setup_dda(v, r, s)) { in_dda = true; occ_reset(o); region = region_of(stg, v); fine = v.fine; break; }
@@ -582,6 +583,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
           bool entered = false;
           while (vi < nvol) {
             const DVolume& v = svol[vi];
+            if (nvol > 1 && !volume_may_hit(v, org, D)) { vi++; continue; }
             const ORay r = make_oray(xform_scalar(org, 1.0f, v.iM), xform_scalar(D, 0.0f, v.iM));
             vi++;
             if (setup_dda(v, r, s)) { entered = true; occ_reset(o); region = region_of(stg, v); fine = v.fine; break; }
