@@ -257,7 +257,8 @@ def main():
         e2e_t, e2e_rays = float(emax[0]), float(esum[1])
     e2e_value = e2e_rays / e2e_t / 1e6
     own_rows = sum(min(ROW_TILE, H - k * ROW_TILE) for k in tiles_r[rank])
-    h2d = W * H * 16  # the ABI takes and returns the full-frame accumulator / image
+    # vp_render moves only the rows a rank renders; summed over the ranks that is the whole frame
+    h2d = W * H * 16
     d2h = W * H * 16 + W * H * 4
 
     if rank != 0:

@@ -669,15 +669,34 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
   CU(c->d_accum.reserve(n));
   CU(c->d_rgb8.reserve(n));
   c->acc_w = fp->width; c->acc_h = fp->height;
+  // Only the rows this call renders are moved: a contiguous row range, or - with interleaved row tiles whose
+  // height divides the frame - one strided 2-D copy over the owned tiles (pitch = stride tiles).
+  const int rb = (fp->row_begin == 0 && fp->row_end == 0) ? 0 : fp->row_begin;
+  const int re = (fp->row_begin == 0 && fp->row_end == 0) ? fp->height : fp->row_end;
+  const bool tiled = fp->row_tile > 0 && fp->row_tile_stride > 1 && rb == 0 && re == fp->height && fp->height % fp->row_tile == 0;
+  const size_t W = (size_t)fp->width;
+  auto xfer = [&](void* dst, const void* src, size_t elem, cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
+    if (tiled) {
+      const size_t chunk = (size_t)fp->row_tile * W * elem, pitch = chunk * (size_t)fp->row_tile_stride;
+      const size_t ntile = (size_t)fp->height / fp->row_tile;
+      const size_t owned = (ntile - fp->row_tile_phase + fp->row_tile_stride - 1) / fp->row_tile_stride;
+      const size_t off = chunk * (size_t)fp->row_tile_phase;
+      if (owned == 0) return cudaSuccess;
+      return cudaMemcpy2DAsync((char*)dst + off, pitch, (const char*)src + off, pitch, chunk, owned, kind, st);
+    }
+    const size_t off = (size_t)rb * W * elem, bytes = (size_t)(re > rb ? re - rb : 0) * W * elem;
+    if (bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync((char*)dst + off, (const char*)src + off, bytes, kind, st);
+  };
   // the accumulator is only read by the resolve stage: upload it on the copy stream while the frame is traced
-  CU(cudaMemcpyAsync(c->d_accum.p, accum, n * sizeof(float4), cudaMemcpyHostToDevice, c->copy));
+  CU(xfer(c->d_accum.p, accum, sizeof(float4), cudaMemcpyHostToDevice, c->copy));
   CU(cudaEventRecord(c->ev_copy, c->copy));
   c->wait_copy = true;
   VpStats local;
   if (int rc = launch_render(c, cam, fp, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, stats ? stats : &local)) return rc;
   if (c->wait_copy) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->wait_copy = false; }  // spp == 0: nothing consumed the upload
-  CU(cudaMemcpyAsync(accum, c->d_accum.p, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-  if (rgb8) CU(cudaMemcpyAsync(rgb8, c->d_rgb8.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(xfer(accum, c->d_accum.p, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  if (rgb8) CU(xfer(rgb8, c->d_rgb8.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
