@@ -178,17 +178,39 @@ def main():
     sess.set_scene(sc)
     cc = cam.to_c()
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
-    rgb8 = torch.zeros((H, W), dtype=torch.int32, device=dev)
+    # frames in flight: a step is enqueued with VP_FLAG_DEFER, so its latency-bound tail overlaps the next step's wide
+    # first bounces; with several ranks the finished image of step k is gathered on a second stream meanwhile, hence
+    # one RGB8 image per frame in flight
+    NBUF = 3 if world > 1 else 1
+    rgb8s = [torch.zeros((H, W), dtype=torch.int32, device=dev) for _ in range(NBUF)]
+    rgb8 = rgb8s[0]
     stream = torch.cuda.current_stream(dev)
+    comm = torch.cuda.Stream(dev) if world > 1 else None
+    gathered = [None] * NBUF
     tiles_r = [sharding.tiles_of_rank(H, world, r) for r in range(world)]
     gather = sharding.FrameGather(rgb8, world, rank) if world > 1 else None
 
-    def step(i, stats=None, flags=0):
+    def fence(on, back=0):
+        lib.check(lib.c_render_fence(sess.ctx, on.cuda_stream, back), "render_fence")
+
+    def step(i, flags=abi.VP_FLAG_DEFER):
+        img = rgb8s[i % NBUF]
+        if gathered[i % NBUF] is not None:
+            stream.wait_event(gathered[i % NBUF])  # the gather that last read this image
         fp = frame_params(fpd, frame_index=i, flags=flags, **shard)
-        lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp), accum.data_ptr(), rgb8.data_ptr(), stream.cuda_stream,
-                                      C.byref(stats) if stats is not None else None), "render_device")
+        lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp), accum.data_ptr(), img.data_ptr(), stream.cuda_stream, None),
+                  "render_device")
         if world > 1:
-            gather(rgb8)  # pack own tiles -> one NCCL all_gather -> de-interleave: every rank ends with the image
+            with torch.cuda.stream(comm):
+                fence(comm)   # this frame resolved
+                gather(img)   # pack own tiles -> one NCCL all_gather -> de-interleave: every rank ends with the image
+                gathered[i % NBUF] = torch.cuda.Event()
+                gathered[i % NBUF].record(comm)
+
+    def drain():
+        if world > 1:
+            stream.wait_stream(comm)
+        fence(stream)
 
     # L2 flush between timed iterations (the frame's working set is far below the 126 MB L2)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -197,31 +219,37 @@ def main():
     sampler.start()
     for i in range(args.warmup):
         step(i)
+    drain()
     torch.cuda.synchronize(dev)
 
     lib.check(lib.c_stats_begin(sess.ctx), "stats_begin")
     sampler.mark()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    t_begin.record(stream)
     for i in range(args.steps):
         flush.fill_(float(i))
-        ev[i][0].record(stream)
-        # every 10th step also records CUDA events around its extend-stage launches (kept sparse: the extra
-        # event records cost ~6 % of a step when enabled on all of them)
-        step(args.warmup + i, flags=abi.VP_FLAG_TIME_STAGES if i % 10 == 0 else 0)
-        ev[i][1].record(stream)
+        if i % 10 == 0:
+            # every 10th step runs alone (pipeline drained, not deferred) with CUDA events around its extend-stage
+            # launches: the roofline's kernel duration is measured inside the timed region, without other frames'
+            # kernels sharing the SMs
+            drain()
+            step(args.warmup + i, flags=abi.VP_FLAG_TIME_STAGES)
+        else:
+            step(args.warmup + i)
+    drain()
+    t_end.record(stream)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(t_begin.elapsed_time(t_end))
     clocks = sampler.finish()
     st = abi.VpStats()
     lib.check(lib.c_stats_end(sess.ctx, C.byref(st)), "stats_end")
     ext_ms, ext_n = C.c_double(), C.c_uint64()
     lib.check(lib.c_stage_times(sess.ctx, C.byref(ext_ms), C.byref(ext_n)), "stage_times")
-    total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms, float(st.rays), float(st.kernel_launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -326,7 +354,9 @@ def main():
             "dtype": "f32", "data": "reference assets (room.vox grid fixture), synthetic camera/lights",
             "config": {"workload": scenes.WORKLOAD_NAMES[args.config], "resolution": [W, H], "spp_per_step": 1,
                        "rays_per_step": rays_total / args.steps, "sharding": f"interleaved {ROW_TILE}-row tiles x{world}" if world > 1 else "none",
-                       "l2": "flushed between timed iterations (256 MiB fill)"},
+                       "l2": "flushed between timed iterations (256 MiB fill, inside the timed region)",
+                       "frames_in_flight": 3, "timed_region": "one CUDA-event pair around all steps incl. the L2 flushes; every "
+                       "10th step runs alone with stage events (VP_FLAG_TIME_STAGES)"},
             "ms_per_frame": total_ms / args.steps,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

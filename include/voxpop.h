@@ -103,6 +103,11 @@ typedef struct VpFrameParams {
 #define VP_FLAG_COUNT_STEPS 1u /* also count DDA cell visits (instrumented kernel variant, slower) */
 #define VP_FLAG_MEGAKERNEL 2u  /* single-kernel path walk instead of the wavefront pipeline (A/B measurement) */
 #define VP_FLAG_TIME_STAGES 8u /* record CUDA events around every extend-stage launch (read with vp_stage_times) */
+#define VP_FLAG_DEFER 16u      /* vp_render_device with stats == NULL only: frames in flight.  The call enqueues the frame on the
+                                  library's own streams (after everything cuda_stream holds now) and returns WITHOUT making
+                                  cuda_stream wait for it, so the latency-bound tail of this frame overlaps the start of the next
+                                  call's.  Frames still resolve in call order (the accumulator is a running average).  Consume
+                                  accum/rgb8 only behind vp_render_fence; any non-deferred call also waits for all earlier ones. */
 #define VP_FLAG_PERSISTENT 4u  /* all stages of a pass inside ONE persistent kernel with device-side queues instead of one
                                   kernel per stage and bounce (lower fixed latency on very small frames, slower at full load) */
 
@@ -173,9 +178,15 @@ int vp_render(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, float* 
  * calls, e.g. a torch tensor that NCCL gathers afterwards).  accum_rgba_dev: W*H float4,
  * rgb8_dev: W*H uint32 or NULL.  cuda_stream: a cudaStream_t (NULL = default stream).
  * With stats == NULL the call only enqueues work and returns; otherwise it synchronises
- * the stream and fills the counters. */
+ * the stream and fills the counters.  The samples of one call (spp > 1) are pipelined over
+ * up to three internal stream pairs; cuda_stream orders the call: it starts after what the
+ * stream holds and (unless VP_FLAG_DEFER) the stream waits for its last resolve. */
 int vp_render_device(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, void* accum_rgba_dev, void* rgb8_dev,
                      void* cuda_stream, VpStats* stats);
+/* Makes cuda_stream wait until the render call issued `frames_back` calls ago (0 = the most recent one,
+ * at most 7) has resolved; with resolves in call order that covers every earlier call too.  Enqueue only,
+ * no host synchronisation.  Needed after VP_FLAG_DEFER calls; harmless otherwise. */
+int vp_render_fence(vp_ctx* ctx, void* cuda_stream, int frames_back);
 /* Library-owned resident accumulator: Renderer::accumulator kept in HBM between frames.
  * vp_accum_reset = allocate/zero (Renderer::ResetAccumulator, renderer.cpp:343-346, plus
  * the memset of Init :702); vp_render_resident = Update() on it; vp_accum_download

@@ -77,6 +77,7 @@ VP_FLAG_COUNT_STEPS = 1
 VP_FLAG_MEGAKERNEL = 2
 VP_FLAG_PERSISTENT = 4
 VP_FLAG_TIME_STAGES = 8
+VP_FLAG_DEFER = 16
 
 HIT_DTYPE = np.dtype([("volume", "<i4"), ("cell", "<u4"), ("t", "<f4"), ("normal", "<f4", (3,)),
                       ("material", "u1"), ("face", "i1"), ("inside", "u1"), ("pad", "u1")])
@@ -88,6 +89,7 @@ ABI_SYMBOLS = [
     "create", "destroy", "last_error", "set_volumes", "update_volume_grid", "update_volume_transform",
     "set_materials", "set_lights", "set_prims", "set_sky", "render", "render_resident", "accum_reset",
     "accum_download", "render_device", "trace_primary", "find_nearest", "is_occluded", "trace", "info", "stats_begin", "stats_end", "stage_times",
+    "render_fence",
 ]
 
 
@@ -138,6 +140,7 @@ class Lib:
         f("stats_begin", C.c_int, [C.c_void_p], optional=True)
         f("stats_end", C.c_int, [C.c_void_p, C.POINTER(VpStats)], optional=True)
         f("stage_times", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)], optional=True)
+        f("render_fence", C.c_int, [C.c_void_p, C.c_void_p, C.c_int], optional=True)
 
     def _f(self, name, restype, argtypes, optional=False):
         try:

@@ -63,16 +63,37 @@ struct DevBuf {
 
 }  // namespace
 
+// One frame in flight of the wavefront pipeline: its own stream pair, stage events and HBM-resident path state, so
+// that the latency-bound tail of one Update() pass overlaps the wide first bounces of the next one.
+struct WfLane {
+  cudaStream_t main = nullptr;  // generate, extend(k) -> shade(k), resolve
+  cudaStream_t side = nullptr;  // shadow stage
+  cudaEvent_t ev_done = nullptr;  // recorded after the lane's resolve
+  cudaEvent_t ev_shade[VP_MAX_LEVELS] = {}, ev_shadow[VP_MAX_LEVELS] = {};
+  WfState wf{};
+  DevBuf<unsigned char> d_wf;
+  uint32_t cap = 0;
+  int levels = 0, samples = 0;
+};
+constexpr int kLanes = 3;       // frames in flight
+constexpr int kCallRing = 8;    // completion events kept for vp_render_fence
+
 struct vp_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t side = nullptr;  // shadow stage of the wavefront pipeline
+  WfLane lane[kLanes];
+  int next_lane = 0;
+  cudaEvent_t ev_in = nullptr;      // recorded on the caller's stream when a render call enters
+  cudaEvent_t ev_direct = nullptr;  // recorded after a launch made directly on the caller's stream (single-kernel formulations)
+  bool direct_recorded = false;
+  cudaEvent_t ev_last = nullptr;    // most recent resolve (any lane or direct): resolves are chained through it
+  cudaEvent_t ev_call[kCallRing] = {};
+  unsigned long long ncalls = 0;
   cudaStream_t copy = nullptr;  // vp_render: accumulator upload, overlapped with the trace (only the resolve stage reads it)
   cudaEvent_t ev_copy = nullptr;
   bool wait_copy = false;       // the next resolve / k_render must wait for ev_copy
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t ev_shade[VP_MAX_LEVELS] = {}, ev_shadow[VP_MAX_LEVELS] = {};
   std::vector<HostVolume> vols;
   DevBuf<DVolume> d_vols;
   DevBuf<VpMaterial> d_mat;
@@ -92,11 +113,6 @@ struct vp_ctx {
   DScene sc{};
   bool have_volumes = false;
   int blocks_per_sm = 0;
-  // wavefront path state (HBM-resident, sized for the largest frame / depth seen)
-  WfState wf{};
-  DevBuf<unsigned char> d_wf;
-  uint32_t wf_cap = 0;
-  int wf_levels = 0, wf_samples = 0;
   int wf_blocks_extend = 0, wf_blocks_shadow = 0;
   unsigned long long host_launches = 0;
   int tune_refill = kRefill;  // VP_REFILL
@@ -232,12 +248,13 @@ int grid_blocks(const vp_ctx* c, long long work_warps)
   return (int)(need < full ? need : full);
 }
 
-int wf_reserve(vp_ctx* c, uint32_t cap, int levels, int samples)
+// path state of one lane (HBM-resident, sized for the largest frame / depth seen)
+int wf_reserve(WfLane& L, uint32_t cap, int levels, int samples)
 {
-  if (cap <= c->wf_cap && levels <= c->wf_levels && samples <= c->wf_samples && c->d_wf.p) return 0;
-  cap = cap > c->wf_cap ? cap : c->wf_cap;
-  levels = levels > c->wf_levels ? levels : c->wf_levels;
-  samples = samples > c->wf_samples ? samples : c->wf_samples;
+  if (cap <= L.cap && levels <= L.levels && samples <= L.samples && L.d_wf.p) return 0;
+  cap = cap > L.cap ? cap : L.cap;
+  levels = levels > L.levels ? levels : L.levels;
+  samples = samples > L.samples ? samples : L.samples;
   const size_t f4 = sizeof(float4);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -248,9 +265,9 @@ int wf_reserve(vp_ctx* c, uint32_t cap, int levels, int samples)
   const size_t o_pq = take(3 * pq_len * 4), o_pctl = take(kCtlWords * 4);
   const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_qs = take(2 * cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
   CU(cudaDeviceSynchronize());
-  CU(c->d_wf.reserve(off));
-  unsigned char* b = c->d_wf.p;
-  WfState& w = c->wf;
+  CU(L.d_wf.reserve(off));
+  unsigned char* b = L.d_wf.p;
+  WfState& w = L.wf;
   w.cap = cap;
   w.r0 = (float4*)(b + o_r0); w.r1 = (float4*)(b + o_r1); w.h0 = (float2*)(b + o_h0); w.h1 = (uint32_t*)(b + o_h1); w.hn = (float4*)(b + o_hn);
   w.term = (float4*)(b + o_term); w.lm = (float4*)(b + o_lm); w.la = (float4*)(b + o_la);
@@ -261,18 +278,21 @@ int wf_reserve(vp_ctx* c, uint32_t cap, int levels, int samples)
   w.pctl = (uint32_t*)(b + o_pctl);
   CU(cudaMemset(b + o_pq, 0xFF, 3 * pq_len * 4));  // all slots empty
   CU(cudaMemset(w.pctl, 0, kCtlWords * 4));
-  c->wf_cap = cap; c->wf_levels = levels; c->wf_samples = samples;
+  L.cap = cap; L.levels = levels; L.samples = samples;
   return 0;
 }
 
 // wavefront formulation: per pass  generate -> (extend, shade, shadow) x (max_bounces + 1) -> resolve
-// One Update() pass.  Main chain on `stream`: generate, then extend(k) -> shade(k) per bounce, resolve.
-// The shadow stage of bounce k only feeds the fold (level k's light term), so it runs on the context's
+// One Update() pass on lane L.  Main chain on L.main: generate, then extend(k) -> shade(k) per bounce, resolve.
+// The shadow stage of bounce k only feeds the fold (level k's light term), so it runs on the lane's
 // side stream, overlapping the tails of the next bounce's extend/shade; shade(k+2) waits for shadow(k)
-// before reusing its request buffer and resolve waits for all of them.
+// before reusing its request buffer and resolve waits for all of them.  Resolves of successive passes are
+// chained through c->ev_last (the accumulator is a running average: order matters); nothing else of a pass
+// depends on the previous one, which is what lets kLanes passes be in flight.
 template <bool CS>
-int launch_wavefront_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
+int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
 {
+  cudaStream_t stream = L.main;
   const size_t sm = smem_bytes(c);
   CU(cudaMemsetAsync(p.st.counts, 0, (size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t), stream));
   const int wide = c->sm_count * 8;
@@ -290,17 +310,20 @@ int launch_wavefront_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
     }
     k_wf_extend<CS><<<c->wf_blocks_extend, kWfBlock, sm, stream>>>(p);
     if (e1) CU(cudaEventRecord(e1, stream));
-    if (it >= 2) CU(cudaStreamWaitEvent(stream, c->ev_shadow[it - 2], 0));  // shade(k) reuses the id queue of shadow(k-2)
+    if (it >= 2) CU(cudaStreamWaitEvent(stream, L.ev_shadow[it - 2], 0));  // shade(k) reuses the id queue of shadow(k-2)
     k_wf_shade<CS><<<wide, kWfBlock, sm, stream>>>(p);
-    CU(cudaEventRecord(c->ev_shade[it], stream));
-    CU(cudaStreamWaitEvent(c->side, c->ev_shade[it], 0));
-    k_wf_shadow<CS><<<c->wf_blocks_shadow, kWfBlock, sm, c->side>>>(p);
-    CU(cudaEventRecord(c->ev_shadow[it], c->side));
+    CU(cudaEventRecord(L.ev_shade[it], stream));
+    CU(cudaStreamWaitEvent(L.side, L.ev_shade[it], 0));
+    k_wf_shadow<CS><<<c->wf_blocks_shadow, kWfBlock, sm, L.side>>>(p);
+    CU(cudaEventRecord(L.ev_shadow[it], L.side));
     c->host_launches += 3;
   }
-  for (int it = (p.max_bounces >= 1 ? p.max_bounces - 1 : 0); it <= p.max_bounces; it++) CU(cudaStreamWaitEvent(stream, c->ev_shadow[it], 0));
+  for (int it = (p.max_bounces >= 1 ? p.max_bounces - 1 : 0); it <= p.max_bounces; it++) CU(cudaStreamWaitEvent(stream, L.ev_shadow[it], 0));
   if (c->wait_copy) { CU(cudaStreamWaitEvent(stream, c->ev_copy, 0)); c->wait_copy = false; }
+  if (c->ev_last && c->ev_last != L.ev_done) CU(cudaStreamWaitEvent(stream, c->ev_last, 0));
   k_wf_resolve<<<wide, kWfBlock, 0, stream>>>(p);
+  CU(cudaEventRecord(L.ev_done, stream));
+  c->ev_last = L.ev_done;
   c->host_launches++;
   CU(cudaGetLastError());
   return 0;
@@ -324,15 +347,37 @@ int launch_persistent_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
   return 0;
 }
 
-int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream)
+// the caller's stream waits for every pass enqueued so far (resolves are chained, the last one covers all)
+int join_lanes(vp_ctx* c, cudaStream_t stream)
+{
+  if (c->ev_last) CU(cudaStreamWaitEvent(stream, c->ev_last, 0));
+  return 0;
+}
+
+// host-side wait for everything the lanes hold (scene edits, downloads, teardown)
+int quiesce(vp_ctx* c)
+{
+  for (WfLane& L : c->lane)
+    if (L.main) CU(cudaStreamSynchronize(L.main));
+  return 0;
+}
+
+// a launch made directly on the caller's stream is finished: later lane passes order themselves after it
+int mark_direct(vp_ctx* c, cudaStream_t stream)
+{
+  CU(cudaEventRecord(c->ev_direct, stream));
+  c->direct_recorded = true;
+  c->ev_last = c->ev_direct;
+  return 0;
+}
+
+int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream, bool overlap)
 {
   const uint32_t tiles = (uint32_t)((fp->width + 7) / 8) * (uint32_t)((fp->height + 3) / 4);
   const int levels = fp->max_bounces + 1 > 1 ? fp->max_bounces + 1 : 1;
   const int samples = c->sc.area_samples > 1 ? c->sc.area_samples : 1;
-  if (int rc = wf_reserve(c, tiles * 32u, levels, samples)) return rc;
   WfParams p;
-  p.sc = c->sc; p.cam = *cam; p.st = c->wf;
-  p.st.cap = tiles * 32u;  // paths of this frame (strides use the frame's own cap)
+  p.sc = c->sc; p.cam = *cam;
   p.W = fp->width; p.H = fp->height; p.max_bounces = fp->max_bounces;
   p.seed = fp->seed; p.aa = fp->aa_strength;
   p.row_begin = fp->row_begin; p.row_end = fp->row_end;
@@ -343,46 +388,89 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   p.persistent = 0;
   c->time_stages_now = (fp->flags & VP_FLAG_TIME_STAGES) != 0;
   const bool staged = !((fp->flags & VP_FLAG_PERSISTENT) != 0 || c->tune_persistent);
+  const bool cs = (fp->flags & VP_FLAG_COUNT_STEPS) != 0;
+  if (staged) CU(cudaEventRecord(c->ev_in, stream));
+  else if (int rc = join_lanes(c, stream)) return rc;
+  bool entered[kLanes] = {};
   for (int s = 0; s < fp->spp; s++) {
     p.frame = fp->frame_index + (uint32_t)s;
     p.write_rgb8 = (s == fp->spp - 1);
-    const bool cs = (fp->flags & VP_FLAG_COUNT_STEPS) != 0;
     int rc;
-    if (staged) rc = cs ? launch_wavefront_pass<true>(c, p, stream) : launch_wavefront_pass<false>(c, p, stream);
-    else rc = cs ? launch_persistent_pass<true>(c, p, stream) : launch_persistent_pass<false>(c, p, stream);
+    if (staged) {
+      // lanes rotate only when passes can overlap (several samples in this call, or a deferred call)
+      const int li = (overlap || fp->spp > 1) ? (c->next_lane++ % kLanes) : 0;
+      WfLane& L = c->lane[li];
+      if ((rc = wf_reserve(L, tiles * 32u, levels, samples))) return rc;
+      if (!entered[li]) {
+        CU(cudaStreamWaitEvent(L.main, c->ev_in, 0));
+        if (c->direct_recorded) CU(cudaStreamWaitEvent(L.main, c->ev_direct, 0));
+        entered[li] = true;
+      }
+      p.st = L.wf;
+      p.st.cap = tiles * 32u;  // paths of this frame (strides use the frame's own cap)
+      rc = cs ? launch_wavefront_pass<true>(c, L, p) : launch_wavefront_pass<false>(c, L, p);
+    } else {
+      WfLane& L = c->lane[0];
+      if ((rc = wf_reserve(L, tiles * 32u, levels, samples))) return rc;
+      p.st = L.wf;
+      p.st.cap = tiles * 32u;
+      rc = cs ? launch_persistent_pass<true>(c, p, stream) : launch_persistent_pass<false>(c, p, stream);
+    }
     if (rc) return rc;
   }
-  if (!staged) CU(cudaMemcpyAsync(&c->last_error_word, c->wf.pctl + kError, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  if (!staged) {
+    CU(cudaMemcpyAsync(&c->last_error_word, c->lane[0].wf.pctl + kError, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    if (int rc = mark_direct(c, stream)) return rc;
+  }
   return 0;
 }
 
-// core: enqueue the render kernel on `stream` for device buffers
+// core: enqueue one render call (fp->spp Update() passes) for device buffers.  Work runs on the context's lanes; the
+// caller's `stream` orders it: the passes start after what the stream holds now, and - unless the call is deferred
+// (VP_FLAG_DEFER without stats) - the stream waits for the last resolve before anything enqueued later.
 int launch_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream,
-                  VpStats* stats)
+                  VpStats* stats, bool allow_defer)
 {
   RenderParams p;
   fill_params(c, cam, fp, p);
   p.accum = accum; p.rgb8 = rgb8;
+  const bool defer = allow_defer && !stats && (fp->flags & VP_FLAG_DEFER) != 0;
   unsigned long long before[8] = {0};
   if (stats) {
+    if (int rc = join_lanes(c, stream)) return rc;
     CU(cudaMemcpyAsync(before, c->d_counters.p, sizeof(before), cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
   }
-  CU(cudaMemsetAsync(c->d_counters.p + 8, 0, sizeof(unsigned long long), stream));
   const long long tiles = (long long)((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
   const int blocks = grid_blocks(c, tiles);
   const unsigned long long launches_before = c->host_launches;
   if (stats) CU(cudaEventRecord(c->ev0, stream));
   const bool mega = (fp->flags & VP_FLAG_MEGAKERNEL) || c->sc.area_samples > kMaxAreaSamples || fp->max_bounces < 0;
   if (!mega) {
-    if (int rc = launch_wavefront(c, cam, fp, accum, rgb8, stream)) return rc;
+    if (int rc = launch_wavefront(c, cam, fp, accum, rgb8, stream, defer)) return rc;
   } else {
+    if (int rc = join_lanes(c, stream)) return rc;
+    CU(cudaMemsetAsync(c->d_counters.p + 8, 0, sizeof(unsigned long long), stream));
     if (c->wait_copy) { CU(cudaStreamWaitEvent(stream, c->ev_copy, 0)); c->wait_copy = false; }
     if (fp->flags & VP_FLAG_COUNT_STEPS) k_render<true><<<blocks, kBlock, smem_bytes(c), stream>>>(p);
     else k_render<false><<<blocks, kBlock, smem_bytes(c), stream>>>(p);
     c->host_launches++;
+    if (int rc = mark_direct(c, stream)) return rc;
   }
   CU(cudaGetLastError());
+  // completion event of this call (vp_render_fence), then the join
+  cudaEvent_t done = c->ev_call[c->ncalls % kCallRing];
+  c->ncalls++;
+  if (c->ev_last && c->ev_last != c->ev_direct) {
+    // the last resolve sits on a lane: find it and record behind it
+    cudaStream_t at = stream;
+    for (WfLane& L : c->lane)
+      if (L.ev_done == c->ev_last) at = L.main;
+    CU(cudaEventRecord(done, at));
+  } else {
+    CU(cudaEventRecord(done, stream));
+  }
+  if (!defer) CU(cudaStreamWaitEvent(stream, done, 0));
   if (stats) {
     CU(cudaEventRecord(c->ev1, stream));
     unsigned long long h[8];
@@ -429,12 +517,19 @@ vp_ctx* vp_create(int device)
   vp_ctx* c = new vp_ctx;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  bool evok = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess;
-  for (int i = 0; i < VP_MAX_LEVELS && evok; i++)
-    evok = cudaEventCreateWithFlags(&c->ev_shade[i], cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&c->ev_shadow[i], cudaEventDisableTiming) == cudaSuccess;
+  bool evok = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_direct, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < kCallRing && evok; i++) evok = cudaEventCreateWithFlags(&c->ev_call[i], cudaEventDisableTiming) == cudaSuccess;
+  for (WfLane& L : c->lane) {
+    evok = evok && cudaStreamCreateWithFlags(&L.main, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < VP_MAX_LEVELS && evok; i++)
+      evok = cudaEventCreateWithFlags(&L.ev_shade[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&L.ev_shadow[i], cudaEventDisableTiming) == cudaSuccess;
+  }
   if (!evok || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
       cudaEventCreate(&c->ev1) != cudaSuccess || c->d_counters.reserve(16) != cudaSuccess ||
       cudaMemset(c->d_counters.p, 0, 16 * sizeof(unsigned long long)) != cudaSuccess) {
@@ -487,17 +582,26 @@ void vp_destroy(vp_ctx* c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
   for (auto& v : c->vols) free_volume(v);
   c->d_vols.release(); c->d_mat.release(); c->d_pl.release(); c->d_al.release(); c->d_sl.release();
   c->d_sph.release(); c->d_tri.release(); c->d_sky.release(); c->d_regions.release(); c->d_counters.release(); c->d_accum.release();
-  c->d_wf.release();
   c->d_rgb8.release(); c->d_scratch_in.release(); c->d_scratch_out.release(); c->d_scratch_aux.release();
   for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
-  for (int i = 0; i < VP_MAX_LEVELS; i++) {
-    if (c->ev_shade[i]) cudaEventDestroy(c->ev_shade[i]);
-    if (c->ev_shadow[i]) cudaEventDestroy(c->ev_shadow[i]);
+  for (WfLane& L : c->lane) {
+    L.d_wf.release();
+    for (int i = 0; i < VP_MAX_LEVELS; i++) {
+      if (L.ev_shade[i]) cudaEventDestroy(L.ev_shade[i]);
+      if (L.ev_shadow[i]) cudaEventDestroy(L.ev_shadow[i]);
+    }
+    if (L.ev_done) cudaEventDestroy(L.ev_done);
+    if (L.side) cudaStreamDestroy(L.side);
+    if (L.main) cudaStreamDestroy(L.main);
   }
-  if (c->side) cudaStreamDestroy(c->side);
+  for (cudaEvent_t e : c->ev_call)
+    if (e) cudaEventDestroy(e);
+  if (c->ev_in) cudaEventDestroy(c->ev_in);
+  if (c->ev_direct) cudaEventDestroy(c->ev_direct);
   if (c->copy) cudaStreamDestroy(c->copy);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -510,7 +614,7 @@ int vp_set_volumes(vp_ctx* c, const VpVolume* vols, int n)
 {
   if (!c || n < 0 || (n > 0 && !vols)) return fail(VP_EINVAL, "bad arguments to vp_set_volumes");
   if ((size_t)n * sizeof(DVolume) + 16 > 64 * 1024) return fail(VP_EINVAL, "too many volumes (%d)", n);
-  if (bind(c)) return VP_ECUDA;
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
   for (int i = 0; i < n; i++)
     if (!vols[i].grid || vols[i].n == 0 || vols[i].n > 512) return fail(VP_EINVAL, "volume %d: bad grid pointer or size %u", i, vols[i].n);
   for (auto& v : c->vols) free_volume(v);
@@ -552,7 +656,7 @@ int vp_update_volume_grid(vp_ctx* c, int vi, uint32_t offset, uint32_t len, cons
   HostVolume& v = c->vols[vi];
   const size_t total = (size_t)v.n * v.n * v.n;
   if ((size_t)offset + len > total) return fail(VP_EINVAL, "dirty range [%u,+%u) exceeds grid of %zu bytes", offset, len, total);
-  if (bind(c)) return VP_ECUDA;
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
   CU(cudaMemcpyAsync(v.grid + offset, bytes, len, cudaMemcpyHostToDevice, c->stream));
   if (build_masks(c, v)) return VP_ECUDA;
   CU(cudaStreamSynchronize(c->stream));
@@ -562,7 +666,7 @@ int vp_update_volume_grid(vp_ctx* c, int vi, uint32_t offset, uint32_t len, cons
 int vp_update_volume_transform(vp_ctx* c, int vi, const float M[16], const float iM[16], const float bmin[3], const float bmax[3])
 {
   if (!c || vi < 0 || vi >= (int)c->vols.size() || !M || !iM || !bmin || !bmax) return fail(VP_EINVAL, "bad arguments to vp_update_volume_transform");
-  if (bind(c)) return VP_ECUDA;
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
   fill_dvolume(c->vols[vi], M, iM, bmin, bmax);
   return upload_volume_table(c);
 }
@@ -570,7 +674,7 @@ int vp_update_volume_transform(vp_ctx* c, int vi, const float M[16], const float
 int vp_set_materials(vp_ctx* c, const VpMaterial* m, int n)
 {
   if (!c || !m || n < 0 || n > VP_MAX_MATERIALS) return fail(VP_EINVAL, "bad arguments to vp_set_materials (n=%d)", n);
-  if (bind(c)) return VP_ECUDA;
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
   if (n > 0) CU(cudaMemcpyAsync(c->d_mat.p, m, sizeof(VpMaterial) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
@@ -580,7 +684,7 @@ int vp_set_lights(vp_ctx* c, const VpPointLight* p, int np, const VpAreaLight* a
                   const VpDirLight* d, int area_samples)
 {
   if (!c || np < 0 || na < 0 || ns < 0 || (np && !p) || (na && !a) || (ns && !s)) return fail(VP_EINVAL, "bad arguments to vp_set_lights");
-  if (bind(c)) return VP_ECUDA;
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
   if (upload_array(c, c->d_pl, p, np) || upload_array(c, c->d_al, a, na) || upload_array(c, c->d_sl, s, ns)) return VP_ECUDA;
   c->sc.pl = c->d_pl.p; c->sc.npl = np;
   c->sc.al = c->d_al.p; c->sc.nal = na;
@@ -593,7 +697,7 @@ int vp_set_lights(vp_ctx* c, const VpPointLight* p, int np, const VpAreaLight* a
 int vp_set_prims(vp_ctx* c, const VpSphere* s, int ns, const VpTriangle* t, int nt)
 {
   if (!c || ns < 0 || nt < 0 || (ns && !s) || (nt && !t)) return fail(VP_EINVAL, "bad arguments to vp_set_prims");
-  if (bind(c)) return VP_ECUDA;
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
   if (upload_array(c, c->d_sph, s, ns) || upload_array(c, c->d_tri, t, nt)) return VP_ECUDA;
   c->sc.sph = c->d_sph.p; c->sc.nsph = ns;
   c->sc.tri = c->d_tri.p; c->sc.ntri = nt;
@@ -603,7 +707,7 @@ int vp_set_prims(vp_ctx* c, const VpSphere* s, int ns, const VpTriangle* t, int 
 int vp_set_sky(vp_ctx* c, const float* rgb, int w, int h, float contribution, int active)
 {
   if (!c || w < 0 || h < 0) return fail(VP_EINVAL, "bad arguments to vp_set_sky");
-  if (bind(c)) return VP_ECUDA;
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
   const bool have = rgb && w > 0 && h > 0;
   if (have) {
     const size_t n = (size_t)w * h * 3;
@@ -624,13 +728,22 @@ int vp_render_device(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, vo
   if (int rc = check_frame(c, cam, fp)) return rc;
   if (!accum_dev) return fail(VP_EINVAL, "null accumulator");
   if (bind(c)) return VP_ECUDA;
-  return launch_render(c, cam, fp, (float4*)accum_dev, (uint32_t*)rgb8_dev, (cudaStream_t)stream, stats);
+  return launch_render(c, cam, fp, (float4*)accum_dev, (uint32_t*)rgb8_dev, (cudaStream_t)stream, stats, true);
+}
+
+int vp_render_fence(vp_ctx* c, void* stream, int frames_back)
+{
+  if (!c || frames_back < 0 || frames_back >= kCallRing) return fail(VP_EINVAL, "bad arguments to vp_render_fence (frames_back %d, at most %d)", frames_back, kCallRing - 1);
+  if (bind(c)) return VP_ECUDA;
+  if ((unsigned long long)frames_back >= c->ncalls) return 0;  // nothing that old was ever enqueued
+  CU(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_call[(c->ncalls - 1 - (unsigned long long)frames_back) % kCallRing], 0));
+  return 0;
 }
 
 int vp_accum_reset(vp_ctx* c, int w, int h)
 {
   if (!c || w <= 0 || h <= 0) return fail(VP_EINVAL, "bad arguments to vp_accum_reset");
-  if (bind(c)) return VP_ECUDA;
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
   const size_t n = (size_t)w * h;
   CU(c->d_accum.reserve(n));
   CU(c->d_rgb8.reserve(n));
@@ -646,13 +759,13 @@ int vp_render_resident(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, 
   if (int rc = check_frame(c, cam, fp)) return rc;
   if (c->acc_w != fp->width || c->acc_h != fp->height) return fail(VP_ESTATE, "vp_accum_reset(%d,%d) must precede vp_render_resident", fp->width, fp->height);
   if (bind(c)) return VP_ECUDA;
-  return launch_render(c, cam, fp, c->d_accum.p, c->d_rgb8.p, c->stream, stats);
+  return launch_render(c, cam, fp, c->d_accum.p, c->d_rgb8.p, c->stream, stats, false);
 }
 
 int vp_accum_download(vp_ctx* c, float* accum, uint32_t* rgb8)
 {
   if (!c || c->acc_w <= 0) return fail(VP_ESTATE, "no resident accumulator");
-  if (bind(c)) return VP_ECUDA;
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
   const size_t n = (size_t)c->acc_w * c->acc_h;
   if (accum) CU(cudaMemcpyAsync(accum, c->d_accum.p, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
   if (rgb8) CU(cudaMemcpyAsync(rgb8, c->d_rgb8.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -664,7 +777,7 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
 {
   if (int rc = check_frame(c, cam, fp)) return rc;
   if (!accum) return fail(VP_EINVAL, "null accumulator");
-  if (bind(c)) return VP_ECUDA;
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
   const size_t n = (size_t)fp->width * fp->height;
   CU(c->d_accum.reserve(n));
   CU(c->d_rgb8.reserve(n));
@@ -693,7 +806,7 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
   CU(cudaEventRecord(c->ev_copy, c->copy));
   c->wait_copy = true;
   VpStats local;
-  if (int rc = launch_render(c, cam, fp, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, stats ? stats : &local)) return rc;
+  if (int rc = launch_render(c, cam, fp, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, stats ? stats : &local, false)) return rc;
   if (c->wait_copy) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->wait_copy = false; }  // spp == 0: nothing consumed the upload
   CU(xfer(accum, c->d_accum.p, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
   if (rgb8) CU(xfer(rgb8, c->d_rgb8.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));

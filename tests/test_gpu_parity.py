@@ -255,3 +255,50 @@ def test_cpp_renderer_mirror(product, oracle):
         want, want_rgb, st = s.render(cam, vp.frame_params(W, H, max_bounces=mb, spp=frames))
     check_accum(acc, want, "C++ mirror")
     assert np.count_nonzero(rgb != want_rgb) == 0 and rays.value == st.rays
+
+
+def test_frames_in_flight(product, oracle):
+    """vp_render_device with VP_FLAG_DEFER: several frames overlap on the library's stream pairs; they must resolve
+    in call order, i.e. give the accumulator of the same frames rendered one after the other (oracle: one call
+    with spp = number of frames).  Mixes deferred single-sample calls, a multi-sample call (more samples than
+    lanes), a non-deferred call with stats in the middle and a scene edit (which has to wait for the frames)."""
+    import torch
+    sc, cam, fpd = small_config(2, 160, 90)
+    W, H = fpd["width"], fpd["height"]
+    plan = [(1, True), (1, True), (1, True), (1, True), (5, True), (1, False), (1, True), (2, True), (1, True)]
+    total = sum(n for n, _ in plan)
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        want, want_rgb, st_want = s.render(cam, params(fpd, spp=total))
+    dev = torch.device("cuda", 0)
+    acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    rgb = torch.zeros((H, W), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    cc = cam.to_c()
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        product.check(product.c_stats_begin(s.ctx), "stats_begin")
+        frame = 0
+        for n, defer in plan:
+            fp = params(fpd, spp=n, frame_index=frame, flags=abi.VP_FLAG_DEFER if defer else 0)
+            st = None if defer else abi.VpStats()
+            product.check(product.c_render_device(s.ctx, C.byref(cc), C.byref(fp), acc.data_ptr(), rgb.data_ptr(), stream.cuda_stream,
+                                                  C.byref(st) if st is not None else None), "render_device")
+            frame += n
+        product.check(product.c_render_fence(s.ctx, stream.cuda_stream, 0), "render_fence")
+        got = acc.cpu().numpy()
+        got_rgb = rgb.cpu().numpy().view(np.uint32)
+        tot = abi.VpStats()
+        product.check(product.c_stats_end(s.ctx, C.byref(tot)), "stats_end")
+        assert tot.rays == st_want.rays
+        # a scene edit while frames are in flight waits for them, and later frames see the edit
+        for i in range(3):
+            fp = params(fpd, spp=1, frame_index=100 + i, flags=abi.VP_FLAG_DEFER)
+            product.check(product.c_render_device(s.ctx, C.byref(cc), C.byref(fp), acc.data_ptr(), rgb.data_ptr(), stream.cuda_stream, None),
+                          "render_device")
+        s.set_scene(sc)
+        assert product.c_render_fence(s.ctx, stream.cuda_stream, 8) != 0  # older than the ring of completion events
+        product.check(product.c_render_fence(s.ctx, stream.cuda_stream, 7), "render_fence")
+        torch.cuda.synchronize(dev)
+    assert np.array_equal(bits(got), bits(want)), "frames in flight changed the accumulator"
+    assert np.array_equal(got_rgb, want_rgb)
