@@ -212,6 +212,7 @@ def main():
             stream.wait_stream(comm)
         fence(stream)
 
+    STAGE_EVERY = 20
     # L2 flush between timed iterations (the frame's working set is far below the 126 MB L2)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
@@ -231,8 +232,8 @@ def main():
     t_begin.record(stream)
     for i in range(args.steps):
         flush.fill_(float(i))
-        if i % 10 == 0:
-            # every 10th step runs alone (pipeline drained, not deferred) with CUDA events around its extend-stage
+        if i % STAGE_EVERY == 0:
+            # every 20th step runs alone (pipeline drained, not deferred) with CUDA events around its extend-stage
             # launches: the roofline's kernel duration is measured inside the timed region, without other frames'
             # kernels sharing the SMs
             drain()
@@ -316,7 +317,7 @@ def main():
     own_rows = sum(min(ROW_TILE, H - k * ROW_TILE) for k in tiles_r[rank])
     px_rank = own_rows * W if world > 1 else W * H
     ext_rays = inst.primary_rays + inst.secondary_rays
-    timed_steps = len(range(0, args.steps, 10))
+    timed_steps = len(range(0, args.steps, STAGE_EVERY))
     ext_launches_per_frame = max(1, ext_n.value // max(1, timed_steps))
     ext_bytes_frame = meta["extend_steps"] * 1 + ext_rays * nvol * 128
     frame_bytes = inst.dda_steps * 1 + (inst.rays + inst.exit_rays) * nvol * 128 + px_rank * 32 + px_rank * 4 + inst.sky_samples * 12
@@ -355,8 +356,8 @@ def main():
             "config": {"workload": scenes.WORKLOAD_NAMES[args.config], "resolution": [W, H], "spp_per_step": 1,
                        "rays_per_step": rays_total / args.steps, "sharding": f"interleaved {ROW_TILE}-row tiles x{world}" if world > 1 else "none",
                        "l2": "flushed between timed iterations (256 MiB fill, inside the timed region)",
-                       "frames_in_flight": 3, "timed_region": "one CUDA-event pair around all steps incl. the L2 flushes; every "
-                       "10th step runs alone with stage events (VP_FLAG_TIME_STAGES)"},
+                       "frames_in_flight": 4, "timed_region": "one CUDA-event pair around all steps incl. the L2 flushes; every "
+                       "20th step runs alone with stage events (VP_FLAG_TIME_STAGES)"},
             "ms_per_frame": total_ms / args.steps,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

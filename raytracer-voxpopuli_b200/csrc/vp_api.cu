@@ -75,7 +75,7 @@ struct WfLane {
   uint32_t cap = 0;
   int levels = 0, samples = 0;
 };
-constexpr int kLanes = 3;       // frames in flight
+constexpr int kLanes = 6;       // most frames in flight (c->nlanes are used: 4 unless VP_LANES says otherwise)
 constexpr int kCallRing = 8;    // completion events kept for vp_render_fence
 
 struct vp_ctx {
@@ -84,6 +84,7 @@ struct vp_ctx {
   cudaStream_t stream = nullptr;
   WfLane lane[kLanes];
   int next_lane = 0;
+  int nlanes = 4;
   cudaEvent_t ev_in = nullptr;      // recorded on the caller's stream when a render call enters
   cudaEvent_t ev_direct = nullptr;  // recorded after a launch made directly on the caller's stream (single-kernel formulations)
   bool direct_recorded = false;
@@ -113,9 +114,12 @@ struct vp_ctx {
   DScene sc{};
   bool have_volumes = false;
   int blocks_per_sm = 0;
-  int wf_blocks_extend = 0, wf_blocks_shadow = 0;
+  int wf_blocks_extend = 0, wf_blocks_shadow = 0;  // persistent grids at full load (occupancy x SMs)
+  int wf_grid_extend = 0, wf_grid_shadow = 0;      // grids of the current call (smaller for small shards)
+  bool wf_blocks_fixed = false;                    // VP_BLOCKS_* given: no per-call sizing
   unsigned long long host_launches = 0;
   int tune_refill = kRefill;  // VP_REFILL
+  int tune_bulk = kBulkLanes; // VP_BULK_LANES
   int tune_persistent = 0;    // VP_PERSISTENT=1: persistent kernel instead of per-stage kernels
   int wf_blocks_persistent = 0;
   uint32_t last_error_word = 0;  // error word of the last persistent launch (valid after a stream sync)
@@ -308,13 +312,13 @@ int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
       e0 = c->tev[c->tev_used++]; e1 = c->tev[c->tev_used++];
       CU(cudaEventRecord(e0, stream));
     }
-    k_wf_extend<CS><<<c->wf_blocks_extend, kWfBlock, sm, stream>>>(p);
+    k_wf_extend<CS><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
     if (e1) CU(cudaEventRecord(e1, stream));
     if (it >= 2) CU(cudaStreamWaitEvent(stream, L.ev_shadow[it - 2], 0));  // shade(k) reuses the id queue of shadow(k-2)
     k_wf_shade<CS><<<wide, kWfBlock, sm, stream>>>(p);
     CU(cudaEventRecord(L.ev_shade[it], stream));
     CU(cudaStreamWaitEvent(L.side, L.ev_shade[it], 0));
-    k_wf_shadow<CS><<<c->wf_blocks_shadow, kWfBlock, sm, L.side>>>(p);
+    k_wf_shadow<CS><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
     CU(cudaEventRecord(L.ev_shadow[it], L.side));
     c->host_launches += 3;
   }
@@ -385,20 +389,41 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   p.row_tile = fp->row_tile; p.row_tile_stride = fp->row_tile_stride; p.row_tile_phase = fp->row_tile_phase;
   p.accum = accum; p.rgb8 = rgb8; p.counters = c->d_counters.p; p.iter = 0;
   p.refill = c->tune_refill;
+  p.bulk = c->tune_bulk;
   p.persistent = 0;
   c->time_stages_now = (fp->flags & VP_FLAG_TIME_STAGES) != 0;
+  // Persistent grids follow the number of paths this call can have: a warp that gets only ~1 ray per lane never refills
+  // and ends at the SIMD efficiency of its longest ray, so small shards run fewer, longer-lived warps (>= 3 blocks per SM
+  // to keep latency hidden; measured on 1/8 frame shares, profiles/README.md).
+  {
+    long long rows = 0;
+    for (int y = p.row_begin; y < p.row_end && y < fp->height; y++)
+      if (y >= 0 && (p.row_tile <= 0 || ((y / p.row_tile) % p.row_tile_stride) == p.row_tile_phase)) rows++;
+    const long long paths = rows * (long long)fp->width;
+    const long long per_sm = (long long)kWfBlock * 8 * c->sm_count;
+    long long want = (paths + per_sm - 1) / per_sm;
+    if (want < 3) want = 3;
+    const long long we = want * c->sm_count < c->wf_blocks_extend ? want * c->sm_count : c->wf_blocks_extend;
+    const long long ws = want * c->sm_count < c->wf_blocks_shadow ? want * c->sm_count : c->wf_blocks_shadow;
+    const bool full = c->wf_blocks_fixed || !(overlap || fp->spp > 1);  // a lone pass wants the lowest latency: full grid
+    c->wf_grid_extend = full ? c->wf_blocks_extend : (int)we;
+    c->wf_grid_shadow = full ? c->wf_blocks_shadow : (int)ws;
+  }
   const bool staged = !((fp->flags & VP_FLAG_PERSISTENT) != 0 || c->tune_persistent);
   const bool cs = (fp->flags & VP_FLAG_COUNT_STEPS) != 0;
   if (staged) CU(cudaEventRecord(c->ev_in, stream));
   else if (int rc = join_lanes(c, stream)) return rc;
   bool entered[kLanes] = {};
+  if (staged && overlap)  // frames in flight: size every lane now rather than one per call (allocation synchronises the device)
+    for (int i = 0; i < c->nlanes; i++)
+      if (int rc = wf_reserve(c->lane[i], tiles * 32u, levels, samples)) return rc;
   for (int s = 0; s < fp->spp; s++) {
     p.frame = fp->frame_index + (uint32_t)s;
     p.write_rgb8 = (s == fp->spp - 1);
     int rc;
     if (staged) {
       // lanes rotate only when passes can overlap (several samples in this call, or a deferred call)
-      const int li = (overlap || fp->spp > 1) ? (c->next_lane++ % kLanes) : 0;
+      const int li = (overlap || fp->spp > 1) ? (c->next_lane++ % c->nlanes) : 0;
       WfLane& L = c->lane[li];
       if ((rc = wf_reserve(L, tiles * 32u, levels, samples))) return rc;
       if (!entered[li]) {
@@ -572,9 +597,11 @@ vp_ctx* vp_create(int device)
   c->wf_blocks_persistent = occ * c->sm_count;
   if (const char* e = getenv("VP_PERSISTENT")) c->tune_persistent = atoi(e);
   if (const char* e = getenv("VP_BLOCKS_PERSISTENT")) c->wf_blocks_persistent = atoi(e) * c->sm_count;
+  if (const char* e = getenv("VP_LANES")) { const int n = atoi(e); c->nlanes = n < 1 ? 1 : (n > kLanes ? kLanes : n); }
+  if (const char* e = getenv("VP_BULK_LANES")) c->tune_bulk = atoi(e);
   if (const char* e = getenv("VP_REFILL")) c->tune_refill = atoi(e);
-  if (const char* e = getenv("VP_BLOCKS_EXTEND")) c->wf_blocks_extend = atoi(e) * c->sm_count;
-  if (const char* e = getenv("VP_BLOCKS_SHADOW")) c->wf_blocks_shadow = atoi(e) * c->sm_count;
+  if (const char* e = getenv("VP_BLOCKS_EXTEND")) { c->wf_blocks_extend = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
+  if (const char* e = getenv("VP_BLOCKS_SHADOW")) { c->wf_blocks_shadow = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
   return c;
 }
 

@@ -183,7 +183,7 @@ __device__ __forceinline__ void p_extend_session(const WfParams& p, const Staged
     if (!in_dda) s.t = 3.0e38f;
     const unsigned thr = dry ? 1u : (unsigned)p.refill;
     const bool drained = dry;
-    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) <= (unsigned)kBulkLanes;
+    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) <= (unsigned)p.bulk;
     for (;;) {
 #pragma unroll
       for (int u = 0; u < 2; u++) {
@@ -197,7 +197,7 @@ __device__ __forceinline__ void p_extend_session(const WfParams& p, const Staged
         }
       }
       const unsigned act = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest));
-      sparse = drained || act <= (unsigned)kBulkLanes;
+      sparse = drained || act <= (unsigned)p.bulk;
       if (act < thr) break;
     }
     if (__float_as_uint(s.t) == kHitTag) { pbest = s.P; volbest = vi - 1; s.t = 3.0e38f; }  // the cell the walk stopped on
@@ -318,7 +318,7 @@ __device__ __forceinline__ void p_shadow_session(const WfParams& p, const Staged
     const unsigned thr = dry ? 1u : (unsigned)p.refill;
     bool occluded = false;
     const bool drained = dry;
-    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) <= (unsigned)kBulkLanes;
+    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) <= (unsigned)p.bulk;
     for (;;) {
 #pragma unroll
       for (int u = 0; u < 2; u++) {
@@ -332,7 +332,7 @@ __device__ __forceinline__ void p_shadow_session(const WfParams& p, const Staged
         }
       }
       const unsigned act = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray));
-      sparse = drained || act <= (unsigned)kBulkLanes;
+      sparse = drained || act <= (unsigned)p.bulk;
       if (act < thr) break;
     }
     if (in_dda) {

@@ -64,6 +64,7 @@ struct WfParams {
   int row_begin, row_end, row_tile, row_tile_stride, row_tile_phase;
   int iter;              // bounce iteration of this launch
   int refill;            // lanes still walking below which idle lanes refill from the queue
+  int bulk;              // with at most this many lanes walking, lanes in empty 8^3/16^3 blocks bulk-advance
   int persistent;        // 1: generate feeds the persistent kernel's extend queue
   int write_rgb8;
   float4* accum;
@@ -101,6 +102,15 @@ __device__ __forceinline__ Staged wf_stage_scene(const DScene& sc, unsigned char
   }
   __syncthreads();
   return st;
+}
+// Blocks that get scheduled after the stage queue ran dry (small shards, late bounces) leave before staging the scene
+// into shared memory; `taken` is the queue's ticket counter, n its length.
+__device__ __forceinline__ bool wf_block_has_work(const uint32_t* taken, uint32_t n)
+{
+  __shared__ int go;
+  if (threadIdx.x == 0) go = *reinterpret_cast<const volatile uint32_t*>(taken) < n;
+  __syncthreads();
+  return go != 0;
 }
 // warp-aggregated append of one id per participating lane
 __device__ __forceinline__ void wf_push(uint32_t* queue, uint32_t* counter, bool want, uint32_t id)
@@ -166,6 +176,7 @@ template <bool CS>
 __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
+  if (!wf_block_has_work(p.st.counts + 4 * p.iter + 2, p.st.counts[4 * p.iter])) return;
   const Staged stg = wf_stage_scene(p.sc, smem);
   const DVolume* svol = stg.vol;
   const int lane = threadIdx.x & 31;
@@ -236,7 +247,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
     if (!in_dda) s.t = 3.0e38f;
     const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)p.refill;  // queue drained: run to completion
     const bool drained = thr == 1u;  // no more work to pull: latency of the remaining rays is all that matters
-    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) <= (unsigned)kBulkLanes;
+    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) <= (unsigned)p.bulk;
     for (;;) {
 #pragma unroll
       for (int u = 0; u < 2; u++) {
@@ -251,7 +262,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ 
         }
       }
       const unsigned act = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest));
-      sparse = drained || act <= (unsigned)kBulkLanes;
+      sparse = drained || act <= (unsigned)p.bulk;
       if (act < thr) break;
     }
     if (__float_as_uint(s.t) == kHitTag) { pbest = s.P; volbest = vi - 1; s.t = 3.0e38f; }  // the cell the walk stopped on
@@ -496,6 +507,7 @@ template <bool CS>
 __global__ void __launch_bounds__(kWfBlock) k_wf_shade(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
+  if (blockIdx.x * blockDim.x >= p.st.counts[4 * p.iter]) return;  // grid-stride loop below would be empty
   const Staged stg = wf_stage_scene(p.sc, smem);
   const DVolume* svol = stg.vol;
   const DScene& sc = p.sc;
@@ -530,6 +542,7 @@ template <bool CS>
 __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
+  if (!wf_block_has_work(p.st.counts + 4 * p.iter + 3, p.st.counts[4 * p.iter + 1])) return;
   const Staged stg = wf_stage_scene(p.sc, smem);
   const DVolume* svol = stg.vol;
   const int lane = threadIdx.x & 31;
@@ -631,7 +644,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
     const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)p.refill;
     bool occluded = false;
     const bool drained = thr == 1u;
-    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) <= (unsigned)kBulkLanes;
+    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) <= (unsigned)p.bulk;
     for (;;) {
 #pragma unroll
       for (int u = 0; u < 2; u++) {
@@ -645,7 +658,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ 
         }
       }
       const unsigned act = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray));
-      sparse = drained || act <= (unsigned)kBulkLanes;
+      sparse = drained || act <= (unsigned)p.bulk;
       if (act < thr) break;
     }
     if (in_dda) {

@@ -12,8 +12,8 @@ sc, cam, fpd = scenes.config(cfg)
 W, H = fpd["width"], fpd["height"]
 cc = cam.to_c()
 K = 24
-for world in (1, 8, 16):
-    for S in (1, 3):
+for world in [int(x) for x in os.environ.get("PROBE_WORLDS", "1,8").split(",")]:
+    for S in [int(x) for x in os.environ.get("PROBE_CTX", "1,3").split(",")]:
         sess = [vp.Session(lib, 0) for _ in range(S)]
         for s in sess: s.set_scene(sc)
         streams = [torch.cuda.Stream() for _ in range(S)]
