@@ -43,7 +43,7 @@ def frame_params(fpd, **over):
     d.update(over)
     return vp.frame_params(d["width"], d["height"], max_bounces=d["max_bounces"], spp=d.get("spp", 1),
                            frame_index=d.get("frame_index", 0), seed=scenes.SEED, aa_strength=d["aa_strength"],
-                           row_tile=d.get("row_tile", 0), row_tile_stride=d.get("row_tile_stride", 1),
+                           row_begin=d.get("row_begin", 0), row_end=d.get("row_end", 0), row_tile=d.get("row_tile", 0), row_tile_stride=d.get("row_tile_stride", 1),
                            row_tile_phase=d.get("row_tile_phase", 0), flags=d.get("flags", 0))
 
 
@@ -214,7 +214,7 @@ def main():
 
     STAGE_EVERY = 20
     # L2 flush between timed iterations (the frame's working set is far below the 126 MB L2)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -330,13 +330,28 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # sector-granular view: every DDA cell visit of the reference is a dependent byte load = one 32 B
+    # sector; against the L2 read bandwidth measured here by csrc/vp_probe.cu (48 MiB buffer, ld.global.cg)
+    l2 = None
+    probe_so = os.path.join(ROOT, "raytracer-voxpopuli_b200", "libvoxpop_probe.so")
+    if os.path.exists(probe_so):
+        pl = C.CDLL(probe_so)
+        pl.vp_probe_l2_read.argtypes = [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+        gbs = C.c_double()
+        if pl.vp_probe_l2_read(local, 48 << 20, 40, C.byref(gbs)) == 0:
+            sector_bytes = meta["extend_steps"] * 32
+            l2 = {"peak": gbs.value, "unit": "GB/s", "peak_source": "measured here: 48 MiB L2-resident buffer, 128-bit ld.global.cg, 1184 blocks",
+                  "sector_bytes_per_step": int(sector_bytes), "achieved": sector_bytes / (ext_ms_frame * 1e-3) / 1e9,
+                  "note": "what the reference's one-byte-per-cell loads would move at sector granularity; the kernel itself "
+                          "replaces them by register bit tests (DESIGN.md section 3), its measured L2 traffic is in profiles/"}
+            l2["frac"] = l2["achieved"] / l2["peak"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "k_wf_extend", "peak_source": peak_src,
                 "launches_per_step": int(ext_launches_per_frame), "kernel_ms_per_step": ext_ms_frame, "steps_with_stage_events": timed_steps,
                 "kernel_share_of_step": ext_ms_frame / (total_ms / args.steps),
                 "algorithmic_bytes_per_launch": int(ext_bytes_frame / ext_launches_per_frame),
                 "algorithmic_bytes_per_step_all_stages": int(frame_bytes),
-                "dda_steps_per_step": int(inst.dda_steps),
+                "dda_steps_per_step": int(inst.dda_steps), "l2_sector_view": l2,
                 "note": "traversal of an L2-resident grid, bound by issue slots / divergence / latency, not by HBM: the HBM "
                         "fraction is a few percent by construction (DESIGN.md section 4)"}
 
@@ -349,13 +364,27 @@ def main():
         cpu_baseline = {"value": rays[best] / times[best] / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
                         "ms_per_frame": 1e3 * times[best],
                         "sample": f"best of {reps - 1} full {W}x{H} frames (1 spp) after 1 warm-up, same scene/camera/seeds"}
+        # the 1-thread figure, on a band of rows around the image centre
+        setter = getattr(clib.dll, clib.prefix + "set_threads", None)
+        if setter is not None:
+            band = (H // 2 - 32, H // 2 + 32)
+            setter(1)
+            with vp.Session(clib) as s1:
+                s1.set_scene(sc)
+                acc1 = np.zeros((H, W, 4), np.float32)
+                t0 = time.perf_counter()
+                _, _, st1 = s1.render(cam, frame_params(fpd, frame_index=0, row_begin=band[0], row_end=band[1]), accum=acc1)
+                dt1 = time.perf_counter() - t0
+            setter(cores)
+            cpu_baseline["one_thread"] = {"value": st1.rays / dt1 / 1e6, "unit": "Mrays/s",
+                                          "sample": f"rows {band[0]}..{band[1] - 1} of one {W}x{H} frame, 1 thread"}
 
     line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "reference assets (room.vox grid fixture), synthetic camera/lights",
             "config": {"workload": scenes.WORKLOAD_NAMES[args.config], "resolution": [W, H], "spp_per_step": 1,
                        "rays_per_step": rays_total / args.steps, "sharding": f"interleaved {ROW_TILE}-row tiles x{world}" if world > 1 else "none",
-                       "l2": "flushed between timed iterations (256 MiB fill, inside the timed region)",
+                       "l2": "flushed between timed iterations (160 MiB fill, inside the timed region)",
                        "frames_in_flight": 4, "timed_region": "one CUDA-event pair around all steps incl. the L2 flushes; every "
                        "20th step runs alone with stage events (VP_FLAG_TIME_STAGES)"},
             "ms_per_frame": total_ms / args.steps,

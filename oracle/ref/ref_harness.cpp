@@ -129,6 +129,8 @@ void vpref_destroy(vpref_ctx* c)
 }
 
 int vpref_threads() { return omp_get_max_threads(); }
+// bench.py: the 1-thread CPU figure SURVEY.md 8(d) asks for, beside the all-cores one
+void vpref_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
 
 int vpref_default_materials(vpref_ctx* c, VpMaterial* out, int n)
 {

@@ -845,6 +845,14 @@ int vpo_threads(void)
   return 1;
 #endif
 }
+void vpo_set_threads(int n)
+{
+#ifdef _OPENMP
+  omp_set_num_threads(n > 0 ? n : 1);
+#else
+  (void)n;
+#endif
+}
 int vpo_set_volumes(vpo_ctx* c, const VpVolume* v, int n)
 {
   free_volumes(c);

@@ -2,6 +2,7 @@
   libvoxpop_b200.so      CUDA sm_100a kernels + C ABI      (csrc/vp_api.cu)
   libvoxpop_host.so      C++ scene-authoring mirror        (host/voxpop_host.cpp)
   libvoxpop_renderer.so  C++ Renderer mirror over the ABI  (host/voxpop_renderer.cpp)
+  libvoxpop_probe.so     L2 bandwidth probe for bench.py   (csrc/vp_probe.cu)
 """
 import os
 import subprocess
@@ -34,6 +35,11 @@ def build(force=False, verbose_ptxas=False):
     so = os.path.join(PKG, "libvoxpop_b200.so")
     if force or _stale(so, cu):
         _run(["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + ["-o", so, cu[0]])
+    probe_src = os.path.join(csrc, "vp_probe.cu")
+    pso = os.path.join(PKG, "libvoxpop_probe.so")
+    if force or _stale(pso, [probe_src]):
+        _run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+              "-cudart", "static", "-o", pso, probe_src])
     host_src = [os.path.join(PKG, "host", f) for f in ("voxpop_host.cpp", "voxpop_host.hpp")] + [hdr]
     hso = os.path.join(PKG, "libvoxpop_host.so")
     if force or _stale(hso, host_src):
