@@ -187,6 +187,28 @@ int vp_render_device(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, 
  * at most 7) has resolved; with resolves in call order that covers every earlier call too.  Enqueue only,
  * no host synchronisation.  Needed after VP_FLAG_DEFER calls; harmless otherwise. */
 int vp_render_fence(vp_ctx* ctx, void* cuda_stream, int frames_back);
+/* ---- second frame mode: reprojection (Renderer::Tick, static-camera branch, renderer.cpp:1997-2101) -------------
+ * Pass 1 per pixel: Camera::GetPrimaryRayNoDOF (template/camera.h:103-110), TraceReproject (renderer.cpp:1330-1586:
+ * the Trace recursion with the first hit's albedo kept apart from the illumination and a Fresnel-free non-metal
+ * branch) -> albedoBuffer, illuminationBuffer, rayData.  Pass 2 per pixel: project the hit into the previous frame
+ * (Camera::PointToUV :34-50), IsOccludedPrevFrame (:767-774), SampleHistory (:777-830, bilinear), ClampHistory
+ * (:855-910, 3x3 YCoCg variance box), lerp by a per-material weight (:2051-2086), tonemap albedo*illumination. */
+typedef struct VpPrevCamera { /* what Renderer::CopyToPrevCamera keeps (renderer.cpp:1893-1902) */
+  float cam_pos[3];
+  float left_normal[3], right_normal[3], top_normal[3], bottom_normal[3]; /* Camera::SetFrustumNormals, camera.h:53-66 */
+} VpPrevCamera;
+/* history_in: W*H float3 = illuminationHistoryBuffer; history_out: W*H float3 = tempIlluminationBuffer (the caller
+ * swaps them for the next frame, renderer.cpp:2100); must not alias.  albedo / illumination: optional W*H float3 dumps
+ * of pass 1.  fp: width, height, max_bounces, frame_index, seed are used (one pass; the whole frame - row ranges are
+ * rejected because pass 2 reads its neighbours).  HOST pointers. */
+int vp_render_reproject(vp_ctx* ctx, const VpCamera* cam, const VpPrevCamera* prev, const VpFrameParams* fp,
+                        const float* history_in, float* history_out, uint32_t* rgb8, float* albedo, float* illumination,
+                        VpStats* stats);
+/* Same on DEVICE buffers of the caller (history ping-pong resident in HBM); albedo/illumination dumps omitted. */
+int vp_render_reproject_device(vp_ctx* ctx, const VpCamera* cam, const VpPrevCamera* prev, const VpFrameParams* fp,
+                               const void* history_in_dev, void* history_out_dev, void* rgb8_dev, void* cuda_stream,
+                               VpStats* stats);
+
 /* Library-owned resident accumulator: Renderer::accumulator kept in HBM between frames.
  * vp_accum_reset = allocate/zero (Renderer::ResetAccumulator, renderer.cpp:343-346, plus
  * the memset of Init :702); vp_render_resident = Update() on it; vp_accum_download

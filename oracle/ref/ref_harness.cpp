@@ -303,6 +303,118 @@ int vpref_render(vpref_ctx* c, const VpCamera* cam, const VpFrameParams* fp, flo
   return 0;
 }
 
+// Reprojection frame mode: the two pixel loops of Renderer::Tick's static-camera branch (renderer.cpp:2003-2100)
+// re-stated under OpenMP with the per-pixel reseed; every call below is the reference's own function, the buffers are
+// the reference's own members (std::vector after patch P6).
+int vpref_render_reproject(vpref_ctx* c, const VpCamera* cam, const VpPrevCamera* prev, const VpFrameParams* fp, const float* hist_in,
+                           float* hist_out, uint32_t* rgb8, float* albedo_out, float* illum_out, VpStats* stats)
+{
+  Renderer* r = c->r;
+  const int W = fp->width, H = fp->height;
+  g_vp_scrwidth = W, g_vp_scrheight = H;
+  set_camera(r, cam);
+  r->maxBounces = fp->max_bounces;
+  const uint32_t npix = (uint32_t)W * (uint32_t)H;
+  r->illuminationBuffer.assign(npix, float3(0));
+  r->albedoBuffer.assign(npix, float3(0));
+  r->tempIlluminationBuffer.assign(npix, float3(0));
+  r->illuminationHistoryBuffer.resize(npix);
+  r->rayData.resize(npix);
+  for (uint32_t i = 0; i < npix; i++) r->illuminationHistoryBuffer[i] = f3(hist_in + 3 * (size_t)i);
+  r->prevCamera.camPos = f3(prev->cam_pos);
+  r->prevCamera.leftNormal = f3(prev->left_normal);
+  r->prevCamera.rightNormal = f3(prev->right_normal);
+  r->prevCamera.topNormal = f3(prev->top_normal);
+  r->prevCamera.bottomNormal = f3(prev->bottom_normal);
+  std::atomic<unsigned long long> nearest{0}, shadow{0}, exitray{0}, steps{0}, primary{0};
+  const double t0 = omp_get_wtime();
+#pragma omp parallel
+  {
+    g_vp_cnt = VpRefCounters();
+    unsigned long long prim = 0;
+#pragma omp for schedule(dynamic, 1)
+    for (int y = 0; y < H; y++)
+    {
+      const uint32_t pitch = y * W;
+      for (uint32_t x = 0; x < (uint32_t)W; x++)
+      {
+        seed = pixel_seed(pitch + x, fp->frame_index, npix, fp->seed);
+        Ray primaryRay = r->camera.GetPrimaryRayNoDOF(static_cast<float>(x), static_cast<float>(y));
+        const AlbedoIlluminationData data = {r->TraceReproject(primaryRay, r->maxBounces)};
+        const uint32_t index = pitch + x;
+        r->albedoBuffer[index] = data.albedo;
+        r->illuminationBuffer[index] = data.illumination;
+        r->rayData[index] = RayDataReproject::GetRayInfo(primaryRay);
+        if (r->maxBounces >= 0) prim++;
+      }
+    }
+#pragma omp for schedule(dynamic, 1)
+    for (int y = 0; y < H; y++)
+    {
+      const int32_t pitch = y * W;
+      for (int32_t x = 0; x < W; x++)
+      {
+        const uint32_t index = x + pitch;
+        float3 finalIllumination{0};
+        const RayDataReproject rayInfo{r->rayData[index]};
+        float3 intersectionP{rayInfo.intersectionPoint};
+        const MaterialType::MatType matType = rayInfo.materialIndex;
+        float3 newSample{r->illuminationBuffer[index]};
+        const float2 halfAPixel = {HALF_PIXEL_W, HALF_PIXEL_H};
+        const float2 uv{r->prevCamera.PointToUV(intersectionP) + halfAPixel};
+        if (r->IsValid(uv) && !r->IsOccludedPrevFrame(intersectionP))
+        {
+          float3 historySample;
+          historySample = r->SampleHistory(uv);
+          r->ClampHistory(historySample, newSample, {x, y});
+          float w = {0.9f};
+          switch (matType)  // renderer.cpp:2051-2086
+          {
+          case MaterialType::NON_METAL_WHITE: case MaterialType::NON_METAL_RED: case MaterialType::NON_METAL_BLUE:
+          case MaterialType::NON_METAL_GREEN: case MaterialType::NON_METAL_PINK: w = 0.8f; break;
+          case MaterialType::METAL_HIGH: case MaterialType::METAL_MID: case MaterialType::METAL_LOW: w = 0.5f; break;
+          case MaterialType::GLASS: w = 0.5f; break;
+          case MaterialType::SMOKE_LOW_DENSITY: case MaterialType::SMOKE_LOW2_DENSITY: case MaterialType::SMOKE_MID_DENSITY:
+          case MaterialType::SMOKE_MID2_DENSITY: case MaterialType::SMOKE_HIGH_DENSITY: case MaterialType::SMOKE_PLAYER: w = 0.9f; break;
+          case MaterialType::EMISSIVE: w = 0; break;
+          default: w = 0.9f; break;
+          }
+          finalIllumination = lerp(newSample, historySample, w);
+        }
+        else
+        {
+          finalIllumination = newSample;
+        }
+        r->tempIlluminationBuffer[index] = finalIllumination;
+        float4 acesPixel = r->ApplyReinhardJodie(r->albedoBuffer[index] * finalIllumination);
+        if (rgb8) rgb8[index] = RGBF32_to_RGB8(&acesPixel);
+      }
+    }
+    nearest += g_vp_cnt.nearest, shadow += g_vp_cnt.shadow, exitray += g_vp_cnt.exitray, steps += g_vp_cnt.steps;
+    primary += prim;
+  }
+  const double t1 = omp_get_wtime();
+  for (uint32_t i = 0; i < npix; i++)
+  {
+    const float3 h = r->tempIlluminationBuffer[i], a = r->albedoBuffer[i], l = r->illuminationBuffer[i];
+    hist_out[3 * (size_t)i] = h.x, hist_out[3 * (size_t)i + 1] = h.y, hist_out[3 * (size_t)i + 2] = h.z;
+    if (albedo_out) albedo_out[3 * (size_t)i] = a.x, albedo_out[3 * (size_t)i + 1] = a.y, albedo_out[3 * (size_t)i + 2] = a.z;
+    if (illum_out) illum_out[3 * (size_t)i] = l.x, illum_out[3 * (size_t)i + 1] = l.y, illum_out[3 * (size_t)i + 2] = l.z;
+  }
+  if (stats)
+  {
+    stats->primary_rays = primary;
+    stats->secondary_rays = nearest - primary;
+    stats->shadow_rays = shadow;
+    stats->exit_rays = exitray;
+    stats->dda_steps = steps;
+    stats->sky_samples = 0;
+    stats->device_ms = (t1 - t0) * 1e3;
+    stats->kernel_launches = 0;
+  }
+  return 0;
+}
+
 int vpref_trace_primary(vpref_ctx* c, const VpCamera* cam, const VpFrameParams* fp, VpHit* hits)
 {
   Renderer* r = c->r;

@@ -647,6 +647,89 @@ static f3 sample_sky(const vpo_ctx* c, f3 d)
   return smul(c->sky_contrib, v3(c->sky[idx], c->sky[idx + 1], c->sky[idx + 2]));
 }
 
+/* GLASS bounce: renderer.cpp:1146-1205 (Trace) == :1360-1418 (TraceDialectric), up to the recursive call.
+ * Returns the attenuation colour and the next ray. */
+static f3 glass_bounce(Thread* T, Ray* ray, int voxIndex, Ray* next)
+{
+  vpo_ctx* c = T->c;
+  const int m = ray->mat;
+  f3 color = v3s(1.0f);
+  int inGlass = ray->inside;
+  const float ior = c->mat[m].ior;
+  const float ratio = inGlass ? ior : 1.0f / ior;
+  int insideVolume = 1;
+  if (inGlass) {
+    color = albedo(c, m);
+    if (voxIndex >= 0) { /* reference indexes voxelVolumes[voxIndex] unguarded (UB for -1) */
+      const Volume* v = &c->vol[voxIndex];
+      const f3 bO = ray->O, bD = ray->D, brD = ray->rD, bS = ray->Dsign;
+      ray->O = xform_scalar(ray->O, 1.0f, v->iM);
+      ray->D = xform_scalar(ray->D, 0.0f, v->iM);
+      ray->rD = rcp3(ray->D);
+      ray->Dsign = compute_dsign(ray->D);
+      insideVolume = scene_find_exit(T, v, ray, 0, 8);
+      ray->O = bO; ray->D = bD; ray->rD = brD; ray->Dsign = bS;
+    }
+  }
+  if (!insideVolume) { ray->O = add(ray->O, muls(ray->D, ray->t)); ray->t = 0; }
+  const float ct = stdmin(dot3(neg(ray->D), ray->N), 1.0f);
+  const float st = sqrtf(1.0f - ct * ct);
+  const int cannot = ratio * st > 1.0f;
+  f3 rdir, rn;
+  if (cannot || schlick(ct, ratio) > rnd(T)) { rdir = reflect3(ray->D, ray->N); rn = ray->N; }
+  else { rdir = refract3(ray->D, ray->N, ratio); inGlass = !inGlass; rn = neg(ray->N); }
+  *next = make_ray(offset_ray(isect(ray), rn), rdir);
+  next->inside = inGlass;
+  return color;
+}
+
+/* SMOKE bounce: renderer.cpp:1210-1310 (Trace) == :1425-1499 (TraceSmoke), up to the recursive call. */
+static f3 smoke_bounce(Thread* T, Ray* ray, int voxIndex, Ray* next)
+{
+  vpo_ctx* c = T->c;
+  const int m = ray->mat;
+  f3 color = v3s(1.0f);
+  int inGlass = ray->inside;
+  const float ratio = 1.0f;
+  int insideVolume = 1;
+  float intensity = 0, dist = 0;
+  if (voxIndex == 0) { /* player volume: inLight side channel :1228-1240 */
+    const f3 inc = illumination(T, ray);
+    if (dot3(inc, inc) > 16.0f) T->cnt.in_light = 1;
+  }
+  if (inGlass) {
+    intensity = c->mat[m].emissive;
+    color = albedo(c, m);
+    if (voxIndex >= 0) {
+      const Volume* v = &c->vol[voxIndex];
+      const f3 bO = ray->O, bD = ray->D, brD = ray->rD, bS = ray->Dsign;
+      ray->O = xform_scalar(ray->O, 1.0f, v->iM);
+      ray->D = xform_scalar(ray->D, 0.0f, v->iM);
+      ray->rD = rcp3(ray->D);
+      ray->Dsign = compute_dsign(ray->D);
+      insideVolume = scene_find_exit(T, v, ray, 1, 0);
+      ray->O = bO; ray->D = bD; ray->rD = brD; ray->Dsign = bS;
+    }
+    dist = ray->t;
+  }
+  const float threshold = rnd(T) * 100 - intensity;
+  if (rnd(T) * dist > threshold) {
+    const float lo = ray->t * .45f;
+    const float rr = lo + rnd(T) * (ray->t - lo); /* Rand(min,max), tmpl8math.cpp:154-157 */
+    ray->O = add(ray->O, muls(ray->D, rr));
+    ray->D = random_direction(T);
+    ray->t = 0;
+  }
+  color = absorption(color, intensity, dist);
+  if (!insideVolume) { ray->O = add(ray->O, muls(ray->D, ray->t)); ray->t = 0; }
+  const f3 rdir = refract3(ray->D, ray->N, ratio);
+  inGlass = !inGlass;
+  const f3 rn = neg(ray->N);
+  *next = make_ray(offset_ray(isect(ray), rn), rdir);
+  next->inside = inGlass;
+  return color;
+}
+
 /* ---------- Renderer::Trace: renderer.cpp:1076-1328 ---------- */
 static f3 trace(Thread* T, Ray* ray, int depth)
 {
@@ -676,75 +759,13 @@ static f3 trace(Thread* T, Ray* ray, int depth)
     return color;
   }
   if (m == 8) { /* GLASS :1146-1208 */
-    f3 color = v3s(1.0f);
-    int inGlass = ray->inside;
-    const float ior = c->mat[m].ior;
-    const float ratio = inGlass ? ior : 1.0f / ior;
-    int insideVolume = 1;
-    if (inGlass) {
-      color = albedo(c, m);
-      if (voxIndex >= 0) { /* reference indexes voxelVolumes[voxIndex] unguarded (UB for -1) */
-        const Volume* v = &c->vol[voxIndex];
-        const f3 bO = ray->O, bD = ray->D, brD = ray->rD, bS = ray->Dsign;
-        ray->O = xform_scalar(ray->O, 1.0f, v->iM);
-        ray->D = xform_scalar(ray->D, 0.0f, v->iM);
-        ray->rD = rcp3(ray->D);
-        ray->Dsign = compute_dsign(ray->D);
-        insideVolume = scene_find_exit(T, v, ray, 0, 8);
-        ray->O = bO; ray->D = bD; ray->rD = brD; ray->Dsign = bS;
-      }
-    }
-    if (!insideVolume) { ray->O = add(ray->O, muls(ray->D, ray->t)); ray->t = 0; }
-    const float ct = stdmin(dot3(neg(ray->D), ray->N), 1.0f);
-    const float st = sqrtf(1.0f - ct * ct);
-    const int cannot = ratio * st > 1.0f;
-    f3 rdir, rn;
-    if (cannot || schlick(ct, ratio) > rnd(T)) { rdir = reflect3(ray->D, ray->N); rn = ray->N; }
-    else { rdir = refract3(ray->D, ray->N, ratio); inGlass = !inGlass; rn = neg(ray->N); }
-    Ray nr = make_ray(offset_ray(isect(ray), rn), rdir);
-    nr.inside = inGlass;
+    Ray nr;
+    const f3 color = glass_bounce(T, ray, voxIndex, &nr);
     return mul(trace(T, &nr, depth - 1), color);
   }
   if (m >= 9 && m <= 14) { /* SMOKE_* :1210-1313 */
-    f3 color = v3s(1.0f);
-    int inGlass = ray->inside;
-    const float ratio = 1.0f;
-    int insideVolume = 1;
-    float intensity = 0, dist = 0;
-    if (voxIndex == 0) { /* player volume: inLight side channel :1228-1240 */
-      const f3 inc = illumination(T, ray);
-      if (dot3(inc, inc) > 16.0f) T->cnt.in_light = 1;
-    }
-    if (inGlass) {
-      intensity = c->mat[m].emissive;
-      color = albedo(c, m);
-      if (voxIndex >= 0) {
-        const Volume* v = &c->vol[voxIndex];
-        const f3 bO = ray->O, bD = ray->D, brD = ray->rD, bS = ray->Dsign;
-        ray->O = xform_scalar(ray->O, 1.0f, v->iM);
-        ray->D = xform_scalar(ray->D, 0.0f, v->iM);
-        ray->rD = rcp3(ray->D);
-        ray->Dsign = compute_dsign(ray->D);
-        insideVolume = scene_find_exit(T, v, ray, 1, 0);
-        ray->O = bO; ray->D = bD; ray->rD = brD; ray->Dsign = bS;
-      }
-      dist = ray->t;
-    }
-    const float threshold = rnd(T) * 100 - intensity;
-    if (rnd(T) * dist > threshold) {
-      const float lo = ray->t * .45f;
-      const float rr = lo + rnd(T) * (ray->t - lo); /* Rand(min,max), tmpl8math.cpp:154-157 */
-      ray->O = add(ray->O, muls(ray->D, rr));
-      ray->D = random_direction(T);
-      ray->t = 0;
-    }
-    color = absorption(color, intensity, dist);
-    if (!insideVolume) { ray->O = add(ray->O, muls(ray->D, ray->t)); ray->t = 0; }
-    const f3 rdir = refract3(ray->D, ray->N, ratio);
-    inGlass = !inGlass;
-    const f3 rn = neg(ray->N);
-    Ray nr = make_ray(offset_ray(isect(ray), rn), rdir);
-    nr.inside = inGlass;
+    Ray nr;
+    const f3 color = smoke_bounce(T, ray, voxIndex, &nr);
     return mul(trace(T, &nr, depth - 1), color);
   }
   if (m == 15) /* EMISSIVE :1315-1316 */
@@ -754,6 +775,60 @@ static f3 trace(Thread* T, Ray* ray, int depth)
     const f3 inc = illumination(T, ray);
     Ray nr = make_ray(offset_ray(isect(ray), ray->N), rdir);
     return mul(add(trace(T, &nr, depth - 1), inc), albedo(c, m));
+  }
+}
+
+/* ---------- Renderer::TraceReproject family: renderer.cpp:1330-1586 ---------- */
+typedef struct { f3 albedo, illum; } AlbIll; /* AlbedoIlluminationData, renderer.h:10-19; GetColor() = albedo * illumination */
+static inline f3 ai_color(AlbIll a) { return mul(a.albedo, a.illum); }
+static AlbIll ai(f3 a, f3 i) { AlbIll r; r.albedo = a; r.illum = i; return r; }
+
+static AlbIll sample_sky_reproject(const vpo_ctx* c, f3 d) /* renderer.cpp:2328-2346: same texel arithmetic as SampleSky */
+{
+  return ai(sample_sky(c, d), v3s(1.0f));
+}
+
+static AlbIll trace_reproject(Thread* T, Ray* ray, int depth)
+{
+  vpo_ctx* c = T->c;
+  if (depth < 0) return ai(v3s(0.0f), v3s(0.0f)); /* {0.0f, 0} :1523-1526 */
+  const int voxIndex = find_nearest(T, ray);
+  if (ray->mat == VP_MAT_NONE) { T->cnt.sky++; return sample_sky_reproject(c, ray->D); }
+  const int m = ray->mat;
+  if (m >= 5 && m <= 7) { /* TraceMetal :1330-1340 */
+    const f3 refl = reflect3(ray->D, ray->N);
+    Ray nr = make_ray(offset_ray(isect(ray), ray->N), add(refl, smul(c->mat[m].roughness, random_sphere_sample(T))));
+    const f3 ill = ai_color(trace_reproject(T, &nr, depth - 1));
+    return ai(albedo(c, m), ill);
+  }
+  if (m <= 4) { /* TraceNonMetal :1342-1358: no Fresnel draw, always the Lambert branch */
+    f3 ill = v3s(0);
+    const f3 rdir = add(ray->N, random_sphere_sample(T)); /* RandomLambertianReflectionVector */
+    const f3 inc = illumination(T, ray);
+    Ray nr = make_ray(offset_ray(isect(ray), ray->N), rdir);
+    ill = add(ill, inc);
+    ill = add(ill, ai_color(trace_reproject(T, &nr, depth - 1)));
+    return ai(albedo(c, m), ill);
+  }
+  if (m == 8) { /* TraceDialectric :1360-1423 */
+    Ray nr;
+    const f3 color = glass_bounce(T, ray, voxIndex, &nr);
+    return ai(color, ai_color(trace_reproject(T, &nr, depth - 1)));
+  }
+  if (m >= 9 && m <= 14) { /* TraceSmoke :1425-1501 */
+    Ray nr;
+    const f3 color = smoke_bounce(T, ray, voxIndex, &nr);
+    return ai(color, ai_color(trace_reproject(T, &nr, depth - 1)));
+  }
+  if (m == 15) /* TraceEmmision :1503-1506 */
+    return ai(muls(albedo(c, m), c->mat[m].emissive), v3s(1.0f));
+  { /* TraceModelMaterials :1508-1518 */
+    const f3 rdir = diffuse_reflection(T, ray->N);
+    const f3 inc = illumination(T, ray);
+    Ray nr = make_ray(offset_ray(isect(ray), ray->N), rdir);
+    f3 ill = inc;
+    ill = add(ill, ai_color(trace_reproject(T, &nr, depth - 1)));
+    return ai(albedo(c, m), ill);
   }
 }
 
@@ -948,6 +1023,174 @@ int vpo_render(vpo_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* 
     stats->primary_rays = primary; stats->secondary_rays = nearest - primary; stats->shadow_rays = shadow;
     stats->exit_rays = exitray; stats->dda_steps = steps; stats->sky_samples = sky; stats->device_ms = (t1 - t0) * 1e3; stats->kernel_launches = 0;
   }
+  return 0;
+}
+
+/* ---------- reprojection frame: Renderer::Tick static-camera branch, renderer.cpp:1997-2101 ---------- */
+static Ray primary_ray_nodof(const VpCamera* cam, float x, float y, int W, int H) /* template/camera.h:103-110 */
+{
+  const float u = x * (1.0f / (float)W);
+  const float v = y * (1.0f / (float)H);
+  const f3 TL = ld3(cam->top_left), TR = ld3(cam->top_right), BL = ld3(cam->bottom_left), cp = ld3(cam->cam_pos);
+  const f3 P = add(add(TL, smul(u, sub(TR, TL))), smul(v, sub(BL, TL)));
+  return make_ray(cp, sub(P, cp));
+}
+static inline float stdminf(float a, float b) { return a < b ? a : b; } /* fminf, tmpl8math.h:401 */
+static inline float fmaxf8(float a, float b) { return a > b ? a : b; }  /* fmaxf, tmpl8math.h:406 */
+static inline float clamp1(float f, float a, float b) { return fmaxf8(a, stdminf(f, b)); } /* tmpl8math.h:2105 */
+static inline f3 rgb_to_ycocg(f3 c) /* renderer.cpp:832-838 */
+{
+  const float Y = dot3(c, v3(1, 2, 1)) * 0.25f;
+  const float Co = dot3(c, v3(2, 0, -2)) * 0.25f + (0.5f * 256.0f / 255.0f);
+  const float Cg = dot3(c, v3(-1, 2, -1)) * 0.25f + (0.5f * 256.0f / 255.0f);
+  return v3(Y, Co, Cg);
+}
+static inline f3 ycocg_to_rgb(f3 c) /* renderer.cpp:841-850 */
+{
+  const float Y = c.x;
+  const float Co = c.y - (0.5f * 256.0f / 255.0f);
+  const float Cg = c.z - (0.5f * 256.0f / 255.0f);
+  return v3(Y + Co - Cg, Y + Cg, Y - Co - Cg);
+}
+static inline int valid_screen(int x, int y, int W, int H) /* Renderer::IsValidScreen on int2 -> float2, renderer.cpp:1640-1643 */
+{
+  return (float)x >= 0.0f && (float)x < (float)W && (float)y >= 0.0f && (float)y < (float)H;
+}
+static f3 sample_history(const float* hist, float u, float v, int W, int H) /* renderer.cpp:777-830 */
+{
+  u -= 1.0f / (float)W / 2.0f; /* HALF_PIXEL_W, camera.h:7 */
+  v -= 1.0f / (float)H / 2.0f;
+  const float px = u * (float)W, py = v * (float)H;
+  const int tlx = f2i(px), tly = f2i(py);
+  const float fx = px - (float)tlx, fy = py - (float)tly;
+  const float gx = 1 - fx, gy = 1 - fy;
+  const int v1 = valid_screen(tlx, tly, W, H), v2 = valid_screen(tlx + 1, tly, W, H);
+  const int v3_ = valid_screen(tlx, tly + 1, W, H), v4 = valid_screen(tlx + 1, tly + 1, W, H);
+  float w1 = v1 ? gx * gy : 0.0f, w2 = v2 ? fx * gy : 0.0f, w3 = v3_ ? gx * fy : 0.0f, w4 = v4 ? fx * fy : 0.0f;
+  const float total = w1 + w2 + w3 + w4;
+  const float rcp = 1.0f / total;
+  w1 *= rcp; w2 *= rcp; w3 *= rcp; w4 *= rcp;
+  f3 avg = v3s(0.0f);
+  if (v1) avg = add(avg, smul(w1, ld3(hist + 3 * ((size_t)tly * W + tlx))));
+  if (v2) avg = add(avg, smul(w2, ld3(hist + 3 * ((size_t)tly * W + tlx + 1))));
+  if (v3_) avg = add(avg, smul(w3, ld3(hist + 3 * ((size_t)(tly + 1) * W + tlx))));
+  if (v4) avg = add(avg, smul(w4, ld3(hist + 3 * ((size_t)(tly + 1) * W + tlx + 1))));
+  return avg;
+}
+static f3 clamp_history(f3 hist, f3 sample, const float* illum, int x, int y, int W, int H) /* renderer.cpp:855-910 */
+{
+  static const int off[8][2] = {{-1, -1}, {0, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {0, 1}, {1, 1}};
+  sample = rgb_to_ycocg(sample);
+  hist = rgb_to_ycocg(hist);
+  unsigned n = 1;
+  f3 avg = sample, var = mul(sample, sample);
+  for (int i = 0; i < 8; i++) {
+    const int qx = x + off[i][0], qy = y + off[i][1];
+    if (valid_screen(qx, qy, W, H)) {
+      const f3 f = rgb_to_ycocg(ld3(illum + 3 * ((size_t)qx + (size_t)qy * W)));
+      avg = add(avg, f);
+      var = add(var, mul(f, f));
+      n++;
+    }
+  }
+  const float inv = 1.0f / (float)n;
+  avg = muls(avg, inv);
+  var = muls(var, inv);
+  const float sig = 0.75f;
+  const f3 sigma = v3(sqrtf(stdmax(0.0f, var.x - (avg.x * avg.x))), sqrtf(stdmax(0.0f, var.y - (avg.y * avg.y))),
+                      sqrtf(stdmax(0.0f, var.z - (avg.z * avg.z))));
+  const f3 lo = sub(avg, smul(sig, sigma)), hi = add(avg, smul(sig, sigma));
+  hist = v3(clamp1(hist.x, lo.x, hi.x), clamp1(hist.y, lo.y, hi.y), clamp1(hist.z, lo.z, hi.z));
+  hist = ycocg_to_rgb(hist);
+  return v3(fmaxf8(hist.x, 0.0f), fmaxf8(hist.y, 0.0f), fmaxf8(hist.z, 0.0f));
+}
+static float history_weight(int m) /* renderer.cpp:2051-2086 */
+{
+  if (m <= 4) return 0.8f;             /* NON_METAL_* */
+  if (m >= 5 && m <= 8) return 0.5f;   /* METAL_*, GLASS */
+  if (m >= 9 && m <= 14) return 0.9f;  /* SMOKE_* */
+  if (m == 15) return 0.0f;            /* EMISSIVE */
+  return 0.9f;
+}
+
+int vpo_render_reproject(vpo_ctx* c, const VpCamera* cam, const VpPrevCamera* prev, const VpFrameParams* fp, const float* hist_in,
+                         float* hist_out, uint32_t* out8, float* albedo_out, float* illum_out, VpStats* stats)
+{
+  const int W = fp->width, H = fp->height;
+  const uint32_t npix = (uint32_t)W * (uint32_t)H;
+  if (!hist_in || !hist_out || hist_in == hist_out) return 1;
+  float* alb = albedo_out ? albedo_out : (float*)malloc((size_t)npix * 12);
+  float* ill = illum_out ? illum_out : (float*)malloc((size_t)npix * 12);
+  float* rayP = (float*)malloc((size_t)npix * 12); /* RayDataReproject: intersectionPoint + materialIndex are what pass 2 reads */
+  uint8_t* rayM = (uint8_t*)malloc(npix);
+  uint64_t nearest = 0, shadow = 0, exitray = 0, steps = 0, primary = 0, sky = 0;
+  double t0 = 0, t1 = 0;
+#ifdef _OPENMP
+  t0 = omp_get_wtime();
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nearest, shadow, exitray, steps, primary, sky)
+  for (int y = 0; y < H; y++) { /* pass 1, renderer.cpp:2003-2022 */
+    Thread T; memset(&T, 0, sizeof(T)); T.c = c;
+    for (int x = 0; x < W; x++) {
+      const uint32_t px = (uint32_t)y * (uint32_t)W + (uint32_t)x;
+      T.seed = pixel_seed(px, fp->frame_index, npix, fp->seed);
+      Ray pr = primary_ray_nodof(cam, (float)x, (float)y, W, H);
+      const AlbIll d = trace_reproject(&T, &pr, fp->max_bounces);
+      alb[3 * px] = d.albedo.x; alb[3 * px + 1] = d.albedo.y; alb[3 * px + 2] = d.albedo.z;
+      ill[3 * px] = d.illum.x; ill[3 * px + 1] = d.illum.y; ill[3 * px + 2] = d.illum.z;
+      const f3 P = isect(&pr); /* RayDataReproject::GetRayInfo, renderer.h:31-34 */
+      rayP[3 * px] = P.x; rayP[3 * px + 1] = P.y; rayP[3 * px + 2] = P.z;
+      rayM[px] = (uint8_t)pr.mat;
+      if (fp->max_bounces >= 0) primary++;
+    }
+    nearest += T.cnt.nearest; shadow += T.cnt.shadow; exitray += T.cnt.exitray; steps += T.cnt.steps; sky += T.cnt.sky;
+  }
+  const f3 pc = ld3(prev->cam_pos);
+  const f3 nl = ld3(prev->left_normal), nr_ = ld3(prev->right_normal), nt = ld3(prev->top_normal), nb = ld3(prev->bottom_normal);
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nearest, shadow, exitray, steps, sky)
+  for (int y = 0; y < H; y++) { /* pass 2, renderer.cpp:2023-2099 */
+    Thread T; memset(&T, 0, sizeof(T)); T.c = c;
+    for (int x = 0; x < W; x++) {
+      const uint32_t px = (uint32_t)x + (uint32_t)y * (uint32_t)W;
+      const f3 P = ld3(rayP + 3 * px);
+      const f3 newS = ld3(ill + 3 * px);
+      /* Camera::PointToUV, template/camera.h:34-50 */
+      const f3 delta = sub(P, pc);
+      const float dl = dot3(nl, delta), dr = dot3(nr_, delta), dt = dot3(nt, delta), db = dot3(nb, delta);
+      const float u = dl / (dl + dr) + 1.0f / (float)W / 2.0f;
+      const float v = dt / (dt + db) + 1.0f / (float)H / 2.0f;
+      f3 fin;
+      int reuse = u >= 0.0f && u < 1.0f && v >= 0.0f && v < 1.0f; /* IsValid :1635-1638 */
+      if (reuse) { /* IsOccludedPrevFrame :767-774 */
+        const f3 dirTo = sub(P, pc);
+        const f3 dn = normalize3(dirTo);
+        const f3 pos = offset_ray(P, neg(dn));
+        const f3 dd = sub(pos, pc);
+        Ray occ = make_ray(pc, dn);
+        occ.t = sqrtf(dot3(dd, dd)); /* length() */
+        reuse = !is_occluded(&T, &occ);
+      }
+      if (reuse) {
+        f3 h = sample_history(hist_in, u, v, W, H);
+        h = clamp_history(h, newS, ill, x, y, W, H);
+        const float w = history_weight(rayM[px]);
+        fin = add(newS, smul(w, sub(h, newS))); /* lerp, tmpl8math.h:2220 */
+      } else fin = newS;
+      hist_out[3 * px] = fin.x; hist_out[3 * px + 1] = fin.y; hist_out[3 * px + 2] = fin.z;
+      if (out8) out8[px] = rgb8(reinhard_jodie(mul(ld3(alb + 3 * px), fin)));
+    }
+    nearest += T.cnt.nearest; shadow += T.cnt.shadow; exitray += T.cnt.exitray; steps += T.cnt.steps; sky += T.cnt.sky;
+  }
+#ifdef _OPENMP
+  t1 = omp_get_wtime();
+#endif
+  if (stats) {
+    stats->primary_rays = primary; stats->secondary_rays = nearest - primary; stats->shadow_rays = shadow;
+    stats->exit_rays = exitray; stats->dda_steps = steps; stats->sky_samples = sky; stats->device_ms = (t1 - t0) * 1e3; stats->kernel_launches = 0;
+  }
+  if (!albedo_out) free(alb);
+  if (!illum_out) free(ill);
+  free(rayP); free(rayM);
   return 0;
 }
 

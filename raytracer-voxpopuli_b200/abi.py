@@ -52,6 +52,11 @@ class VpCamera(C.Structure):
                 ("up", F3), ("focal_distance", C.c_float), ("defocus_jitter", C.c_float)]
 
 
+class VpPrevCamera(C.Structure):
+    _fields_ = [("cam_pos", C.c_float * 3), ("left_normal", C.c_float * 3), ("right_normal", C.c_float * 3),
+                ("top_normal", C.c_float * 3), ("bottom_normal", C.c_float * 3)]
+
+
 class VpFrameParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("max_bounces", C.c_int32), ("spp", C.c_int32),
                 ("frame_index", C.c_uint32), ("seed", C.c_uint32), ("aa_strength", C.c_float),
@@ -89,7 +94,7 @@ ABI_SYMBOLS = [
     "create", "destroy", "last_error", "set_volumes", "update_volume_grid", "update_volume_transform",
     "set_materials", "set_lights", "set_prims", "set_sky", "render", "render_resident", "accum_reset",
     "accum_download", "render_device", "trace_primary", "find_nearest", "is_occluded", "trace", "info", "stats_begin", "stats_end", "stage_times",
-    "render_fence",
+    "render_fence", "render_reproject", "render_reproject_device",
 ]
 
 
@@ -121,6 +126,10 @@ class Lib:
         f("set_sky", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int])
         f("render", C.c_int, [C.c_void_p, C.POINTER(VpCamera), C.POINTER(VpFrameParams), C.c_void_p, C.c_void_p,
                               C.POINTER(VpStats)])
+        f("render_reproject", C.c_int, [C.c_void_p, C.POINTER(VpCamera), C.POINTER(VpPrevCamera), C.POINTER(VpFrameParams), C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VpStats)], optional=True)
+        f("render_reproject_device", C.c_int, [C.c_void_p, C.POINTER(VpCamera), C.POINTER(VpPrevCamera), C.POINTER(VpFrameParams),
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VpStats)], optional=True)
         f("trace_primary", C.c_int, [C.c_void_p, C.POINTER(VpCamera), C.POINTER(VpFrameParams), C.c_void_p])
         f("find_nearest", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p])
         f("is_occluded", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p])

@@ -110,6 +110,9 @@ struct vp_ctx {
   DevBuf<float4> d_accum;                 // library-owned resident accumulator / staging for vp_render
   DevBuf<uint32_t> d_rgb8;
   DevBuf<unsigned char> d_scratch_in, d_scratch_out, d_scratch_aux;
+  // reprojection frame mode: pass-1 outputs (albedoBuffer, illuminationBuffer, rayData) and host-API staging of the history
+  DevBuf<float> d_rp_alb, d_rp_ill, d_rp_hist_in, d_rp_hist_out;
+  DevBuf<float4> d_rp_ray;
   int acc_w = 0, acc_h = 0;
   DScene sc{};
   bool have_volumes = false;
@@ -293,6 +296,13 @@ int wf_reserve(WfLane& L, uint32_t cap, int levels, int samples)
 // before reusing its request buffer and resolve waits for all of them.  Resolves of successive passes are
 // chained through c->ev_last (the accumulator is a running average: order matters); nothing else of a pass
 // depends on the previous one, which is what lets kLanes passes be in flight.
+// arguments of the reprojection frame mode (device pointers)
+struct RpArgs {
+  VpPrevCamera prev;
+  const float* hist_in;
+  float* hist_out;
+};
+
 template <bool CS>
 int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
 {
@@ -326,9 +336,13 @@ int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
   if (c->wait_copy) { CU(cudaStreamWaitEvent(stream, c->ev_copy, 0)); c->wait_copy = false; }
   if (c->ev_last && c->ev_last != L.ev_done) CU(cudaStreamWaitEvent(stream, c->ev_last, 0));
   k_wf_resolve<<<wide, kWfBlock, 0, stream>>>(p);
+  c->host_launches++;
+  if (p.reproject) {  // pass 2 reads the 3x3 neighbourhood of what resolve just wrote: a kernel boundary
+    k_wf_reproject<CS><<<wide, kWfBlock, sm, stream>>>(p);
+    c->host_launches++;
+  }
   CU(cudaEventRecord(L.ev_done, stream));
   c->ev_last = L.ev_done;
-  c->host_launches++;
   CU(cudaGetLastError());
   return 0;
 }
@@ -375,7 +389,8 @@ int mark_direct(vp_ctx* c, cudaStream_t stream)
   return 0;
 }
 
-int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream, bool overlap)
+int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream, bool overlap,
+                     const RpArgs* rp = nullptr)
 {
   const uint32_t tiles = (uint32_t)((fp->width + 7) / 8) * (uint32_t)((fp->height + 3) / 4);
   const int levels = fp->max_bounces + 1 > 1 ? fp->max_bounces + 1 : 1;
@@ -391,6 +406,10 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   p.refill = c->tune_refill;
   p.bulk = c->tune_bulk;
   p.persistent = 0;
+  p.reproject = rp ? 1 : 0;
+  p.rp_alb = c->d_rp_alb.p; p.rp_ill = c->d_rp_ill.p; p.rp_ray = c->d_rp_ray.p;
+  p.hist_in = rp ? rp->hist_in : nullptr; p.hist_out = rp ? rp->hist_out : nullptr;
+  if (rp) p.prev = rp->prev; else memset(&p.prev, 0, sizeof(p.prev));
   c->time_stages_now = (fp->flags & VP_FLAG_TIME_STAGES) != 0;
   // Persistent grids follow the number of paths this call can have: a warp that gets only ~1 ray per lane never refills
   // and ends at the SIMD efficiency of its longest ray, so small shards run fewer, longer-lived warps (>= 3 blocks per SM
@@ -409,7 +428,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
     c->wf_grid_extend = full ? c->wf_blocks_extend : (int)we;
     c->wf_grid_shadow = full ? c->wf_blocks_shadow : (int)ws;
   }
-  const bool staged = !((fp->flags & VP_FLAG_PERSISTENT) != 0 || c->tune_persistent);
+  const bool staged = rp || !((fp->flags & VP_FLAG_PERSISTENT) != 0 || c->tune_persistent);
   const bool cs = (fp->flags & VP_FLAG_COUNT_STEPS) != 0;
   if (staged) CU(cudaEventRecord(c->ev_in, stream));
   else if (int rc = join_lanes(c, stream)) return rc;
@@ -417,9 +436,10 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   if (staged && overlap)  // frames in flight: size every lane now rather than one per call (allocation synchronises the device)
     for (int i = 0; i < c->nlanes; i++)
       if (int rc = wf_reserve(c->lane[i], tiles * 32u, levels, samples)) return rc;
-  for (int s = 0; s < fp->spp; s++) {
+  const int passes = rp ? 1 : fp->spp;
+  for (int s = 0; s < passes; s++) {
     p.frame = fp->frame_index + (uint32_t)s;
-    p.write_rgb8 = (s == fp->spp - 1);
+    p.write_rgb8 = (s == passes - 1);
     int rc;
     if (staged) {
       // lanes rotate only when passes can overlap (several samples in this call, or a deferred call)
@@ -454,7 +474,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
 // caller's `stream` orders it: the passes start after what the stream holds now, and - unless the call is deferred
 // (VP_FLAG_DEFER without stats) - the stream waits for the last resolve before anything enqueued later.
 int launch_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream,
-                  VpStats* stats, bool allow_defer)
+                  VpStats* stats, bool allow_defer, const RpArgs* rp = nullptr)
 {
   RenderParams p;
   fill_params(c, cam, fp, p);
@@ -470,9 +490,9 @@ int launch_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float
   const int blocks = grid_blocks(c, tiles);
   const unsigned long long launches_before = c->host_launches;
   if (stats) CU(cudaEventRecord(c->ev0, stream));
-  const bool mega = (fp->flags & VP_FLAG_MEGAKERNEL) || c->sc.area_samples > kMaxAreaSamples || fp->max_bounces < 0;
+  const bool mega = !rp && ((fp->flags & VP_FLAG_MEGAKERNEL) || c->sc.area_samples > kMaxAreaSamples || fp->max_bounces < 0);
   if (!mega) {
-    if (int rc = launch_wavefront(c, cam, fp, accum, rgb8, stream, defer)) return rc;
+    if (int rc = launch_wavefront(c, cam, fp, accum, rgb8, stream, defer, rp)) return rc;
   } else {
     if (int rc = join_lanes(c, stream)) return rc;
     CU(cudaMemsetAsync(c->d_counters.p + 8, 0, sizeof(unsigned long long), stream));
@@ -586,6 +606,8 @@ vp_ctx* vp_create(int device)
   cudaFuncSetAttribute(k_wf_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_reproject<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_reproject<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_extend<false>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
   c->wf_blocks_extend = occ * c->sm_count;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shadow<false>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
@@ -613,6 +635,7 @@ void vp_destroy(vp_ctx* c)
   for (auto& v : c->vols) free_volume(v);
   c->d_vols.release(); c->d_mat.release(); c->d_pl.release(); c->d_al.release(); c->d_sl.release();
   c->d_sph.release(); c->d_tri.release(); c->d_sky.release(); c->d_regions.release(); c->d_counters.release(); c->d_accum.release();
+  c->d_rp_alb.release(); c->d_rp_ill.release(); c->d_rp_ray.release(); c->d_rp_hist_in.release(); c->d_rp_hist_out.release();
   c->d_rgb8.release(); c->d_scratch_in.release(); c->d_scratch_out.release(); c->d_scratch_aux.release();
   for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
   for (WfLane& L : c->lane) {
@@ -764,6 +787,54 @@ int vp_render_fence(vp_ctx* c, void* stream, int frames_back)
   if (bind(c)) return VP_ECUDA;
   if ((unsigned long long)frames_back >= c->ncalls) return 0;  // nothing that old was ever enqueued
   CU(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_call[(c->ncalls - 1 - (unsigned long long)frames_back) % kCallRing], 0));
+  return 0;
+}
+
+static int check_reproject(const vp_ctx* c, const VpCamera* cam, const VpPrevCamera* prev, const VpFrameParams* fp)
+{
+  if (int rc = check_frame(c, cam, fp)) return rc;
+  if (!prev) return fail(VP_EINVAL, "null previous camera");
+  if (fp->max_bounces < 0) return fail(VP_EINVAL, "reprojection needs max_bounces >= 0");
+  if (c->sc.area_samples > kMaxAreaSamples) return fail(VP_EINVAL, "reprojection supports at most %d area-light samples", kMaxAreaSamples);
+  const bool whole = (fp->row_begin == 0 && (fp->row_end == 0 || fp->row_end == fp->height)) && (fp->row_tile <= 0 || fp->row_tile_stride <= 1);
+  if (!whole) return fail(VP_EINVAL, "reprojection renders whole frames (pass 2 reads the 3x3 neighbourhood and the history)");
+  return 0;
+}
+
+int vp_render_reproject_device(vp_ctx* c, const VpCamera* cam, const VpPrevCamera* prev, const VpFrameParams* fp, const void* history_in_dev,
+                               void* history_out_dev, void* rgb8_dev, void* stream, VpStats* stats)
+{
+  if (int rc = check_reproject(c, cam, prev, fp)) return rc;
+  if (!history_in_dev || !history_out_dev || history_in_dev == history_out_dev) return fail(VP_EINVAL, "history in/out must be two distinct buffers");
+  if (bind(c)) return VP_ECUDA;
+  const size_t n = (size_t)fp->width * fp->height;
+  if (c->d_rp_alb.cap < 3 * n || c->d_rp_ill.cap < 3 * n || c->d_rp_ray.cap < n) {
+    if (quiesce(c)) return VP_ECUDA;
+    CU(c->d_rp_alb.reserve(3 * n)); CU(c->d_rp_ill.reserve(3 * n)); CU(c->d_rp_ray.reserve(n));
+  }
+  RpArgs rp;
+  rp.prev = *prev; rp.hist_in = (const float*)history_in_dev; rp.hist_out = (float*)history_out_dev;
+  return launch_render(c, cam, fp, nullptr, (uint32_t*)rgb8_dev, (cudaStream_t)stream, stats, false, &rp);
+}
+
+int vp_render_reproject(vp_ctx* c, const VpCamera* cam, const VpPrevCamera* prev, const VpFrameParams* fp, const float* history_in,
+                        float* history_out, uint32_t* rgb8, float* albedo, float* illumination, VpStats* stats)
+{
+  if (int rc = check_reproject(c, cam, prev, fp)) return rc;
+  if (!history_in || !history_out || history_in == history_out) return fail(VP_EINVAL, "history in/out must be two distinct buffers");
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
+  const size_t n = (size_t)fp->width * fp->height;
+  CU(c->d_rp_hist_in.reserve(3 * n)); CU(c->d_rp_hist_out.reserve(3 * n)); CU(c->d_rgb8.reserve(n));
+  CU(cudaMemcpyAsync(c->d_rp_hist_in.p, history_in, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  VpStats local;
+  if (int rc = vp_render_reproject_device(c, cam, prev, fp, c->d_rp_hist_in.p, c->d_rp_hist_out.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream,
+                                          stats ? stats : &local))
+    return rc;
+  CU(cudaMemcpyAsync(history_out, c->d_rp_hist_out.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (rgb8) CU(cudaMemcpyAsync(rgb8, c->d_rgb8.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (albedo) CU(cudaMemcpyAsync(albedo, c->d_rp_alb.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (illumination) CU(cudaMemcpyAsync(illumination, c->d_rp_ill.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -70,6 +70,14 @@ struct WfParams {
   float4* accum;
   uint32_t* rgb8;
   unsigned long long* counters;  // same slots as RenderParams
+  // reprojection frame mode (Renderer::Tick static-camera branch, renderer.cpp:1997-2101)
+  int reproject;          // 1: TraceReproject variant of the shade stage, resolve splits albedo / illumination
+  float* rp_alb;          // albedoBuffer        [W*H] float3
+  float* rp_ill;          // illuminationBuffer  [W*H] float3
+  float4* rp_ray;         // rayData             [W*H]: intersection point, w = material byte
+  const float* hist_in;   // illuminationHistoryBuffer [W*H] float3
+  float* hist_out;        // tempIlluminationBuffer    [W*H] float3
+  VpPrevCamera prev;
 };
 
 __device__ __forceinline__ bool wf_row_selected(const WfParams& p, int y)
@@ -144,9 +152,14 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant_
     if (on) {
       const uint32_t px = (uint32_t)y * (uint32_t)p.W + (uint32_t)x;
       uint32_t seed = pixel_seed(px, p.frame, npix, p.seed);
-      const float rx = rnd(seed) * p.aa;
-      const float ry = rnd(seed) * p.aa;
-      const Ray pr = primary_ray(p.cam, (float)x + rx, (float)y + ry, p.W, p.H, seed);
+      Ray pr;
+      if (p.reproject) {
+        pr = primary_ray_nodof(p.cam, (float)x, (float)y, p.W, p.H);  // renderer.cpp:2010: no jitter, no draws
+      } else {
+        const float rx = rnd(seed) * p.aa;
+        const float ry = rnd(seed) * p.aa;
+        pr = primary_ray(p.cam, (float)x + rx, (float)y + ry, p.W, p.H, seed);
+      }
       p.st.r0[path] = make_float4(pr.O.x, pr.O.y, pr.O.z, __uint_as_float(pack_r0w(0, p.max_bounces, 0)));
       p.st.r1[path] = make_float4(pr.D.x, pr.D.y, pr.D.z, __uint_as_float(seed));
       p.st.term[path] = make_float4(0, 0, 0, 0);
@@ -402,6 +415,12 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
   int depth = (int)((rb >> 8) & 0xFFu) - 1;
   int top = (int)((rb >> 16) & 0xFFu);
   const int m = ray.mat;
+  if (p.reproject && p.iter == 0) {  // RayDataReproject::GetRayInfo(primaryRay), renderer.h:31-34 (a primary ray is never inside a medium)
+    int x, y;
+    wf_pixel_of(p, path, x, y);
+    const f3 P = isect(ray);
+    __stcg(p.rp_ray + ((size_t)y * p.W + x), make_float4(P.x, P.y, P.z, __uint_as_float((uint32_t)m & 255u)));
+  }
   if (m == VP_MAT_NONE) {
     cn.sky++;
     const f3 t = sample_sky(sc, ray.D);
@@ -419,6 +438,12 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
       nr = spawn(offset_ray(isect(ray), ray.N), add(refl, muls(random_sphere_sample(seed), rough)), 0);
       const f3 al = albedo_of(sc, m);
       L.type = 0; L.mx = al.x; L.my = al.y; L.mz = al.z;
+    } else if (m <= 4 && p.reproject) {  // TraceNonMetal, renderer.cpp:1342-1358: no Fresnel draw, always the Lambert branch
+      const f3 rdir = add(ray.N, random_sphere_sample(seed));
+      illum = true;
+      nr = spawn(offset_ray(isect(ray), ray.N), rdir, 0);
+      const f3 al = albedo_of(sc, m);
+      L.type = 4; L.mx = al.x; L.my = al.y; L.mz = al.z;
     } else if (m <= 4) {
       if (rnd(seed) > schlick_nonmetal(dot3(neg(ray.D), ray.N))) {
         const f3 rdir = add(ray.N, random_sphere_sample(seed));
@@ -682,7 +707,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_resolve(const __grid_constant__
     const int top = (int)((__float_as_uint(p.st.r0[path].w) >> 16) & 0xFFu);
     const float4 t4 = p.st.term[path];
     f3 R = v3(t4.x, t4.y, t4.z);
-    for (int l = top - 1; l >= 0; l--) {
+    for (int l = top - 1; l >= (p.reproject ? 1 : 0); l--) {
       const float4 m4 = p.st.lm[(size_t)l * cap + path];
       const float4 a4 = p.st.la[(size_t)l * cap + path];
       const int type = __float_as_int(m4.w);
@@ -690,6 +715,22 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_resolve(const __grid_constant__
       if (type == 0) R = mul(R, M);
       else if (type == 1) R = add(add(v3s(0), A), mul(R, M));
       else if (type == 2) R = mul(add(R, A), M);
+      else if (type == 4) R = mul(add(add(v3s(0), A), R), M);  // TraceNonMetal: albedo * ((0 + incLight) + child)
+    }
+    if (p.reproject) {
+      // the first hit keeps albedo and illumination apart (AlbedoIlluminationData of the primary ray, renderer.cpp:2013-2018)
+      f3 alb = R, ill = v3s(1.0f);  // miss / emissive: {colour, 1}
+      if (top > 0) {
+        const float4 m4 = p.st.lm[path];
+        const float4 a4 = p.st.la[path];
+        const int type = __float_as_int(m4.w);
+        const f3 A = v3(a4.x, a4.y, a4.z);
+        alb = v3(m4.x, m4.y, m4.z);
+        ill = type == 0 ? R : (type == 4 ? add(add(v3s(0), A), R) : add(R, A));
+      }
+      p.rp_alb[3 * (size_t)px] = alb.x; p.rp_alb[3 * (size_t)px + 1] = alb.y; p.rp_alb[3 * (size_t)px + 2] = alb.z;
+      p.rp_ill[3 * (size_t)px] = ill.x; p.rp_ill[3 * (size_t)px + 1] = ill.y; p.rp_ill[3 * (size_t)px + 2] = ill.z;
+      continue;
     }
     float4 acc = p.accum[px];
     const float weight = 1.0f / ((float)p.frame + 1.0f);
@@ -702,6 +743,126 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_resolve(const __grid_constant__
     p.accum[px] = acc;
     if (p.write_rgb8 && p.rgb8) p.rgb8[px] = rgb8(reinhard_jodie(v3(acc.x, acc.y, acc.z)));
   }
+}
+
+// ---- reprojection pass 2 (renderer.cpp:2023-2099): one lane per pixel -----------------------------------------
+__device__ __forceinline__ bool rp_valid_screen(int x, int y, int W, int H)  // IsValidScreen on an int2 (renderer.cpp:1640-1643)
+{
+  return (float)x >= 0.0f && (float)x < (float)W && (float)y >= 0.0f && (float)y < (float)H;
+}
+__device__ __forceinline__ f3 rp_ycocg(f3 c)  // RGBToYCoCg, renderer.cpp:832-838
+{
+  const float k = 0.5f * 256.0f / 255.0f;
+  return v3(dot3(c, v3(1, 2, 1)) * 0.25f, dot3(c, v3(2, 0, -2)) * 0.25f + k, dot3(c, v3(-1, 2, -1)) * 0.25f + k);
+}
+__device__ __forceinline__ f3 rp_rgb(f3 c)  // YCoCgToRGB, renderer.cpp:841-850
+{
+  const float k = 0.5f * 256.0f / 255.0f;
+  const float Y = c.x, Co = c.y - k, Cg = c.z - k;
+  return v3(Y + Co - Cg, Y + Cg, Y - Co - Cg);
+}
+__device__ __forceinline__ float rp_clamp(float f, float a, float b)  // clamp = fmaxf(a, fminf(f, b)), tmpl8math.h:401-409,2105
+{
+  const float lo = f < b ? f : b;
+  return a > lo ? a : lo;
+}
+__device__ __forceinline__ f3 rp_sample_history(const float* hist, float u, float v, int W, int H)  // renderer.cpp:777-830
+{
+  u -= 1.0f / (float)W / 2.0f;
+  v -= 1.0f / (float)H / 2.0f;
+  const float px = u * (float)W, py = v * (float)H;
+  const int tlx = f2i(px), tly = f2i(py);
+  const float fx = px - (float)tlx, fy = py - (float)tly;
+  const float gx = 1 - fx, gy = 1 - fy;
+  const bool v1 = rp_valid_screen(tlx, tly, W, H), v2 = rp_valid_screen(tlx + 1, tly, W, H);
+  const bool v3_ = rp_valid_screen(tlx, tly + 1, W, H), v4 = rp_valid_screen(tlx + 1, tly + 1, W, H);
+  float w1 = v1 ? gx * gy : 0.0f, w2 = v2 ? fx * gy : 0.0f, w3 = v3_ ? gx * fy : 0.0f, w4 = v4 ? fx * fy : 0.0f;
+  const float total = w1 + w2 + w3 + w4;
+  const float rcp = 1.0f / total;
+  w1 *= rcp; w2 *= rcp; w3 *= rcp; w4 *= rcp;
+  f3 avg = v3s(0.0f);
+  if (v1) avg = add(avg, muls(ld3(hist + 3 * ((size_t)tly * W + tlx)), w1));
+  if (v2) avg = add(avg, muls(ld3(hist + 3 * ((size_t)tly * W + tlx + 1)), w2));
+  if (v3_) avg = add(avg, muls(ld3(hist + 3 * ((size_t)(tly + 1) * W + tlx)), w3));
+  if (v4) avg = add(avg, muls(ld3(hist + 3 * ((size_t)(tly + 1) * W + tlx + 1)), w4));
+  return avg;
+}
+__device__ __forceinline__ f3 rp_clamp_history(f3 hist, f3 sample, const float* illum, int x, int y, int W, int H)  // renderer.cpp:855-910
+{
+  sample = rp_ycocg(sample);
+  hist = rp_ycocg(hist);
+  unsigned n = 1;
+  f3 avg = sample, var = mul(sample, sample);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int k = i < 4 ? i : i + 1;  // the 3x3 ring in row-major order, centre skipped
+    const int qx = x + (k % 3) - 1, qy = y + (k / 3) - 1;
+    if (rp_valid_screen(qx, qy, W, H)) {
+      const f3 f = rp_ycocg(ld3(illum + 3 * ((size_t)qx + (size_t)qy * W)));
+      avg = add(avg, f);
+      var = add(var, mul(f, f));
+      n++;
+    }
+  }
+  const float inv = 1.0f / (float)n;
+  avg = muls(avg, inv);
+  var = muls(var, inv);
+  const f3 sigma = v3(sqrtf(stdmax(0.0f, var.x - (avg.x * avg.x))), sqrtf(stdmax(0.0f, var.y - (avg.y * avg.y))),
+                      sqrtf(stdmax(0.0f, var.z - (avg.z * avg.z))));
+  const f3 lo = sub(avg, muls(sigma, 0.75f)), hi = add(avg, muls(sigma, 0.75f));
+  hist = v3(rp_clamp(hist.x, lo.x, hi.x), rp_clamp(hist.y, lo.y, hi.y), rp_clamp(hist.z, lo.z, hi.z));
+  hist = rp_rgb(hist);
+  return v3(hist.x > 0.0f ? hist.x : 0.0f, hist.y > 0.0f ? hist.y : 0.0f, hist.z > 0.0f ? hist.z : 0.0f);
+}
+__device__ __forceinline__ float rp_history_weight(int m)  // renderer.cpp:2051-2086
+{
+  if (m <= 4) return 0.8f;
+  if (m <= 8) return 0.5f;
+  if (m <= 14) return 0.9f;
+  if (m == 15) return 0.0f;
+  return 0.9f;
+}
+
+template <bool CS>
+__global__ void __launch_bounds__(kWfBlock) k_wf_reproject(const __grid_constant__ WfParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Staged stg = wf_stage_scene(p.sc, smem);
+  Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
+  const int W = p.W, H = p.H;
+  const f3 pc = ld3(p.prev.cam_pos);
+  const f3 nl = ld3(p.prev.left_normal), nr = ld3(p.prev.right_normal), nt = ld3(p.prev.top_normal), nb = ld3(p.prev.bottom_normal);
+  for (uint32_t path = blockIdx.x * blockDim.x + threadIdx.x; path < p.st.cap; path += gridDim.x * blockDim.x) {
+    int x, y;
+    if (!wf_pixel_of(p, path, x, y)) continue;
+    const size_t px = (size_t)x + (size_t)y * W;
+    const float4 rd = p.rp_ray[px];
+    const f3 P = v3(rd.x, rd.y, rd.z);
+    const f3 newS = ld3(p.rp_ill + 3 * px);
+    // Camera::PointToUV (template/camera.h:34-50) + half a pixel
+    const f3 delta = sub(P, pc);
+    const float dl = dot3(nl, delta), dr = dot3(nr, delta), dt = dot3(nt, delta), db = dot3(nb, delta);
+    const float u = dl / (dl + dr) + 1.0f / (float)W / 2.0f;
+    const float v = dt / (dt + db) + 1.0f / (float)H / 2.0f;
+    bool reuse = u >= 0.0f && u < 1.0f && v >= 0.0f && v < 1.0f;  // IsValid
+    if (reuse) {  // IsOccludedPrevFrame, renderer.cpp:767-774
+      const f3 dn = normalize3(sub(P, pc));
+      const f3 pos = offset_ray(P, neg(dn));
+      const f3 dd = sub(pos, pc);
+      reuse = !is_occluded<CS>(p.sc, stg, pc, dn, sqrtf(dot3(dd, dd)), cn);
+    }
+    f3 fin = newS;
+    if (reuse) {
+      f3 h = rp_sample_history(p.hist_in, u, v, W, H);
+      h = rp_clamp_history(h, newS, p.rp_ill, x, y, W, H);
+      const float w = rp_history_weight((int)(__float_as_uint(rd.w) & 255u));
+      fin = add(newS, muls(sub(h, newS), w));  // lerp(a, b, t) = a + t * (b - a)
+    }
+    p.hist_out[3 * px] = fin.x; p.hist_out[3 * px + 1] = fin.y; p.hist_out[3 * px + 2] = fin.z;
+    if (p.rgb8) p.rgb8[px] = rgb8(reinhard_jodie(mul(ld3(p.rp_alb + 3 * px), fin)));
+  }
+  wf_add_counter(p.counters + 1, cn.shadow);
+  if (CS) wf_add_counter(p.counters + 3, cn.steps);
 }
 
 }  // namespace vp

@@ -70,6 +70,14 @@ def look_at(pos, target, width, height, focal_distance=1.0, defocus_jitter=0.0):
                   out.focal_distance, out.defocus_jitter)
 
 
+def prev_camera(pos, target, width, height):
+    """What Renderer::CopyToPrevCamera keeps of a camera looking from pos at target: position + frustum-plane normals."""
+    out = abi.VpPrevCamera()
+    p, t = _f3(pos), _f3(target)
+    dll().vph_camera_prev(p.ctypes.data, t.ctypes.data, int(width), int(height), C.byref(out))
+    return out
+
+
 def cos_degrees(d):
     return float(dll().vph_cos_degrees(float(d)))
 

@@ -299,6 +299,26 @@ void Camera::UpdateFrame()  // template/camera.h:121-123,150-170 with no key pre
   topRight = camPos + 2 * ahead + ASPECT * right + up;
   bottomLeft = camPos + 2 * ahead - ASPECT * right - up;
 }
+void Camera::SetFrustumNormals()
+{
+  const float ASPECT = static_cast<float>(width) / static_cast<float>(height);
+  const float3 leftFrustumDirection = (2 * ahead) - (ASPECT * right);
+  const float3 rightFrustumDirection = (2 * ahead) + (ASPECT * right);
+  const float3 topFrustumDirection = (2 * ahead) + up;
+  const float3 bottomFrustumDirection = (2 * ahead) - up;
+  leftNormal = cross(up, leftFrustumDirection);
+  rightNormal = cross(rightFrustumDirection, up);
+  topNormal = cross(right, topFrustumDirection);
+  bottomNormal = cross(bottomFrustumDirection, right);
+}
+VpPrevCamera Camera::PackPrev() const
+{
+  VpPrevCamera c;
+  auto st = [](float* d, const float3& v) { d[0] = v.x, d[1] = v.y, d[2] = v.z; };
+  st(c.cam_pos, camPos), st(c.left_normal, leftNormal), st(c.right_normal, rightNormal), st(c.top_normal, topNormal),
+      st(c.bottom_normal, bottomNormal);
+  return c;
+}
 VpCamera Camera::Pack() const
 {
   VpCamera c;
@@ -397,6 +417,14 @@ void vph_camera_look_at(const float pos[3], const float target[3], int width, in
   c.focalDistance = focal_distance, c.defocusJitter = defocus_jitter;
   c.LookAt(float3(pos[0], pos[1], pos[2]), float3(target[0], target[1], target[2]));
   *out = c.Pack();
+}
+
+void vph_camera_prev(const float pos[3], const float target[3], int width, int height, VpPrevCamera* out)
+{
+  Camera c(width, height);
+  c.LookAt(float3(pos[0], pos[1], pos[2]), float3(target[0], target[1], target[2]));
+  c.SetFrustumNormals();
+  *out = c.PackPrev();
 }
 
 float vph_cos_degrees(float d) { return CosDegrees(d); }

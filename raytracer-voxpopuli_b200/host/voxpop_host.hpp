@@ -130,6 +130,10 @@ class Camera {  // template/camera.h
   void UpdateFrame();
   void LookAt(const float3& pos, const float3& target) { camPos = pos; camTarget = target; UpdateFrame(); }
   VpCamera Pack() const;
+  // Camera::SetFrustumNormals (template/camera.h:53-66) and the part of the camera Renderer::CopyToPrevCamera keeps
+  void SetFrustumNormals();
+  VpPrevCamera PackPrev() const;
+  float3 leftNormal, rightNormal, topNormal, bottomNormal;
   int width, height;
   float3 ahead, right, up;
   float3 camPos, camTarget;

@@ -143,6 +143,25 @@ class Session:
                                          rgb8.ctypes.data if want_rgb8 else None, C.byref(st)), "render")
         return accum, rgb8, st
 
+    def render_reproject(self, cam: Camera, prev, fp, history=None, want_buffers=True):
+        """One frame of the reprojection mode (Renderer::Tick static-camera branch).  prev: abi.VpPrevCamera;
+        history: float32 [H, W, 3] of the previous frame (zeros if None).  Returns (new history, rgb8, albedo,
+        illumination, stats)."""
+        W, H = fp.width, fp.height
+        if history is None:
+            history = np.zeros((H, W, 3), dtype=np.float32)
+        assert history.dtype == np.float32 and history.flags.c_contiguous and history.size == W * H * 3
+        out = np.zeros((H, W, 3), dtype=np.float32)
+        rgb8 = np.zeros((H, W), dtype=np.uint32)
+        alb = np.zeros((H, W, 3), dtype=np.float32) if want_buffers else None
+        ill = np.zeros((H, W, 3), dtype=np.float32) if want_buffers else None
+        st = abi.VpStats()
+        cc = cam.to_c()
+        self.lib.check(self.lib.c_render_reproject(self.ctx, C.byref(cc), C.byref(prev), C.byref(fp), history.ctypes.data, out.ctypes.data,
+                                                   rgb8.ctypes.data, alb.ctypes.data if want_buffers else None,
+                                                   ill.ctypes.data if want_buffers else None, C.byref(st)), "render_reproject")
+        return out, rgb8, alb, ill, st
+
     def trace_primary(self, cam: Camera, fp):
         hits = np.zeros(fp.width * fp.height, dtype=abi.HIT_DTYPE)
         cc = cam.to_c()

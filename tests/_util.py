@@ -92,3 +92,27 @@ def params(fpd, **over):
                            aa_strength=d["aa_strength"], row_begin=d.get("row_begin", 0), row_end=d.get("row_end", 0),
                            row_tile=d.get("row_tile", 0), row_tile_stride=d.get("row_tile_stride", 1),
                            row_tile_phase=d.get("row_tile_phase", 0), flags=d.get("flags", 0))
+
+
+def reproject_sequence(lib, idx, width, height, frames=3, max_bounces=None):
+    """`frames` frames of the reprojection mode (Renderer::Tick static-camera branch) with a camera that drifts between
+    frames, each frame reprojecting into the previous camera and history.  Returns per frame
+    (history, rgb8, albedo, illumination, [primary, secondary, shadow, exit, steps])."""
+    sc, cam, fpd = small_config(idx, width, height)
+    if max_bounces is not None:
+        fpd["max_bounces"] = max_bounces
+    pos = np.array(cam.cam_pos, np.float32)
+    tl, tr, bl = (np.array(v, np.float32) for v in (cam.top_left, cam.top_right, cam.bottom_left))
+    target = tl + (tr - tl) * np.float32(0.5) + (bl - tl) * np.float32(0.5)  # centre of the image plane
+    out, hist = [], None
+    with vp.Session(lib) as s:
+        s.set_scene(sc)
+        prev = host.prev_camera(pos, target, width, height)
+        for f in range(frames):
+            camf = host.look_at(pos, target, width, height)
+            h, rgb, alb, ill, st = s.render_reproject(camf, prev, params(fpd, spp=1, frame_index=f), hist)
+            out.append((h, rgb, alb, ill, [st.primary_rays, st.secondary_rays, st.shadow_rays, st.exit_rays, st.dda_steps]))
+            hist = h
+            prev = host.prev_camera(pos, target, width, height)
+            pos = pos + np.array([0.01, 0.004, -0.006], np.float32)
+    return out

@@ -98,3 +98,16 @@ def test_vox_loader_matches_fixtures():
         g2, m2 = host.load_vox(f"/root/reference/assets/{name}.vox", n)
         assert np.array_equal(grid, g2), name
         assert np.array_equal(bits(mats), bits(m2)), name
+
+
+@pytest.mark.parametrize("idx", [2, 3, 4])
+def test_reprojection_golden(oracle, idx):
+    """Reprojection frame mode against goldens generated from the reference build (tools/make_golden.py)."""
+    from _util import reproject_sequence
+    g = np.load(os.path.join(GOLDEN, f"reproject_cfg{idx}_64x36.npz"))
+    out = reproject_sequence(oracle, idx, 64, 36)
+    for f, o in enumerate(out):
+        assert np.array_equal(bits(g[f"history{f}"]), bits(o[0])), f"frame {f} history"
+        assert np.array_equal(g[f"rgb8_{f}"], o[1]), f"frame {f} rgb8"
+        assert list(g[f"stats{f}"]) == o[4]
+    assert np.array_equal(bits(g["albedo2"]), bits(out[2][2])) and np.array_equal(bits(g["illumination2"]), bits(out[2][3]))

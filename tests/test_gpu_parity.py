@@ -302,3 +302,77 @@ def test_frames_in_flight(product, oracle):
         torch.cuda.synchronize(dev)
     assert np.array_equal(bits(got), bits(want)), "frames in flight changed the accumulator"
     assert np.array_equal(got_rgb, want_rgb)
+
+
+@pytest.mark.parametrize("idx", [1, 2, 3, 4, 5])
+def test_reprojection_vs_oracle(product, oracle, idx):
+    """Second frame mode (vp_render_reproject): pass-1 buffers, the reprojected history and the RGB8 image of three
+    drifting-camera frames against the oracle - bit-identical, counters included - and against the committed goldens
+    generated from the reference build."""
+    from _util import reproject_sequence
+    want = reproject_sequence(oracle, idx, 96, 54)
+    got = reproject_sequence(product, idx, 96, 54)
+    for f, (w, g) in enumerate(zip(want, got)):
+        for k, name in ((2, "albedo"), (3, "illumination"), (0, "history")):
+            d = np.abs(w[k].astype(np.float64) - g[k].astype(np.float64))
+            nbit = int(np.count_nonzero((bits(w[k]) != bits(g[k])).any(axis=-1)))
+            print(f"cfg{idx} frame {f} {name}: max|d|={d.max():.3g} pixels not bit-identical={nbit}")
+            assert d.max() <= RGB_ABS_TOL and nbit == 0, f"cfg{idx} frame {f}: {name}"
+        assert np.array_equal(w[1], g[1]), f"cfg{idx} frame {f}: rgb8"
+        assert w[4][:4] == g[4][:4], f"cfg{idx} frame {f}: ray counters {w[4]} vs {g[4]}"
+    if idx in (2, 3, 4):
+        gold = np.load(os.path.join(GOLDEN, f"reproject_cfg{idx}_64x36.npz"))
+        out = reproject_sequence(product, idx, 64, 36)
+        for f, o in enumerate(out):
+            assert np.array_equal(bits(gold[f"history{f}"]), bits(o[0])) and np.array_equal(gold[f"rgb8_{f}"], o[1])
+
+
+def test_reprojection_device_and_errors(product, oracle):
+    """vp_render_reproject_device on caller-owned history ping-pong buffers (torch tensors), interleaved with ordinary
+    accumulating frames on the same context; plus the argument checks."""
+    import torch
+    from _util import host
+    sc, cam, fpd = small_config(2, 128, 72)
+    W, H = fpd["width"], fpd["height"]
+    pos = np.array(cam.cam_pos, np.float32)
+    tl, tr, bl = (np.array(v, np.float32) for v in (cam.top_left, cam.top_right, cam.bottom_left))
+    target = tl + (tr - tl) * np.float32(0.5) + (bl - tl) * np.float32(0.5)
+    prev = host.prev_camera(pos, target, W, H)
+    camf = host.look_at(pos + np.array([0.02, 0, 0], np.float32), target, W, H)
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        h1, _, _, _, _ = s.render_reproject(camf, prev, params(fpd, frame_index=0))
+        h2, rgb2, _, _, _ = s.render_reproject(camf, prev, params(fpd, frame_index=1), h1)
+    dev = torch.device("cuda", 0)
+    hist = [torch.zeros((H, W, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+    rgb = torch.zeros((H, W), dtype=torch.int32, device=dev)
+    acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    cc = camf.to_c()
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        for f in range(2):
+            fp = params(fpd, frame_index=f)
+            product.check(product.c_render_reproject_device(s.ctx, C.byref(cc), C.byref(prev), C.byref(fp), hist[f % 2].data_ptr(),
+                                                            hist[(f + 1) % 2].data_ptr(), rgb.data_ptr(), stream.cuda_stream, None), "reproject_device")
+            # an accumulating frame in between (deferred: it overlaps the next reprojection frame's start)
+            fpa = params(fpd, frame_index=f, flags=abi.VP_FLAG_DEFER)
+            product.check(product.c_render_device(s.ctx, C.byref(cc), C.byref(fpa), acc.data_ptr(), None, stream.cuda_stream, None), "render_device")
+        product.check(product.c_render_fence(s.ctx, stream.cuda_stream, 0), "fence")
+        torch.cuda.synchronize(dev)
+        assert np.array_equal(bits(hist[0].cpu().numpy()), bits(h2))
+        assert np.array_equal(rgb.cpu().numpy().view(np.uint32), rgb2)
+        # argument checks
+        fp = params(fpd, frame_index=0)
+        assert product.c_render_reproject_device(s.ctx, C.byref(cc), C.byref(prev), C.byref(fp), hist[0].data_ptr(), hist[0].data_ptr(),
+                                                 rgb.data_ptr(), stream.cuda_stream, None) != 0  # aliasing history
+        fp = params(fpd, frame_index=0, row_begin=8, row_end=16)
+        assert product.c_render_reproject_device(s.ctx, C.byref(cc), C.byref(prev), C.byref(fp), hist[0].data_ptr(), hist[1].data_ptr(),
+                                                 rgb.data_ptr(), stream.cuda_stream, None) != 0  # row ranges
+        fp = params(fpd, frame_index=0, max_bounces=-1)
+        assert product.c_render_reproject_device(s.ctx, C.byref(cc), C.byref(prev), C.byref(fp), hist[0].data_ptr(), hist[1].data_ptr(),
+                                                 rgb.data_ptr(), stream.cuda_stream, None) != 0
+    with vp.Session(oracle) as s:  # the accumulating frames were not disturbed
+        s.set_scene(sc)
+        want_acc, _, _ = s.render(camf, params(fpd, spp=2))
+    assert np.array_equal(bits(acc.cpu().numpy()), bits(want_acc))

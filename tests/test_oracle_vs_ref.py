@@ -91,3 +91,19 @@ def test_small_pins(ref, oracle):
         ref.dll.vpref_sampling(int(s), nrm.ctypes.data, x.ctypes.data, C.byref(sa))
         oracle.dll.vpo_sampling(int(s), nrm.ctypes.data, y.ctypes.data, C.byref(sb))
         assert np.array_equal(bits(x), bits(y)) and sa.value == sb.value
+
+
+@pytest.mark.parametrize("idx", [1, 2, 3, 4, 5])
+def test_reprojection_frames_bit_exact(ref, oracle, idx):
+    """Second frame mode (TraceReproject + history reprojection, renderer.cpp:1330-1586,1997-2101): three frames with a
+    drifting camera; history, albedo, illumination, RGB8 and the ray / step counters must be identical."""
+    from _util import reproject_sequence
+    a = reproject_sequence(ref, idx, 80, 45)
+    b = reproject_sequence(oracle, idx, 80, 45)
+    for f, (x, y) in enumerate(zip(a, b)):
+        for k, name in ((0, "history"), (2, "albedo"), (3, "illumination")):
+            assert np.array_equal(bits(x[k]), bits(y[k])), f"cfg{idx} frame {f}: {name} differs"
+        assert np.array_equal(x[1], y[1]), f"cfg{idx} frame {f}: rgb8 differs"
+        assert x[4] == y[4], f"cfg{idx} frame {f}: counters {x[4]} vs {y[4]}"
+    # the history is really used: the last frame differs from its own illumination buffer
+    assert np.count_nonzero(bits(a[-1][0]) != bits(a[-1][3])) > 0

@@ -56,6 +56,17 @@ def main():
     with open(os.path.join(GOLDEN, "fullres_hit_digests.json"), "w") as f:
         json.dump(digests, f, indent=1, sort_keys=True)
 
+    # ---- reprojection frame mode: three drifting-camera frames per config -------------------
+    from _util import reproject_sequence
+    for idx in (2, 3, 4):
+        out = reproject_sequence(ref, idx, *SMALL)
+        blob = {}
+        for f, o in enumerate(out):
+            blob[f"history{f}"] = o[0]; blob[f"rgb8_{f}"] = o[1]; blob[f"stats{f}"] = np.array(o[4], np.uint64)
+        blob["albedo2"] = out[2][2]; blob["illumination2"] = out[2][3]
+        np.savez_compressed(os.path.join(GOLDEN, f"reproject_cfg{idx}_64x36.npz"), **blob)
+        print("reproject", idx, out[2][4], flush=True)
+
     # ---- small pins -----------------------------------------------------------------------
     d = ref.dll
     rng = np.random.default_rng(7)
