@@ -157,6 +157,10 @@ class Renderer {
   // push voxelVolumes / materials / lights / prims / sky to the device ("dirty" call, between frames)
   void UploadScene();
   void Update();                                  // one accumulated frame, renderer.cpp:1646-1891
+  // the static-camera branch of Tick (renderer.cpp:1997-2101): one reprojected frame into screenPixels; keeps
+  // illuminationHistoryBuffer, and CopyToPrevCamera() (renderer.cpp:1893-1902) is the caller's move, as in the reference
+  void UpdateReproject();
+  void CopyToPrevCamera() { camera.SetFrustumNormals(); prevCamera = camera; }
   float3 Trace(Ray& ray, int depth, uint32_t seed);  // Renderer::Trace with an explicit RNG state
   int32_t FindNearest(Ray& ray);                  // renderer.cpp:946-1018
   bool IsOccluded(Ray& ray) const;                // renderer.cpp:209-243
@@ -174,7 +178,8 @@ class Renderer {
   std::vector<float> skyPixels;
   std::vector<float> accumulator;    // W*H float4
   std::vector<uint32_t> screenPixels;  // W*H RGB8 (screen->pixels)
-  Camera camera;
+  std::vector<float> illuminationHistoryBuffer, tempIlluminationBuffer;  // W*H float3 (renderer.h:242-243)
+  Camera camera, prevCamera;
   std::vector<std::shared_ptr<Material>> materials;
   std::vector<PointLight> pointLights;
   std::vector<SphereAreaLight> areaLights;

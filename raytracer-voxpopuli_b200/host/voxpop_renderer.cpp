@@ -100,6 +100,21 @@ void Renderer::Update()  // renderer.cpp:1646-1891
   numRenderedFrames++;
 }
 
+void Renderer::UpdateReproject()  // renderer.cpp:1997-2101
+{
+  const size_t n = (size_t)width * height * 3;
+  if (illuminationHistoryBuffer.size() != n) illuminationHistoryBuffer.assign(n, 0.0f);
+  tempIlluminationBuffer.resize(n);
+  const VpCamera cam = camera.Pack();
+  const VpPrevCamera prev = prevCamera.PackPrev();
+  const VpFrameParams fp = frame_params(*this, 1);
+  if (vp_render_reproject(ctx_, &cam, &prev, &fp, illuminationHistoryBuffer.data(), tempIlluminationBuffer.data(), screenPixels.data(), nullptr,
+                          nullptr, &lastStats))
+    throw std::runtime_error(vp_last_error());
+  illuminationHistoryBuffer.swap(tempIlluminationBuffer);  // renderer.cpp:2100
+  numRenderedFrames++;
+}
+
 static VpRay pack_ray(const Ray& ray)
 {
   VpRay r;
@@ -167,6 +182,36 @@ extern "C" int vphr_demo_render(const char* vox_path, const uint8_t* grid, uint3
     memcpy(accum_out, r.accumulator.data(), r.accumulator.size() * sizeof(float));
     memcpy(rgb8_out, r.screenPixels.data(), r.screenPixels.size() * sizeof(uint32_t));
     *rays_out = rays;
+    return 0;
+  } catch (const std::exception& e) {
+    return -1;
+  }
+}
+
+// Test hook: the same scene through the mirror's reprojection mode with a camera that moves between frames
+// (tests/test_gpu_parity.py::test_cpp_renderer_mirror_reproject replays it through the oracle).
+extern "C" int vphr_demo_reproject(const uint8_t* grid, uint32_t n, int width, int height, int frames, int max_bounces, float* history_out,
+                                   uint32_t* rgb8_out)
+{
+  try {
+    Renderer r(width, height);
+    Scene s(float3(0, 0, 0), n);
+    memcpy(s.grid.data(), grid, s.grid.size());
+    s.SetTransform(float3(0, 0.3f, 0));
+    r.voxelVolumes.push_back(s);
+    r.pointLights.resize(1);
+    r.pointLights[0].data.position = float3(0.5f, 1.6f, -0.6f);
+    r.pointLights[0].data.color = float3(4, 4, 4);
+    r.maxBounces = max_bounces;
+    r.UploadScene();
+    for (int f = 0; f < frames; f++) {
+      r.camera.LookAt(float3(0.5f + 0.01f * (float)f, 0.55f, -0.75f), float3(0.5f, 0.3f, 0.5f));
+      if (f == 0) r.CopyToPrevCamera();
+      r.UpdateReproject();
+      r.CopyToPrevCamera();
+    }
+    memcpy(history_out, r.illuminationHistoryBuffer.data(), r.illuminationHistoryBuffer.size() * sizeof(float));
+    memcpy(rgb8_out, r.screenPixels.data(), r.screenPixels.size() * sizeof(uint32_t));
     return 0;
   } catch (const std::exception& e) {
     return -1;

@@ -376,3 +376,30 @@ def test_reprojection_device_and_errors(product, oracle):
         s.set_scene(sc)
         want_acc, _, _ = s.render(camf, params(fpd, spp=2))
     assert np.array_equal(bits(acc.cpu().numpy()), bits(want_acc))
+
+
+def test_cpp_renderer_mirror_reproject(product, oracle):
+    """voxpop::Renderer::UpdateReproject / CopyToPrevCamera (the C++ mirror of the static-camera branch of Tick)."""
+    from _util import host
+    so = os.path.join(os.path.dirname(vp.PRODUCT_SO), "libvoxpop_renderer.so")
+    dll = C.CDLL(so)
+    dll.vphr_demo_reproject.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    grid, n, _ = scenes.load_grid("teapot")
+    W, H, frames, mb = 96, 54, 3, 5
+    hist = np.zeros((H, W, 3), np.float32)
+    rgb = np.zeros((H, W), np.uint32)
+    assert dll.vphr_demo_reproject(grid.ctypes.data, n, W, H, frames, mb, hist.ctypes.data, rgb.ctypes.data) == 0
+    M, iM, a, b = host.make_transform((0, 0, 0), (0, 0.3, 0))
+    sc = vp.SceneDesc(volumes=[vp.Volume(grid, n, a, b, M, iM)], materials=host.default_materials(),
+                      point_lights=[((0.5, 1.6, -0.6), (4, 4, 4))])
+    tgt = (0.5, 0.3, 0.5)
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        h = None
+        for f in range(frames):
+            pos = (np.float32(0.5) + np.float32(0.01) * np.float32(f), 0.55, -0.75)
+            if f == 0:
+                prev = host.prev_camera(pos, tgt, W, H)
+            h, want_rgb, _, _, _ = s.render_reproject(host.look_at(pos, tgt, W, H), prev, vp.frame_params(W, H, max_bounces=mb, spp=1, frame_index=f), h)
+            prev = host.prev_camera(pos, tgt, W, H)
+    assert np.array_equal(bits(hist), bits(h)) and np.array_equal(rgb, want_rgb)
