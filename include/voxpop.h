@@ -209,6 +209,21 @@ int vp_render_reproject_device(vp_ctx* ctx, const VpCamera* cam, const VpPrevCam
                                const void* history_in_dev, void* history_out_dev, void* rgb8_dev, void* cuda_stream,
                                VpStats* stats);
 
+/* ---- gameplay side channels of the frame loop ---------------------------------------------------
+ * Renderer::inLight (renderer.cpp:1228-1240,1445-1449): set by Trace / TraceReproject when a smoke cell of volume 0 (the
+ * player) is hit and the light sampled there exceeds sqrLength 16.  *in_light = 1 if that happened in any frame rendered
+ * since the previous call, then the flag is cleared (Tick clears it once per frame, :2206).  Synchronises the device. */
+int vp_in_light(vp_ctx* ctx, int* in_light);
+/* Renderer::FindNearestPlayer (renderer.cpp:1020-1071) per ray: nearest voxel hit over volumes 1..V-1 (the player
+ * volume 0 is skipped) that ignores the smoke materials SMOKE_LOW_DENSITY..SMOKE_PLAYER (Scene::FindNearestExcept,
+ * template/scene.cpp:813-873); no spheres / triangles.  current_chunk reproduces the rule of :1068-1069 (chunk >= 2:
+ * hits in the last three volumes, and misses, report volume -1); pass 0 to switch it off. */
+int vp_find_nearest_player(vp_ctx* ctx, const VpRay* rays, int n, int current_chunk, VpHit* hits);
+/* The autofocus ray of Tick (renderer.cpp:1987-1991): GetPrimaryRay(W/2, H/2) - its two lens draws taken from `seed` -
+ * walked through every volume's Scene::FindNearest as the reference does (untransformed), focalDistance =
+ * clamp(t, -1, 1e4). */
+int vp_focus_distance(vp_ctx* ctx, const VpCamera* cam, int width, int height, uint32_t seed, float* focal_distance);
+
 /* Library-owned resident accumulator: Renderer::accumulator kept in HBM between frames.
  * vp_accum_reset = allocate/zero (Renderer::ResetAccumulator, renderer.cpp:343-346, plus
  * the memset of Init :702); vp_render_resident = Update() on it; vp_accum_download

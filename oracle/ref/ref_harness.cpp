@@ -468,6 +468,44 @@ int vpref_find_nearest(vpref_ctx* c, const VpRay* rays, int n, VpHit* hits)
   return 0;
 }
 
+// gameplay side channels: the reference's own members / methods
+int vpref_in_light(vpref_ctx* c, int* out)
+{
+  *out = c->r->inLight ? 1 : 0;
+  c->r->inLight = false;  // renderer.cpp:2206
+  return 0;
+}
+
+int vpref_find_nearest_player(vpref_ctx* c, const VpRay* rays, int n, int current_chunk, VpHit* hits)
+{
+  c->r->currentChunk = (size_t)current_chunk;
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; i++)
+  {
+    Ray ray;
+    ray.O = f3(rays[i].o), ray.D = f3(rays[i].d), ray.t = rays[i].t, ray.isInsideGlass = rays[i].inside != 0;
+    ray.rD = float3(1 / ray.D.x, 1 / ray.D.y, 1 / ray.D.z), ray.Dsign = Ray::ComputeDsign(ray.D);
+    g_vp_lastcell = 0xFFFFFFFFu, g_vp_lastface = -1;
+    const int vol = c->r->FindNearestPlayer(ray);
+    fill_hit(&hits[i], ray, vol);
+  }
+  c->r->currentChunk = 0;
+  return 0;
+}
+
+int vpref_focus_distance(vpref_ctx* c, const VpCamera* cam, int W, int H, uint32_t s, float* out)
+{
+  Renderer* r = c->r;
+  g_vp_scrwidth = W, g_vp_scrheight = H;
+  set_camera(r, cam);
+  seed = s;
+  Ray focusRay = r->camera.GetPrimaryRay(SCRWIDTH / 2, SCRHEIGHT / 2);  // renderer.cpp:1987-1991
+  for (auto& scene : r->voxelVolumes)
+    scene.FindNearest(focusRay);
+  *out = clamp(focusRay.t, -1.0f, 1e4f);
+  return 0;
+}
+
 int vpref_is_occluded(vpref_ctx* c, const VpRay* rays, int n, uint8_t* out)
 {
 #pragma omp parallel for schedule(static)

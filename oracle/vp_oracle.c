@@ -61,6 +61,7 @@ typedef struct vpo_ctx {
   VpSphere* sph; int nsph;
   VpTriangle* tri; int ntri;
   float* sky; int skyw, skyh; float sky_contrib; int sky_active;
+  int in_light; /* Renderer::inLight, renderer.h:231 */
 } vpo_ctx;
 
 typedef struct { uint64_t nearest, shadow, exitray, steps, sky; uint32_t lastcell; int lastface; int in_light; } Counters;
@@ -1014,6 +1015,10 @@ int vpo_render(vpo_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* 
         if (fp->max_bounces >= 0) primary++;
       }
       nearest += T.cnt.nearest; shadow += T.cnt.shadow; exitray += T.cnt.exitray; steps += T.cnt.steps; sky += T.cnt.sky;
+      if (T.cnt.in_light) {
+#pragma omp atomic write
+        c->in_light = 1;
+      }
     }
   }
 #ifdef _OPENMP
@@ -1144,6 +1149,10 @@ int vpo_render_reproject(vpo_ctx* c, const VpCamera* cam, const VpPrevCamera* pr
       if (fp->max_bounces >= 0) primary++;
     }
     nearest += T.cnt.nearest; shadow += T.cnt.shadow; exitray += T.cnt.exitray; steps += T.cnt.steps; sky += T.cnt.sky;
+    if (T.cnt.in_light) {
+#pragma omp atomic write
+      c->in_light = 1;
+    }
   }
   const f3 pc = ld3(prev->cam_pos);
   const f3 nl = ld3(prev->left_normal), nr_ = ld3(prev->right_normal), nt = ld3(prev->top_normal), nb = ld3(prev->bottom_normal);
@@ -1225,6 +1234,71 @@ int vpo_find_nearest(vpo_ctx* c, const VpRay* rays, int n, VpHit* hits)
     const int vol = find_nearest(&T, &r);
     fill_hit(&hits[i], &r, vol, &T.cnt);
   }
+  return 0;
+}
+/* ---------- gameplay side channels ---------- */
+int vpo_in_light(vpo_ctx* c, int* out) /* Renderer::inLight; cleared as Tick does once per frame (renderer.cpp:2206) */
+{
+  *out = c->in_light;
+  c->in_light = 0;
+  return 0;
+}
+/* Scene::FindNearestExcept, template/scene.cpp:813-873 */
+static int scene_find_nearest_except(Thread* T, const Volume* v, Ray* ray, int lo, int hi)
+{
+  DDA s;
+  if (!setup_dda(v, ray, &s)) return 0;
+  while (s.t < ray->t) {
+    const uint8_t cell = v->grid[cell_index(v, &s)];
+    T->cnt.steps++;
+    if (cell != VP_MAT_NONE && s.t < ray->t && (cell < lo || cell > hi)) {
+      ray->t = s.t;
+      ray->N = get_normal_voxel(T, ray, v);
+      ray->mat = cell;
+      T->cnt.lastcell = cell_index(v, &s);
+      return 1;
+    }
+    if (!dda_advance(&s, v->n, 0)) break;
+  }
+  return 0;
+}
+/* Renderer::FindNearestPlayer, renderer.cpp:1020-1071 */
+static int find_nearest_player(Thread* T, Ray* ray, int current_chunk)
+{
+  vpo_ctx* c = T->c;
+  int voxelIndex = -2;
+  for (int i = 1; i < c->nvol; i++) { /* skip player */
+    const Volume* v = &c->vol[i];
+    const f3 bO = ray->O, bD = ray->D, brD = ray->rD, bS = ray->Dsign;
+    ray->O = xform_pos_sse(ray->O, v->iM);
+    ray->D = xform_vec_sse(ray->D, v->iM);
+    ray->rD = rcp3(ray->D); /* SlowReciprocal pin */
+    ray->Dsign = compute_dsign(ray->D);
+    if (scene_find_nearest_except(T, v, ray, 9, 14)) voxelIndex = i; /* SMOKE_LOW_DENSITY .. SMOKE_PLAYER */
+    ray->O = bO; ray->D = bD; ray->rD = brD; ray->Dsign = bS;
+  }
+  if (current_chunk >= 2 && (uint64_t)(uint32_t)voxelIndex > (uint64_t)c->nvol - 4u) voxelIndex = -1; /* :1068-1069: uint32 against size_t */
+  return voxelIndex;
+}
+int vpo_find_nearest_player(vpo_ctx* c, const VpRay* rays, int n, int current_chunk, VpHit* hits)
+{
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; i++) {
+    Thread T; memset(&T, 0, sizeof(T)); T.c = c;
+    Ray r = ray_from_abi(&rays[i]);
+    T.cnt.lastcell = 0xFFFFFFFFu; T.cnt.lastface = -1;
+    const int vol = find_nearest_player(&T, &r, current_chunk);
+    fill_hit(&hits[i], &r, vol, &T.cnt);
+  }
+  return 0;
+}
+/* the autofocus ray of Tick, renderer.cpp:1987-1991 */
+int vpo_focus_distance(vpo_ctx* c, const VpCamera* cam, int W, int H, uint32_t seed, float* out)
+{
+  Thread T; memset(&T, 0, sizeof(T)); T.c = c; T.seed = seed;
+  Ray fr = primary_ray(&T, cam, (float)(W / 2), (float)(H / 2), W, H);
+  for (int i = 0; i < c->nvol; i++) scene_find_nearest(&T, &c->vol[i], &fr); /* scene.FindNearest(focusRay): untransformed */
+  *out = clamp1(fr.t, -1.0f, 1e4f);
   return 0;
 }
 int vpo_is_occluded(vpo_ctx* c, const VpRay* rays, int n, uint8_t* out)

@@ -94,7 +94,7 @@ ABI_SYMBOLS = [
     "create", "destroy", "last_error", "set_volumes", "update_volume_grid", "update_volume_transform",
     "set_materials", "set_lights", "set_prims", "set_sky", "render", "render_resident", "accum_reset",
     "accum_download", "render_device", "trace_primary", "find_nearest", "is_occluded", "trace", "info", "stats_begin", "stats_end", "stage_times",
-    "render_fence", "render_reproject", "render_reproject_device",
+    "render_fence", "render_reproject", "render_reproject_device", "in_light", "find_nearest_player", "focus_distance",
 ]
 
 
@@ -130,6 +130,9 @@ class Lib:
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VpStats)], optional=True)
         f("render_reproject_device", C.c_int, [C.c_void_p, C.POINTER(VpCamera), C.POINTER(VpPrevCamera), C.POINTER(VpFrameParams),
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VpStats)], optional=True)
+        f("in_light", C.c_int, [C.c_void_p, C.POINTER(C.c_int)], optional=True)
+        f("find_nearest_player", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p], optional=True)
+        f("focus_distance", C.c_int, [C.c_void_p, C.POINTER(VpCamera), C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_float)], optional=True)
         f("trace_primary", C.c_int, [C.c_void_p, C.POINTER(VpCamera), C.POINTER(VpFrameParams), C.c_void_p])
         f("find_nearest", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p])
         f("is_occluded", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p])

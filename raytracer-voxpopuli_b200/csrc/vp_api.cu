@@ -121,6 +121,7 @@ struct vp_ctx {
   int wf_grid_extend = 0, wf_grid_shadow = 0;      // grids of the current call (smaller for small shards)
   bool wf_blocks_fixed = false;                    // VP_BLOCKS_* given: no per-call sizing
   unsigned long long host_launches = 0;
+  unsigned long long in_light_seen = 0;  // value of the device's inLight counter at the previous vp_in_light
   int tune_refill = kRefill;  // VP_REFILL
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
   int tune_persistent = 0;    // VP_PERSISTENT=1: persistent kernel instead of per-stage kernels
@@ -596,6 +597,8 @@ vp_ctx* vp_create(int device)
   cudaFuncSetAttribute(k_render<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_nearest_player, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_focus, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_occluded, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render<false>, kBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
@@ -961,6 +964,52 @@ int vp_find_nearest(vp_ctx* c, const VpRay* rays, int n, VpHit* hits)
   return 0;
 }
 
+int vp_find_nearest_player(vp_ctx* c, const VpRay* rays, int n, int current_chunk, VpHit* hits)
+{
+  BatchParams p;
+  if (int rc = batch_common(c, rays, n, p)) return rc;
+  if (n == 0) return 0;
+  if (!hits) return fail(VP_EINVAL, "null hits");
+  CU(c->d_scratch_out.reserve((size_t)n * sizeof(VpHit)));
+  p.hits = reinterpret_cast<VpHit*>(c->d_scratch_out.p);
+  p.depth = current_chunk;
+  k_nearest_player<<<grid_blocks(c, (n + 31) / 32), kBlock, smem_bytes(c), c->stream>>>(p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(hits, c->d_scratch_out.p, (size_t)n * sizeof(VpHit), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int vp_in_light(vp_ctx* c, int* in_light)
+{
+  if (!c || !in_light) return fail(VP_EINVAL, "bad arguments to vp_in_light");
+  if (bind(c) || quiesce(c)) return VP_ECUDA;
+  CU(cudaDeviceSynchronize());
+  unsigned long long now = 0;
+  CU(cudaMemcpy(&now, c->d_counters.p + 5, sizeof(now), cudaMemcpyDeviceToHost));
+  *in_light = now != c->in_light_seen ? 1 : 0;
+  c->in_light_seen = now;
+  return 0;
+}
+
+int vp_focus_distance(vp_ctx* c, const VpCamera* cam, int width, int height, uint32_t seed, float* focal_distance)
+{
+  if (!c || !cam || !focal_distance || width <= 0 || height <= 0) return fail(VP_EINVAL, "bad arguments to vp_focus_distance");
+  if (!c->have_volumes) return fail(VP_ESTATE, "vp_set_volumes has not been called");
+  if (bind(c)) return VP_ECUDA;
+  VpFrameParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.width = width; fp.height = height; fp.seed = seed; fp.row_tile_stride = 1;
+  RenderParams p;
+  fill_params(c, cam, &fp, p);
+  CU(c->d_scratch_out.reserve(sizeof(float)));
+  k_focus<<<1, 32, smem_bytes(c), c->stream>>>(p, reinterpret_cast<float*>(c->d_scratch_out.p));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(focal_distance, c->d_scratch_out.p, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int vp_is_occluded(vp_ctx* c, const VpRay* rays, int n, uint8_t* out)
 {
   BatchParams p;
@@ -1003,6 +1052,7 @@ int vp_stats_begin(vp_ctx* c)
   CU(cudaDeviceSynchronize());
   CU(cudaMemset(c->d_counters.p, 0, 16 * sizeof(unsigned long long)));
   c->host_launches = 0;
+  c->in_light_seen = 0;
   return 0;
 }
 

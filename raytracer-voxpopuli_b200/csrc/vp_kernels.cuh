@@ -183,6 +183,47 @@ __global__ void __launch_bounds__(kBlock) k_nearest(const __grid_constant__ Batc
   }
 }
 
+// Renderer::FindNearestPlayer per ray (p.depth carries currentChunk)
+__global__ void __launch_bounds__(kBlock) k_nearest_player(const __grid_constant__ BatchParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Staged svol = stage_scene(p.sc, smem);
+  Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+    const VpRay r = p.rays[i];
+    Ray ray; ray.O = ld3(r.o); ray.D = ld3(r.d); ray.N = v3s(0); ray.t = r.t; ray.inside = r.inside != 0; ray.mat = VP_MAT_NONE;
+    NearestOut no; no.cell = 0xFFFFFFFFu; no.face = -1;
+    const int vol = find_nearest_player<false>(p.sc, svol, ray, p.depth, cn, &no);
+    VpHit h;
+    h.volume = vol; h.t = ray.t;
+    h.normal[0] = ray.N.x; h.normal[1] = ray.N.y; h.normal[2] = ray.N.z;
+    h.material = (uint8_t)ray.mat; h.inside = (uint8_t)(ray.inside != 0); h.pad = 0;
+    h.cell = vol >= 0 ? no.cell : 0xFFFFFFFFu;
+    h.face = (int8_t)(vol >= 0 ? no.face : -1);
+    p.hits[i] = h;
+  }
+}
+
+// the autofocus ray of Tick (renderer.cpp:1987-1991): one thread
+__global__ void k_focus(const __grid_constant__ RenderParams p, float* out)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Staged svol = stage_scene(p.sc, smem);
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint32_t seed = p.seed;
+  Ray fr = primary_ray(p.cam, (float)(p.W / 2), (float)(p.H / 2), p.W, p.H, seed);
+  fr.t = 1e34f;
+  unsigned long long steps = 0;
+  for (int i = 0; i < p.sc.nvol; i++) {  // scene.FindNearest(focusRay) on the untransformed ray, as the reference does
+    const DVolume& v = svol.vol[i];
+    const ORay r = make_oray(fr.O, fr.D);
+    float thit; uint32_t cell; int mat;
+    if (scene_find_nearest<false>(v, region_of(svol, v), r, fr.t, thit, cell, mat, steps)) fr.t = thit;
+  }
+  const float lo = fr.t < 1e4f ? fr.t : 1e4f;  // clamp(t, -1, 1e4) = fmaxf(-1, fminf(t, 1e4)), tmpl8math.h:2105
+  *out = -1.0f > lo ? -1.0f : lo;
+}
+
 __global__ void __launch_bounds__(kBlock) k_occluded(const __grid_constant__ BatchParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];

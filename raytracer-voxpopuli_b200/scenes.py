@@ -122,6 +122,23 @@ def config(idx, width=None, height=None):
     raise ValueError(f"unknown config {idx}")
 
 
+def game_scene(width=96, height=54):
+    """A game-like arrangement for the gameplay side channels: the player volume FIRST (the reference
+    keeps it at voxelVolumes[0]), buildings behind it, one monument with smoke cells, and a strong point light right above
+    the player so that Renderer::inLight fires."""
+    vols, tabs = [], []
+    for nm, pos, rot in (("player", (0.25, 0.0, 0.0), (0.0, 0.0, 0.0)), ("SmallBuilding01", (-1.0, 0.0, 1.5), (0.0, 0.0, 0.0)),
+                         ("monu1", (1.0, 0.0, 1.25), (0.0, float(np.float32(np.pi) / np.float32(4.0)), 0.0)),
+                         ("TallBuilding01", (0.0, 0.0, 2.75), (0.0, 0.0, 0.0)), ("monu2", (2.25, 0.0, 2.5), (0.0, 0.0, 0.0))):
+        v, m = _volume(nm, pos, rot)
+        vols.append(v)
+        tabs.append(m)
+    sc = SceneDesc(volumes=vols, materials=_merge_materials(tabs),
+                   point_lights=[((0.75, 1.4, 0.4), (60.0, 60.0, 60.0)), ((0.0, 2.0, 2.0), (3.0, 3.0, 3.0))])
+    cam = host.look_at((0.75, 0.8, -1.6), (0.75, 0.4, 0.5), width, height, focal_distance=1.0, defocus_jitter=2.0)
+    return sc, cam, dict(width=width, height=height, max_bounces=6, spp=1, aa_strength=1.0)
+
+
 WORKLOAD_NAMES = {
     1: "cfg1 teapot.vox 128^3 1280x720 1spp maxBounces=0 1 point light",
     2: "cfg2 room.vox 128^3 1920x1080 1spp maxBounces=14 2 point + 2 spot lights, diffuse+mirror remap",

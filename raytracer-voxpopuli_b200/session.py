@@ -175,6 +175,25 @@ class Session:
         self.lib.check(self.lib.c_find_nearest(self.ctx, rays.ctypes.data, rays.size, hits.ctypes.data), "find_nearest")
         return hits
 
+    # ---- gameplay side channels --------------------------------------------------------
+    def in_light(self):
+        """Renderer::inLight since the previous call (cleared by the call)."""
+        v = C.c_int()
+        self.lib.check(self.lib.c_in_light(self.ctx, C.byref(v)), "in_light")
+        return bool(v.value)
+
+    def find_nearest_player(self, rays, current_chunk=0):
+        rays = np.ascontiguousarray(rays, dtype=abi.RAY_DTYPE)
+        hits = np.zeros(rays.size, dtype=abi.HIT_DTYPE)
+        self.lib.check(self.lib.c_find_nearest_player(self.ctx, rays.ctypes.data, rays.size, int(current_chunk), hits.ctypes.data), "find_nearest_player")
+        return hits
+
+    def focus_distance(self, cam: Camera, width, height, seed):
+        v = C.c_float()
+        cc = cam.to_c()
+        self.lib.check(self.lib.c_focus_distance(self.ctx, C.byref(cc), int(width), int(height), int(seed) & 0xFFFFFFFF, C.byref(v)), "focus_distance")
+        return np.float32(v.value)
+
     def is_occluded(self, rays):
         rays = np.ascontiguousarray(rays, dtype=abi.RAY_DTYPE)
         out = np.zeros(rays.size, dtype=np.uint8)

@@ -116,3 +116,33 @@ def reproject_sequence(lib, idx, width, height, frames=3, max_bounces=None):
             prev = host.prev_camera(pos, target, width, height)
             pos = pos + np.array([0.01, 0.004, -0.006], np.float32)
     return out
+
+
+def side_channels(lib, width=96, height=54):
+    """The gameplay side channels on scenes.game_scene(): inLight after an accumulating frame and after a reprojection
+    frame (and that the read clears it), FindNearestPlayer over a fan of rays with and without the chunk rule, the
+    autofocus distance for a few lens seeds.  Returns a dict of arrays / flags."""
+    sc, cam, fpd = scenes.game_scene(width, height)
+    out = {}
+    with vp.Session(lib) as s:
+        s.set_scene(sc)
+        out["idle"] = s.in_light()
+        acc, rgb, st = s.render(cam, params(fpd, spp=2))
+        out["after_render"] = s.in_light()
+        out["after_read"] = s.in_light()
+        pos = np.array(cam.cam_pos, np.float32)
+        prev = host.prev_camera(pos, (0.75, 0.4, 0.5), width, height)
+        s.render_reproject(cam, prev, params(fpd, frame_index=5))
+        out["after_reproject"] = s.in_light()
+        rng = np.random.default_rng(11)
+        n = 512
+        o = np.tile(np.array([[0.75, 0.6, -1.2]], np.float32), (n, 1)) + rng.uniform(-0.05, 0.05, (n, 3)).astype(np.float32)
+        d = np.stack([rng.uniform(-0.8, 0.8, n), rng.uniform(-0.35, 0.25, n), np.ones(n)], axis=1).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+        rays = vp.make_rays(o, d)
+        out["player0"] = s.find_nearest_player(rays, 0)
+        out["player2"] = s.find_nearest_player(rays, 2)
+        out["nearest"] = s.find_nearest(rays)
+        out["focus"] = np.array([s.focus_distance(cam, width, height, sd) for sd in (1, 0x12345678, 0xDEADBEEF, 77)], np.float32)
+        out["accum"] = acc
+    return out

@@ -403,3 +403,16 @@ def test_cpp_renderer_mirror_reproject(product, oracle):
             h, want_rgb, _, _, _ = s.render_reproject(host.look_at(pos, tgt, W, H), prev, vp.frame_params(W, H, max_bounces=mb, spp=1, frame_index=f), h)
             prev = host.prev_camera(pos, tgt, W, H)
     assert np.array_equal(bits(hist), bits(h)) and np.array_equal(rgb, want_rgb)
+
+
+def test_gameplay_side_channels(product, oracle):
+    """vp_in_light, vp_find_nearest_player, vp_focus_distance against the oracle (which is pinned to the reference's
+    inLight / FindNearestPlayer / focus ray by tests/test_oracle_vs_ref.py)."""
+    from _util import side_channels
+    a, b = side_channels(oracle), side_channels(product)
+    for k in ("idle", "after_render", "after_read", "after_reproject"):
+        assert a[k] == b[k], k
+    assert_hits_equal(a["player0"], b["player0"], "FindNearestPlayer")
+    assert_hits_equal(a["player2"], b["player2"], "FindNearestPlayer chunk 2")
+    assert np.array_equal(bits(a["focus"]), bits(b["focus"]))
+    assert np.array_equal(bits(a["accum"]), bits(b["accum"]))

@@ -107,3 +107,19 @@ def test_reprojection_frames_bit_exact(ref, oracle, idx):
         assert x[4] == y[4], f"cfg{idx} frame {f}: counters {x[4]} vs {y[4]}"
     # the history is really used: the last frame differs from its own illumination buffer
     assert np.count_nonzero(bits(a[-1][0]) != bits(a[-1][3])) > 0
+
+
+def test_gameplay_side_channels(ref, oracle):
+    """inLight, FindNearestPlayer / FindNearestExcept and the autofocus ray (renderer.cpp:1228-1240,1020-1071,1987-1991)."""
+    from _util import side_channels
+    a, b = side_channels(ref), side_channels(oracle)
+    for k in ("idle", "after_render", "after_read", "after_reproject"):
+        assert a[k] == b[k], k
+    assert a["after_render"] and not a["after_read"] and not a["idle"]  # the scene really lights the player; the read clears the flag
+    assert_hits_equal(a["player0"], b["player0"], "FindNearestPlayer")
+    assert_hits_equal(a["player2"], b["player2"], "FindNearestPlayer chunk 2")
+    assert np.array_equal(bits(a["focus"]), bits(b["focus"]))
+    assert np.array_equal(bits(a["accum"]), bits(b["accum"]))
+    # the side channel differs from the ordinary nearest hit (player volume skipped, smoke transparent) and the chunk rule bites
+    assert np.count_nonzero(a["player0"]["volume"] != a["nearest"]["volume"]) > 0
+    assert np.count_nonzero(a["player0"]["volume"] != a["player2"]["volume"]) > 0
