@@ -84,7 +84,9 @@ struct vp_ctx {
   cudaStream_t stream = nullptr;
   WfLane lane[kLanes];
   int next_lane = 0;
-  int nlanes = 4;
+  int nlanes = 4;      // frames in flight wanted (VP_LANES)
+  int lanes_now = 4;   // ... and what the free HBM allows for the current frame size
+  bool lanes_sized = false;
   cudaEvent_t ev_in = nullptr;      // recorded on the caller's stream when a render call enters
   cudaEvent_t ev_direct = nullptr;  // recorded after a launch made directly on the caller's stream (single-kernel formulations)
   bool direct_recorded = false;
@@ -257,8 +259,9 @@ int grid_blocks(const vp_ctx* c, long long work_warps)
 }
 
 // path state of one lane (HBM-resident, sized for the largest frame / depth seen)
-int wf_reserve(WfLane& L, uint32_t cap, int levels, int samples)
+int wf_reserve(WfLane& L, uint32_t cap, int levels, int samples, size_t* bytes_only = nullptr)
 {
+  if (bytes_only) *bytes_only = 0;
   if (cap <= L.cap && levels <= L.levels && samples <= L.samples && L.d_wf.p) return 0;
   cap = cap > L.cap ? cap : L.cap;
   levels = levels > L.levels ? levels : L.levels;
@@ -272,6 +275,7 @@ int wf_reserve(WfLane& L, uint32_t cap, int levels, int samples)
   const size_t pq_len = (size_t)levels * cap + (size_t)64 * 1024 * 32;  // + one window per warp that may be handed out past the last id
   const size_t o_pq = take(3 * pq_len * 4), o_pctl = take(kCtlWords * 4);
   const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_qs = take(2 * cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
+  if (bytes_only) { *bytes_only = off; return 0; }  // what growing this lane would take
   CU(cudaDeviceSynchronize());
   CU(L.d_wf.reserve(off));
   unsigned char* b = L.d_wf.p;
@@ -434,9 +438,35 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   if (staged) CU(cudaEventRecord(c->ev_in, stream));
   else if (int rc = join_lanes(c, stream)) return rc;
   bool entered[kLanes] = {};
-  if (staged && overlap)  // frames in flight: size every lane now rather than one per call (allocation synchronises the device)
-    for (int i = 0; i < c->nlanes; i++)
+  if (staged && (overlap || fp->spp > 1)) {
+    // Frames in flight: size the lanes now rather than one per call (allocation synchronises the device), and only as
+    // many as fit: a lane of a 4K frame at depth 14 with area lights is ~20 GB.  New lanes may take 80 % of the free HBM.
+    int fit = 0;
+    size_t grow = 0, freeb = 0, totalb = 0;
+    bool steady = true;  // every lane in use already holds this frame size: no driver calls on the hot path
+    for (int i = 0; i < c->lanes_now && steady; i++) {
+      if (int rc = wf_reserve(c->lane[i], tiles * 32u, levels, samples, &grow)) return rc;
+      steady = grow == 0;
+    }
+    if (steady && c->lanes_sized) {
+      fit = c->lanes_now;
+    } else {
+      CU(cudaMemGetInfo(&freeb, &totalb));
+      size_t budget = (size_t)((double)freeb * 0.8);
+      for (int i = 0; i < c->nlanes; i++) {
+        if (int rc = wf_reserve(c->lane[i], tiles * 32u, levels, samples, &grow)) return rc;
+        const size_t held = c->lane[i].d_wf.p ? c->lane[i].d_wf.cap : 0;  // freed before the larger block is allocated
+        if (grow > budget + held && fit >= 1) break;
+        if (grow) budget = budget + held > grow ? budget + held - grow : 0;
+        fit++;
+      }
+      c->lanes_sized = true;
+    }
+    c->lanes_now = fit < 1 ? 1 : fit;
+    const int want = overlap ? c->lanes_now : (fp->spp < c->lanes_now ? fp->spp : c->lanes_now);
+    for (int i = 0; i < want; i++)
       if (int rc = wf_reserve(c->lane[i], tiles * 32u, levels, samples)) return rc;
+  }
   const int passes = rp ? 1 : fp->spp;
   for (int s = 0; s < passes; s++) {
     p.frame = fp->frame_index + (uint32_t)s;
@@ -444,7 +474,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
     int rc;
     if (staged) {
       // lanes rotate only when passes can overlap (several samples in this call, or a deferred call)
-      const int li = (overlap || fp->spp > 1) ? (c->next_lane++ % c->nlanes) : 0;
+      const int li = (overlap || fp->spp > 1) ? (c->next_lane++ % c->lanes_now) : 0;
       WfLane& L = c->lane[li];
       if ((rc = wf_reserve(L, tiles * 32u, levels, samples))) return rc;
       if (!entered[li]) {
