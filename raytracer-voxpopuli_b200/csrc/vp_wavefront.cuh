@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant_
 // material byte are produced by the shade stage where all 32 lanes are busy, not here where
 // a hit is a single-lane event inside the stepping loop.
 template <bool CS>
-__global__ void __launch_bounds__(kWfBlock) k_wf_extend(const __grid_constant__ WfParams p)
+__global__ void __launch_bounds__(kWfBlock, 8) k_wf_extend(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   if (!wf_block_has_work(p.st.counts + 4 * p.iter + 2, p.st.counts[4 * p.iter])) return;
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shade(const __grid_constant__ W
 
 // ---- K4: shadow = Renderer::IsOccluded per light sample (renderer.cpp:209-243), lane refill -------
 template <bool CS>
-__global__ void __launch_bounds__(kWfBlock) k_wf_shadow(const __grid_constant__ WfParams p)
+__global__ void __launch_bounds__(kWfBlock, 8) k_wf_shadow(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   if (!wf_block_has_work(p.st.counts + 4 * p.iter + 3, p.st.counts[4 * p.iter + 1])) return;
