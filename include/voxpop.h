@@ -199,8 +199,10 @@ typedef struct VpPrevCamera { /* what Renderer::CopyToPrevCamera keeps (renderer
 } VpPrevCamera;
 /* history_in: W*H float3 = illuminationHistoryBuffer; history_out: W*H float3 = tempIlluminationBuffer (the caller
  * swaps them for the next frame, renderer.cpp:2100); must not alias.  albedo / illumination: optional W*H float3 dumps
- * of pass 1.  fp: width, height, max_bounces, frame_index, seed are used (one pass; the whole frame - row ranges are
- * rejected because pass 2 reads its neighbours).  HOST pointers. */
+ * of pass 1.  fp: width, height, max_bounces, frame_index, seed and the row selection are used (one pass).  With a row
+ * selection (multi-GPU sharding) pass 1 also traces the rows adjacent to the owned ones - pass 2 reads their
+ * illumination - and only the owned rows of history_out / rgb8 are written; history_in must hold the WHOLE previous
+ * frame (gather it between frames).  HOST pointers. */
 int vp_render_reproject(vp_ctx* ctx, const VpCamera* cam, const VpPrevCamera* prev, const VpFrameParams* fp,
                         const float* history_in, float* history_out, uint32_t* rgb8, float* albedo, float* illumination,
                         VpStats* stats);

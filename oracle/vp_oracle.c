@@ -1135,6 +1135,8 @@ int vpo_render_reproject(vpo_ctx* c, const VpCamera* cam, const VpPrevCamera* pr
 #endif
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : nearest, shadow, exitray, steps, primary, sky)
   for (int y = 0; y < H; y++) { /* pass 1, renderer.cpp:2003-2022 */
+    /* row sharding (not in the reference): a shard also traces the rows next to its own, pass 2 reads their illumination */
+    if (!(row_selected(fp, y) || (y > 0 && row_selected(fp, y - 1)) || (y + 1 < H && row_selected(fp, y + 1)))) continue;
     Thread T; memset(&T, 0, sizeof(T)); T.c = c;
     for (int x = 0; x < W; x++) {
       const uint32_t px = (uint32_t)y * (uint32_t)W + (uint32_t)x;
@@ -1158,6 +1160,7 @@ int vpo_render_reproject(vpo_ctx* c, const VpCamera* cam, const VpPrevCamera* pr
   const f3 nl = ld3(prev->left_normal), nr_ = ld3(prev->right_normal), nt = ld3(prev->top_normal), nb = ld3(prev->bottom_normal);
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : nearest, shadow, exitray, steps, sky)
   for (int y = 0; y < H; y++) { /* pass 2, renderer.cpp:2023-2099 */
+    if (!row_selected(fp, y)) continue;
     Thread T; memset(&T, 0, sizeof(T)); T.c = c;
     for (int x = 0; x < W; x++) {
       const uint32_t px = (uint32_t)x + (uint32_t)y * (uint32_t)W;

@@ -412,6 +412,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   p.bulk = c->tune_bulk;
   p.persistent = 0;
   p.reproject = rp ? 1 : 0;
+  p.halo = rp ? 1 : 0;  // no effect on whole frames
   p.rp_alb = c->d_rp_alb.p; p.rp_ill = c->d_rp_ill.p; p.rp_ray = c->d_rp_ray.p;
   p.hist_in = rp ? rp->hist_in : nullptr; p.hist_out = rp ? rp->hist_out : nullptr;
   if (rp) p.prev = rp->prev; else memset(&p.prev, 0, sizeof(p.prev));
@@ -829,8 +830,6 @@ static int check_reproject(const vp_ctx* c, const VpCamera* cam, const VpPrevCam
   if (!prev) return fail(VP_EINVAL, "null previous camera");
   if (fp->max_bounces < 0) return fail(VP_EINVAL, "reprojection needs max_bounces >= 0");
   if (c->sc.area_samples > kMaxAreaSamples) return fail(VP_EINVAL, "reprojection supports at most %d area-light samples", kMaxAreaSamples);
-  const bool whole = (fp->row_begin == 0 && (fp->row_end == 0 || fp->row_end == fp->height)) && (fp->row_tile <= 0 || fp->row_tile_stride <= 1);
-  if (!whole) return fail(VP_EINVAL, "reprojection renders whole frames (pass 2 reads the 3x3 neighbourhood and the history)");
   return 0;
 }
 

@@ -71,6 +71,7 @@ struct WfParams {
   uint32_t* rgb8;
   unsigned long long* counters;  // same slots as RenderParams
   // reprojection frame mode (Renderer::Tick static-camera branch, renderer.cpp:1997-2101)
+  int halo;               // 1: pass 1 also renders the rows next to the owned ones (row-sharded reprojection)
   int reproject;          // 1: TraceReproject variant of the shade stage, resolve splits albedo / illumination
   float* rp_alb;          // albedoBuffer        [W*H] float3
   float* rp_ill;          // illuminationBuffer  [W*H] float3
@@ -80,11 +81,18 @@ struct WfParams {
   VpPrevCamera prev;
 };
 
-__device__ __forceinline__ bool wf_row_selected(const WfParams& p, int y)
+__device__ __forceinline__ bool wf_row_owned(const WfParams& p, int y)
 {
   if (y < p.row_begin || y >= p.row_end) return false;
   if (p.row_tile > 0 && ((y / p.row_tile) % p.row_tile_stride) != p.row_tile_phase) return false;
   return true;
+}
+// rows a pass works on: the owned rows, plus - in pass 1 of a row-sharded reprojection frame - their direct neighbours,
+// whose illumination pass 2 reads (ClampHistory's 3x3 box)
+__device__ __forceinline__ bool wf_row_selected(const WfParams& p, int y)
+{
+  if (wf_row_owned(p, y)) return true;
+  return p.halo && ((y > 0 && wf_row_owned(p, y - 1)) || (y + 1 < p.H && wf_row_owned(p, y + 1)));
 }
 // path id <-> pixel: 8x4 tiles in row-major tile order, lane = position inside the tile
 __device__ __forceinline__ bool wf_pixel_of(const WfParams& p, uint32_t path, int& x, int& y)
@@ -529,7 +537,7 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
 }
 
 template <bool CS>
-__global__ void __launch_bounds__(kWfBlock) k_wf_shade(const __grid_constant__ WfParams p)
+__global__ void __launch_bounds__(kWfBlock, 6) k_wf_shade(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   if (blockIdx.x * blockDim.x >= p.st.counts[4 * p.iter]) return;  // grid-stride loop below would be empty
@@ -834,7 +842,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_reproject(const __grid_constant
   const f3 nl = ld3(p.prev.left_normal), nr = ld3(p.prev.right_normal), nt = ld3(p.prev.top_normal), nb = ld3(p.prev.bottom_normal);
   for (uint32_t path = blockIdx.x * blockDim.x + threadIdx.x; path < p.st.cap; path += gridDim.x * blockDim.x) {
     int x, y;
-    if (!wf_pixel_of(p, path, x, y)) continue;
+    if (!wf_pixel_of(p, path, x, y) || !wf_row_owned(p, y)) continue;
     const size_t px = (size_t)x + (size_t)y * W;
     const float4 rd = p.rp_ray[px];
     const f3 P = v3(rd.x, rd.y, rd.z);

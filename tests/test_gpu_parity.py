@@ -366,9 +366,6 @@ def test_reprojection_device_and_errors(product, oracle):
         fp = params(fpd, frame_index=0)
         assert product.c_render_reproject_device(s.ctx, C.byref(cc), C.byref(prev), C.byref(fp), hist[0].data_ptr(), hist[0].data_ptr(),
                                                  rgb.data_ptr(), stream.cuda_stream, None) != 0  # aliasing history
-        fp = params(fpd, frame_index=0, row_begin=8, row_end=16)
-        assert product.c_render_reproject_device(s.ctx, C.byref(cc), C.byref(prev), C.byref(fp), hist[0].data_ptr(), hist[1].data_ptr(),
-                                                 rgb.data_ptr(), stream.cuda_stream, None) != 0  # row ranges
         fp = params(fpd, frame_index=0, max_bounces=-1)
         assert product.c_render_reproject_device(s.ctx, C.byref(cc), C.byref(prev), C.byref(fp), hist[0].data_ptr(), hist[1].data_ptr(),
                                                  rgb.data_ptr(), stream.cuda_stream, None) != 0
@@ -416,3 +413,39 @@ def test_gameplay_side_channels(product, oracle):
     assert_hits_equal(a["player2"], b["player2"], "FindNearestPlayer chunk 2")
     assert np.array_equal(bits(a["focus"]), bits(b["focus"]))
     assert np.array_equal(bits(a["accum"]), bits(b["accum"]))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_reprojection_row_sharded(product, oracle, world):
+    """Row-sharded reprojection (what each rank of a multi-GPU run does): every shard traces its rows plus their direct
+    neighbours in pass 1, writes only its own rows in pass 2; the merged shards equal the whole frame bit for bit, also
+    on the second frame, which reprojects into the merged (= gathered) history."""
+    from _util import host
+    sharding = __import__("importlib").import_module("raytracer-voxpopuli_b200.sharding")
+    sc, cam, fpd = small_config(4, 128, 72)
+    W, H = fpd["width"], fpd["height"]
+    pos = np.array(cam.cam_pos, np.float32)
+    tl, tr, bl = (np.array(v, np.float32) for v in (cam.top_left, cam.top_right, cam.bottom_left))
+    target = tl + (tr - tl) * np.float32(0.5) + (bl - tl) * np.float32(0.5)
+    cams = [host.look_at(pos + np.array([0.015 * f, 0, 0], np.float32), target, W, H) for f in range(2)]
+    prevs = [host.prev_camera(pos, target, W, H), host.prev_camera(pos, target, W, H)]
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        want, hist = [], None
+        for f in range(2):
+            hist, rgb, _, _, st = s.render_reproject(cams[f], prevs[f], params(fpd, frame_index=f), hist)
+            want.append((hist, rgb, st.rays))
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        hist = None
+        for f in range(2):
+            merged_h = np.zeros((H, W, 3), np.float32)
+            merged_rgb = np.zeros((H, W), np.uint32)
+            for r in range(world):
+                h, rgb, _, _, st = s.render_reproject(cams[f], prevs[f], params(fpd, frame_index=f, **sharding.shard_params(world, r)), hist)
+                for t in sharding.tiles_of_rank(H, world, r):
+                    rows = slice(t * sharding.ROW_TILE, (t + 1) * sharding.ROW_TILE)
+                    merged_h[rows], merged_rgb[rows] = h[rows], rgb[rows]
+            assert np.array_equal(bits(merged_h), bits(want[f][0])), f"frame {f}: merged history differs"
+            assert np.array_equal(merged_rgb, want[f][1]), f"frame {f}: merged rgb8 differs"
+            hist = merged_h

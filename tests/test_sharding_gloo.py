@@ -54,6 +54,62 @@ def test_two_rank_tile_sharding_matches_single_rank():
     assert rays == st.rays
 
 
+def _reproject_cams(W, H, cam):
+    from _util import host
+    pos = np.array(cam.cam_pos, np.float32)
+    tl, tr, bl = (np.array(v, np.float32) for v in (cam.top_left, cam.top_right, cam.bottom_left))
+    target = tl + (tr - tl) * np.float32(0.5) + (bl - tl) * np.float32(0.5)
+    cams = [host.look_at(pos + np.array([0.02 * f, 0, 0], np.float32), target, W, H) for f in range(2)]
+    return cams, host.prev_camera(pos, target, W, H)
+
+
+def _worker_reproject(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = oracle_lib()
+        sc, cam, fpd = small_config(4, 64, 48)
+        cams, prev = _reproject_cams(64, 48, cam)
+        hist = None
+        with vp.Session(lib) as s:
+            s.set_scene(sc)
+            for f in range(2):
+                h, rgb8, _, _, st = s.render_reproject(cams[f], prev, params(fpd, frame_index=f, **sharding.shard_params(world, rank)), hist)
+                ht = torch.from_numpy(h)
+                sharding.FrameGather(ht, world, rank)(ht)  # every rank needs the WHOLE history for the next frame
+                hist = ht.numpy().copy()
+        frame = torch.from_numpy(rgb8.astype(np.int32))
+        sharding.FrameGather(frame, world, rank)(frame)
+        if rank == 0:
+            q.put((frame.numpy().copy(), hist))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_reprojection_matches_single_rank():
+    """Reprojection frame mode sharded over two gloo ranks: halo rows in pass 1, history gathered between frames."""
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_reproject, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    frame, hist = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sc, cam, fpd = small_config(4, 64, 48)
+    cams, prev = _reproject_cams(64, 48, cam)
+    with vp.Session(oracle_lib()) as s:
+        s.set_scene(sc)
+        want = None
+        for f in range(2):
+            want, want_rgb8, _, _, _ = s.render_reproject(cams[f], prev, params(fpd, frame_index=f), want)
+    assert np.array_equal(frame.astype(np.uint32), want_rgb8)
+    assert np.array_equal(hist.view(np.uint32), want.view(np.uint32))
+
+
 def test_tile_ownership_partitions_the_frame():
     for H in (48, 1080, 2160):
         for world in (1, 2, 4, 8):
