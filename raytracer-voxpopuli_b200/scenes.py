@@ -139,6 +139,9 @@ def game_scene(width=96, height=54):
     return sc, cam, dict(width=width, height=height, max_bounces=6, spp=1, aa_strength=1.0)
 
 
+# look-at targets of config()'s cameras (for building a previous-frame camera next to them)
+CAMERA_TARGETS = {1: (0.5, 0.3, 0.5), 2: (0.2, 0.1, 0.15), 3: (0.2, 0.1, 0.15), 4: (0.45, 0.35, 0.9), 5: (0.45, 0.3, 3.5)}
+
 WORKLOAD_NAMES = {
     1: "cfg1 teapot.vox 128^3 1280x720 1spp maxBounces=0 1 point light",
     2: "cfg2 room.vox 128^3 1920x1080 1spp maxBounces=14 2 point + 2 spot lights, diffuse+mirror remap",

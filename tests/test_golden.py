@@ -111,3 +111,16 @@ def test_reprojection_golden(oracle, idx):
         assert np.array_equal(g[f"rgb8_{f}"], o[1]), f"frame {f} rgb8"
         assert list(g[f"stats{f}"]) == o[4]
     assert np.array_equal(bits(g["albedo2"]), bits(out[2][2])) and np.array_equal(bits(g["illumination2"]), bits(out[2][3]))
+
+
+@pytest.mark.parametrize("idx", [1, 4])
+def test_fullres_frame_digest(oracle, idx):
+    """The oracle at full size against the reference build's frame digests (two accumulated samples, counters)."""
+    want = json.load(open(os.path.join(GOLDEN, "fullres_frame_digests.json")))[f"cfg{idx}"]
+    sc, cam, fpd = scenes.config(idx)
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        acc, rgb8, st = s.render(cam, params(fpd, spp=2))
+    assert [st.primary_rays, st.secondary_rays, st.shadow_rays, st.exit_rays, st.dda_steps] == want["stats"]
+    assert hashlib.sha256(acc.tobytes()).hexdigest() == want["accum_sha256"]
+    assert hashlib.sha256(rgb8.tobytes()).hexdigest() == want["rgb8_sha256"]

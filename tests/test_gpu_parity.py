@@ -97,6 +97,30 @@ def test_fullres_primary_hits_digest(product, idx):
     assert hit_digest(hits) == want["sha256"]
 
 
+@pytest.mark.parametrize("idx", [1, 2, 3, 4, 5])
+def test_fullres_frames_digest(product, idx):
+    """Bit-exact FRAMES at BASELINE.json's full sizes: the accumulator and RGB8 image after two accumulated samples, the
+    ray / step counters, and one reprojection frame on top (history + RGB8), against SHA-256 digests of what the
+    reference build produced (tools/make_golden.py)."""
+    from _util import host
+    want = json.load(open(os.path.join(GOLDEN, "fullres_frame_digests.json")))[f"cfg{idx}"]
+    sc, cam, fpd = scenes.config(idx)
+    W, H = fpd["width"], fpd["height"]
+    assert (W, H) == (want["width"], want["height"])
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        acc, rgb8, st = s.render(cam, params(fpd, spp=2, flags=abi.VP_FLAG_COUNT_STEPS))
+        prev = host.prev_camera(np.array(cam.cam_pos, np.float32) + np.array([0.01, 0, 0], np.float32), scenes.CAMERA_TARGETS[idx], W, H)
+        hist, rrgb, _, _, rst = s.render_reproject(cam, prev, params(fpd, spp=1, frame_index=3), np.ascontiguousarray(acc[:, :, :3]),
+                                                   want_buffers=False)
+    assert [st.primary_rays, st.secondary_rays, st.shadow_rays, st.exit_rays, st.dda_steps] == want["stats"]
+    assert hashlib.sha256(acc.tobytes()).hexdigest() == want["accum_sha256"]
+    assert hashlib.sha256(rgb8.tobytes()).hexdigest() == want["rgb8_sha256"]
+    assert [rst.primary_rays, rst.secondary_rays, rst.shadow_rays, rst.exit_rays] == want["reproject_rays"]
+    assert hashlib.sha256(hist.tobytes()).hexdigest() == want["reproject_history_sha256"]
+    assert hashlib.sha256(rrgb.tobytes()).hexdigest() == want["reproject_rgb8_sha256"]
+
+
 def test_batch_seams_and_prims(product, oracle):
     sc, cam, fpd = small_config(4, 64, 36)
     sc.spheres = [((0.2, 0.6, -0.5), 0.3, 5), ((1.0, 0.4, 0.2), 0.25, 1), ((-0.8, 0.5, 0.1), 0.2, 20)]

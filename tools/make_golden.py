@@ -56,6 +56,27 @@ def main():
     with open(os.path.join(GOLDEN, "fullres_hit_digests.json"), "w") as f:
         json.dump(digests, f, indent=1, sort_keys=True)
 
+    # ---- full-size frames: digests of the accumulator / RGB8 after 2 accumulated samples, and of one reprojection frame ----
+    frames = {}
+    for idx in (1, 2, 3, 4, 5):
+        sc, cam, fpd = scenes.config(idx)
+        W, H = fpd["width"], fpd["height"]
+        with vp.Session(ref) as s:
+            s.set_scene(sc)
+            acc, rgb8, st = s.render(cam, params(fpd, spp=2))
+            prev = host.prev_camera(np.array(cam.cam_pos, np.float32) + np.array([0.01, 0, 0], np.float32), scenes.CAMERA_TARGETS[idx], W, H)
+            hist, rrgb, _, _, rst = s.render_reproject(cam, prev, params(fpd, spp=1, frame_index=3),
+                                                       np.ascontiguousarray(acc[:, :, :3]), want_buffers=False)
+        frames[f"cfg{idx}"] = dict(width=W, height=H, accum_sha256=hashlib.sha256(acc.tobytes()).hexdigest(),
+                                   rgb8_sha256=hashlib.sha256(rgb8.tobytes()).hexdigest(),
+                                   stats=[int(st.primary_rays), int(st.secondary_rays), int(st.shadow_rays), int(st.exit_rays), int(st.dda_steps)],
+                                   reproject_history_sha256=hashlib.sha256(hist.tobytes()).hexdigest(),
+                                   reproject_rgb8_sha256=hashlib.sha256(rrgb.tobytes()).hexdigest(),
+                                   reproject_rays=[int(rst.primary_rays), int(rst.secondary_rays), int(rst.shadow_rays), int(rst.exit_rays)])
+        print("fullres frame", idx, frames[f"cfg{idx}"]["stats"], flush=True)
+    with open(os.path.join(GOLDEN, "fullres_frame_digests.json"), "w") as f:
+        json.dump(frames, f, indent=1, sort_keys=True)
+
     # ---- reprojection frame mode: three drifting-camera frames per config -------------------
     from _util import reproject_sequence
     for idx in (2, 3, 4):
