@@ -126,6 +126,7 @@ struct vp_ctx {
   unsigned long long in_light_seen = 0;  // value of the device's inLight counter at the previous vp_in_light
   int tune_refill = kRefill;  // VP_REFILL
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
+  int tune_brickwalk = 1;     // VP_BRICKWALK: 0 = cell walk only (A/B)
   int tune_persistent = 0;    // VP_PERSISTENT=1: persistent kernel instead of per-stage kernels
   int wf_blocks_persistent = 0;
   uint32_t last_error_word = 0;  // error word of the last persistent launch (valid after a stream sync)
@@ -327,13 +328,15 @@ int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
       e0 = c->tev[c->tev_used++]; e1 = c->tev[c->tev_used++];
       CU(cudaEventRecord(e0, stream));
     }
-    k_wf_extend<CS><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
+    if (!CS && c->tune_brickwalk) k_wf_extend<false, true><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
+    else k_wf_extend<CS, false><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
     if (e1) CU(cudaEventRecord(e1, stream));
     if (it >= 2) CU(cudaStreamWaitEvent(stream, L.ev_shadow[it - 2], 0));  // shade(k) reuses the id queue of shadow(k-2)
     k_wf_shade<CS><<<wide, kWfBlock, sm, stream>>>(p);
     CU(cudaEventRecord(L.ev_shade[it], stream));
     CU(cudaStreamWaitEvent(L.side, L.ev_shade[it], 0));
-    k_wf_shadow<CS><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
+    if (!CS && c->tune_brickwalk) k_wf_shadow<false, true><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
+    else k_wf_shadow<CS, false><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
     CU(cudaEventRecord(L.ev_shadow[it], L.side));
     c->host_launches += 3;
   }
@@ -634,17 +637,19 @@ vp_ctx* vp_create(int device)
   cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render<false>, kBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
   c->blocks_per_sm = occ;
-  cudaFuncSetAttribute(k_wf_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  cudaFuncSetAttribute(k_wf_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_extend<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_extend<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_extend<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  cudaFuncSetAttribute(k_wf_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  cudaFuncSetAttribute(k_wf_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_shadow<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_shadow<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_shadow<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_reproject<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_reproject<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_extend<false>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_extend<false, true>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
   c->wf_blocks_extend = occ * c->sm_count;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shadow<false>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shadow<false, true>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
   c->wf_blocks_shadow = occ * c->sm_count;
   // tuning knobs for experiments (defaults are the shipped values)
   cudaFuncSetAttribute(k_wf_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -656,6 +661,7 @@ vp_ctx* vp_create(int device)
   if (const char* e = getenv("VP_LANES")) { const int n = atoi(e); c->nlanes = n < 1 ? 1 : (n > kLanes ? kLanes : n); }
   if (const char* e = getenv("VP_BULK_LANES")) c->tune_bulk = atoi(e);
   if (const char* e = getenv("VP_REFILL")) c->tune_refill = atoi(e);
+  if (const char* e = getenv("VP_BRICKWALK")) c->tune_brickwalk = atoi(e);
   if (const char* e = getenv("VP_BLOCKS_EXTEND")) { c->wf_blocks_extend = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
   if (const char* e = getenv("VP_BLOCKS_SHADOW")) { c->wf_blocks_shadow = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
   return c;
@@ -1127,8 +1133,8 @@ int vp_info(vp_ctx* c, char* buf, int cap)
   if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) return fail(VP_ECUDA, "cudaGetDeviceProperties failed");
   cudaFuncAttributes fa, fe, fs, fh;
   cudaFuncGetAttributes(&fa, k_render<false>);
-  cudaFuncGetAttributes(&fe, k_wf_extend<false>);
-  cudaFuncGetAttributes(&fs, k_wf_shadow<false>);
+  cudaFuncGetAttributes(&fe, k_wf_extend<false, true>);
+  cudaFuncGetAttributes(&fs, k_wf_shadow<false, true>);
   cudaFuncGetAttributes(&fh, k_wf_shade<false>);
   unsigned long long dbg[16] = {0};
   cudaDeviceSynchronize();

@@ -23,6 +23,10 @@
 namespace vp {
 
 constexpr int kWfBlock = 128;
+#ifndef VP_WF_MINBLOCKS
+#define VP_WF_MINBLOCKS 8
+#endif
+constexpr int kWfMinBlocks = VP_WF_MINBLOCKS;  // resident blocks per SM the traversal kernels are compiled for (64 registers at 8)
 constexpr int kRefill = 20;           // refill when fewer lanes than this are still stepping
 constexpr int kBulkLanes = 12;        // with at most this many lanes walking, lanes in empty 8^3/16^3 blocks bulk-advance
 constexpr int kMaxAreaSamples = 8;    // numCheckShadowsAreaLight supported by the wavefront path (reference default 3)
@@ -193,8 +197,8 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant_
 // Writes per path: t, the winning volume and the hit cell (as P).  The face normal and the
 // material byte are produced by the shade stage where all 32 lanes are busy, not here where
 // a hit is a single-lane event inside the stepping loop.
-template <bool CS>
-__global__ void __launch_bounds__(kWfBlock, 8) k_wf_extend(const __grid_constant__ WfParams p)
+template <bool CS, bool BWK>
+__global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   if (!wf_block_has_work(p.st.counts + 4 * p.iter + 2, p.st.counts[4 * p.iter])) return;
@@ -214,6 +218,7 @@ __global__ void __launch_bounds__(kWfBlock, 8) k_wf_extend(const __grid_constant
   const unsigned long long* fine = nullptr;
   DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
   Occ o; occ_reset(o);
+  BW bw; bw.ex = bw.ey = bw.ez = 0; bw.pos = bw.alast = 0; bw.brick = bw.catchup = bw.plain = false;
   unsigned long long steps = 0, steps_er = 0, steps_eb = 0;
   unsigned int nrays = 0;
   for (;;) {
@@ -245,7 +250,11 @@ __global__ void __launch_bounds__(kWfBlock, 8) k_wf_extend(const __grid_constant
         if (nvol > 1 && !volume_may_hit(v, O, D)) { vi++; continue; }
         const ORay r = make_oray(xform_pos_sse(O, v.iM), xform_vec_sse(D, v.iM));
         vi++;
-        if (setup_dda(v, r, s)) { in_dda = true; occ_reset(o); region = region_of(stg, v); fine = v.fine; break; }
+        if (setup_dda(v, r, s)) {
+          in_dda = true; occ_reset(o); region = region_of(stg, v); fine = v.fine;
+          if (BWK) bw_init(v, s, bw);
+          break;
+        }
       }
       if (!in_dda) {
         uint32_t hb = (uint32_t)(volbest + 2) << 8;
@@ -267,24 +276,44 @@ __global__ void __launch_bounds__(kWfBlock, 8) k_wf_extend(const __grid_constant
     //    A lane walks while s.t < tbest: a hit sets tbest = s.t, leaving the grid sets s.t = inf.
     if (!in_dda) s.t = 3.0e38f;
     const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)p.refill;  // queue drained: run to completion
-    const bool drained = thr == 1u;  // no more work to pull: latency of the remaining rays is all that matters
-    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) <= (unsigned)p.bulk;
-    for (;;) {
+    if (BWK) {
+      // one step body for lanes inside empty bricks (a whole brick per step) and lanes inside non-empty ones (the
+      // reference's cell step with the occupancy bit test): vp_device.cuh "brick walk"
+      for (;;) {
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        if (s.t < tbest) {
-          if (CS) steps++;
-          uint32_t skipped = 0;
-          const bool solid = occ_visit(region, fine, o, s, tbest, sparse, skipped);
-          if (CS) steps += skipped;
-          if (CS) { if (o.rm == 0ull) steps_er += 1 + skipped; if (o.m == 0ull) steps_eb += 1 + skipped; }
-          if (solid) { tbest = s.t; s.t = __uint_as_float(kHitTag); }  // NaN tag: stops the walk, recovered below
-          else if (!dda_step(s)) s.t = 3.0e38f;
+        for (int u = 0; u < 2; u++) {
+          if (s.t < tbest) {
+            if ((s.P ^ o.key) >> 6) {
+              occ_fetch(region, fine, o, s.P);
+              const bool nb = o.m == 0ull && !bw.plain;
+              bw.catchup = bw.catchup || (bw.brick && !nb);
+              bw.brick = nb;
+            }
+            if (uw_step(s, bw, o.m)) { tbest = s.t; s.t = __uint_as_float(kHitTag); }  // NaN tag: stops the walk, recovered below
+          }
         }
+        if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) < thr) break;
       }
-      const unsigned act = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest));
-      sparse = drained || act <= (unsigned)p.bulk;
-      if (act < thr) break;
+    } else {
+      const bool drained = thr == 1u;  // no more work to pull: latency of the remaining rays is all that matters
+      bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) <= (unsigned)p.bulk;
+      for (;;) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          if (s.t < tbest) {
+            if (CS) steps++;
+            uint32_t skipped = 0;
+            const bool solid = occ_visit(region, fine, o, s, tbest, sparse, skipped);
+            if (CS) steps += skipped;
+            if (CS) { if (o.rm == 0ull) steps_er += 1 + skipped; if (o.m == 0ull) steps_eb += 1 + skipped; }
+            if (solid) { tbest = s.t; s.t = __uint_as_float(kHitTag); }  // NaN tag: stops the walk, recovered below
+            else if (!dda_step(s)) s.t = 3.0e38f;
+          }
+        }
+        const unsigned act = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest));
+        sparse = drained || act <= (unsigned)p.bulk;
+        if (act < thr) break;
+      }
     }
     if (__float_as_uint(s.t) == kHitTag) { pbest = s.P; volbest = vi - 1; s.t = 3.0e38f; }  // the cell the walk stopped on
     in_dda = s.t < tbest;
@@ -571,8 +600,8 @@ __global__ void __launch_bounds__(kWfBlock, 6) k_wf_shade(const __grid_constant_
 }
 
 // ---- K4: shadow = Renderer::IsOccluded per light sample (renderer.cpp:209-243), lane refill -------
-template <bool CS>
-__global__ void __launch_bounds__(kWfBlock, 8) k_wf_shadow(const __grid_constant__ WfParams p)
+template <bool CS, bool BWK>
+__global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   if (!wf_block_has_work(p.st.counts + 4 * p.iter + 3, p.st.counts[4 * p.iter + 1])) return;
@@ -598,6 +627,7 @@ __global__ void __launch_bounds__(kWfBlock, 8) k_wf_shadow(const __grid_constant
   const unsigned long long* fine = nullptr;
   DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
   Occ o; occ_reset(o);
+  BW bw; bw.ex = bw.ey = bw.ez = 0; bw.pos = bw.alast = 0; bw.brick = bw.catchup = bw.plain = false;
   unsigned long long steps = 0;
   unsigned int nrays = 0;
   for (;;) {
@@ -632,7 +662,11 @@ __global__ void __launch_bounds__(kWfBlock, 8) k_wf_shadow(const __grid_constant
             if (nvol > 1 && !volume_may_hit(v, org, D)) { vi++; continue; }
             const ORay r = make_oray(xform_scalar(org, 1.0f, v.iM), xform_scalar(D, 0.0f, v.iM));
             vi++;
-            if (setup_dda(v, r, s)) { entered = true; occ_reset(o); region = region_of(stg, v); fine = v.fine; break; }
+            if (setup_dda(v, r, s)) {
+              entered = true; occ_reset(o); region = region_of(stg, v); fine = v.fine;
+              if (BWK) bw_init(v, s, bw);
+              break;
+            }
           }
           if (entered) { in_dda = true; break; }
           // all volumes passed unoccluded: analytic primitives, then accept the sample
@@ -676,23 +710,42 @@ __global__ void __launch_bounds__(kWfBlock, 8) k_wf_shadow(const __grid_constant
     if (!in_dda) s.t = 3.0e38f;
     const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted) ? 1u : (unsigned)p.refill;
     bool occluded = false;
-    const bool drained = thr == 1u;
-    bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) <= (unsigned)p.bulk;
-    for (;;) {
+    if (BWK) {
+      // brick lanes / cell lanes as in k_wf_extend; an occupied cell ends the sample
+      for (;;) {
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        if (s.t < tmaxray) {
-          if (CS) steps++;
-          uint32_t skipped = 0;
-          const bool solid = occ_visit(region, fine, o, s, tmaxray, sparse, skipped);
-          if (CS) steps += skipped;
-          if (solid) { occluded = true; s.t = 3.0e38f; }
-          else if (!dda_step(s)) s.t = 3.0e38f;
+        for (int u = 0; u < 2; u++) {
+          if (s.t < tmaxray) {
+            if ((s.P ^ o.key) >> 6) {
+              occ_fetch(region, fine, o, s.P);
+              const bool nb = o.m == 0ull && !bw.plain;
+              bw.catchup = bw.catchup || (bw.brick && !nb);
+              bw.brick = nb;
+            }
+            if (uw_step(s, bw, o.m)) { occluded = true; s.t = 3.0e38f; }
+          }
         }
+        if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) < thr) break;
       }
-      const unsigned act = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray));
-      sparse = drained || act <= (unsigned)p.bulk;
-      if (act < thr) break;
+    } else {
+      const bool drained = thr == 1u;
+      bool sparse = drained || (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) <= (unsigned)p.bulk;
+      for (;;) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          if (s.t < tmaxray) {
+            if (CS) steps++;
+            uint32_t skipped = 0;
+            const bool solid = occ_visit(region, fine, o, s, tmaxray, sparse, skipped);
+            if (CS) steps += skipped;
+            if (solid) { occluded = true; s.t = 3.0e38f; }
+            else if (!dda_step(s)) s.t = 3.0e38f;
+          }
+        }
+        const unsigned act = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray));
+        sparse = drained || act <= (unsigned)p.bulk;
+        if (act < thr) break;
+      }
     }
     if (in_dda) {
       in_dda = s.t < tmaxray;

@@ -1,0 +1,253 @@
+/* TEST INFRASTRUCTURE (CPU model, never linked into the product).
+ *
+ * Exactness model of the two-level walk the CUDA traversal kernels use (csrc/vp_device.cuh, "brick walk"):
+ * the reference's Amanatides-Woo loop (template/scene.cpp:763-804) visits cells in the order obtained by
+ * MERGING three per-axis sequences  tmax_a, tmax_a + d_a, (tmax_a + d_a) + d_a, ...  (sequential float adds),
+ * always consuming the smallest head, ties resolved z before y before x (the nested ifs of :776-803).
+ * Every element is one cell-boundary crossing; every 4th element of an axis crosses a 4x4x4-brick boundary.
+ * Because the merge order is a total order on (value, axis priority), the sequence of BRICKS the walk visits is
+ * the merge of the brick-crossing elements alone.  Through bricks whose occupancy mask is 0 the walk therefore
+ * only needs, per axis, the value of the next brick-crossing element E_a (the same sequential adds, 4 per
+ * crossing) and no per-cell compare/select; when a non-empty brick is entered at key (T, a), the deferred
+ * cell steps of the other axes are caught up (elements with key < (T, a), at most 3 per axis).
+ * s.t at every cell test, the hit cell and the hit t are bit-identical to the cell walk.
+ *
+ * bw_compare() runs both walks on the same rays and reports mismatches plus the event counts that size the
+ * kernel (brick steps, cell steps, mode switches).  Used by tests/test_brickwalk_model.py.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+typedef struct { float F[3], d[3], t; int X[3], dir[3]; } St;
+
+static inline int f2i(float v) { return (v >= -2147483648.0f && v < 2147483648.0f) ? (int)v : (int)0x80000000u; }
+static inline float stdminf_(float a, float b) { return (b < a) ? b : a; }
+static inline float stdmaxf_(float a, float b) { return (a < b) ? b : a; }
+
+/* Setup3DDDA (template/scene.cpp:719-749) for the unit cube [0,1]^3 and an n^3 grid; returns 0 on a miss */
+static int setup(const float O[3], const float D[3], int n, St* s)
+{
+  float rD[3]; int neg[3];
+  for (int a = 0; a < 3; a++) { rD[a] = 1.0f / D[a]; uint32_t u; memcpy(&u, &D[a], 4); neg[a] = (int)(u >> 31); }
+  float t = 0;
+  const int inside = O[0] >= 0 && O[1] >= 0 && O[2] >= 0 && O[0] <= 1 && O[1] <= 1 && O[2] <= 1;
+  if (!inside) {
+    const int sx = D[0] < 0, sy = D[1] < 0, sz = D[2] < 0;
+    float tmin = ((sx ? 1.0f : 0.0f) - O[0]) * rD[0], tmax = ((sx ? 0.0f : 1.0f) - O[0]) * rD[0];
+    const float tminy = ((sy ? 1.0f : 0.0f) - O[1]) * rD[1], tmaxy = ((sy ? 0.0f : 1.0f) - O[1]) * rD[1];
+    if (tmin > tmaxy || tminy > tmax) return 0;
+    tmin = stdmaxf_(tmin, tminy); tmax = stdminf_(tmax, tmaxy);
+    const float tminz = ((sz ? 1.0f : 0.0f) - O[2]) * rD[2], tmaxz = ((sz ? 0.0f : 1.0f) - O[2]) * rD[2];
+    if (tmin > tmaxz || tminz > tmax) return 0;
+    tmin = stdmaxf_(tmin, tminz);
+    if (!(tmin > 0)) return 0;
+    t = tmin;
+    if (t > 1e33f) return 0;
+  }
+  s->t = t;
+  const float gs = (float)n, cell = 1.0f / gs, tt = t + 0.00005f;
+  for (int a = 0; a < 3; a++) {
+    const float pos = gs * (O[a] + tt * D[a]);
+    const float plane = (ceilf(pos) - (float)neg[a]) * cell;
+    int X = f2i(pos); if (X > n - 1) X = n - 1; if (X < 0) X = 0;
+    s->X[a] = X;
+    s->dir[a] = neg[a] ? -1 : 1;
+    s->d[a] = cell * (neg[a] ? -1.0f : 1.0f) * rD[a];
+    s->F[a] = (plane * 1.0f - O[a]) * rD[a];
+  }
+  return 1;
+}
+
+/* axis choice of template/scene.cpp:776-803 */
+static inline int pick(const float v[3])
+{
+  if (v[0] < v[1]) return (v[0] < v[2]) ? 0 : 2;
+  return (v[1] < v[2]) ? 1 : 2;
+}
+
+typedef struct { int hit; float t; int X[3]; uint32_t steps; } Res;
+
+static Res cell_walk(const uint8_t* grid, int n, St s, float tlimit)
+{
+  Res r; memset(&r, 0, sizeof r);
+  while (s.t < tlimit) {
+    r.steps++;
+    if (grid[s.X[0] + n * (s.X[1] + n * s.X[2])] != 255) { r.hit = 1; r.t = s.t; memcpy(r.X, s.X, sizeof r.X); return r; }
+    const int a = pick(s.F);
+    s.t = s.F[a];
+    s.X[a] += s.dir[a];
+    if ((unsigned)s.X[a] >= (unsigned)n) break;
+    s.F[a] += s.d[a];
+  }
+  return r;
+}
+
+typedef struct { uint64_t brick_steps, cell_steps, to_cell, to_brick, rays, ref_steps, nan_rays; } Stats;
+
+static inline uint64_t brick_mask(const uint64_t* fine, int nb, const int X[3])
+{
+  return fine[(X[0] >> 2) + nb * ((X[1] >> 2) + nb * (X[2] >> 2))];
+}
+static inline int mask_bit(uint64_t m, const int X[3]) { return (int)((m >> ((X[0] & 3) | ((X[1] & 3) << 2) | ((X[2] & 3) << 4))) & 1u); }
+
+/* key (v, axis b) < key (T, axis a), b != a: ties go to the higher axis index */
+static inline int key_before(float v, int b, float T, int a) { return v < T || (v == T && b > a); }
+
+static Res brick_walk(const uint8_t* grid, const uint64_t* fine, int n, St s, float tlimit, Stats* st)
+{
+  (void)grid;
+  Res r; memset(&r, 0, sizeof r);
+  const int nb = n >> 2;
+  const int plain = (s.F[0] != s.F[0]) || (s.F[1] != s.F[1]) || (s.F[2] != s.F[2]);  /* NaN tmax: cell walk only */
+  if (plain) st->nan_rays++;
+  uint64_t m = brick_mask(fine, nb, s.X);
+  float E[3];
+  int brick_mode = 0;
+  for (;;) {
+    if (!brick_mode) {
+      /* ---- cell mode: the reference loop, occupancy from the brick mask ---- */
+      int left_grid = 0, changed = 0;
+      while (s.t < tlimit) {
+        st->cell_steps++;
+        if (mask_bit(m, s.X)) { r.hit = 1; r.t = s.t; memcpy(r.X, s.X, sizeof r.X); return r; }
+        const int a = pick(s.F);
+        s.t = s.F[a];
+        const int before = s.X[a] >> 2;
+        s.X[a] += s.dir[a];
+        if ((unsigned)s.X[a] >= (unsigned)n) { left_grid = 1; break; }
+        s.F[a] += s.d[a];
+        if ((s.X[a] >> 2) != before) {
+          m = brick_mask(fine, nb, s.X);
+          if (m == 0 && !plain) { changed = 1; break; }
+        }
+      }
+      if (left_grid || !changed) return r;
+      /* -> brick mode: E_a = the element of axis a that crosses the brick boundary */
+      st->to_brick++;
+      for (int a = 0; a < 3; a++) {
+        const int c = s.X[a] & 3, k = (s.dir[a] < 0) ? c : 3 - c;  /* cell steps before the crossing one */
+        float e = s.F[a];
+        for (int i = 0; i < k; i++) e += s.d[a];
+        E[a] = e;
+      }
+      brick_mode = 1;
+    } else {
+      /* ---- brick mode: the current brick is empty; s.t = time it was entered ---- */
+      int into_solid = 0, a = 0;
+      while (s.t < tlimit) {
+        st->brick_steps++;
+        a = pick(E);
+        const float T = E[a];
+        s.t = T;
+        /* move to the exit face, then across it */
+        s.X[a] = (s.dir[a] < 0) ? (s.X[a] & ~3) : (s.X[a] | 3);
+        s.X[a] += s.dir[a];
+        if ((unsigned)s.X[a] >= (unsigned)n) return r;
+        s.F[a] = T + s.d[a];
+        E[a] = ((s.F[a] + s.d[a]) + s.d[a]) + s.d[a];
+        m = brick_mask(fine, nb, s.X);   /* X of the other axes is stale but inside the same brick column */
+        if (m) { into_solid = 1; break; }
+      }
+      if (!into_solid) return r;
+      /* -> cell mode: catch up the deferred cell steps of the other axes */
+      st->to_cell++;
+      for (int b = 0; b < 3; b++) {
+        if (b == a) continue;
+        while (key_before(s.F[b], b, s.t, a)) { s.F[b] += s.d[b]; s.X[b] += s.dir[b]; }
+      }
+      brick_mode = 0;
+    }
+  }
+}
+
+
+/* The kernels' formulation: ONE step body for both kinds of lanes.  A lane inside an empty brick ("brick" set) merges
+ * the crossing elements E_a, any other lane the cell elements F_a; E_a is kept current by cell steps too (a cell step
+ * only changes E_a when it crosses a brick boundary), so entering brick mode costs nothing.  Leaving it needs no
+ * explicit catch-up either: the deferred elements of the other two axes are the smallest heads, so the ordinary cell
+ * steps that follow consume them first, in merge order; such a step is SILENT (no cell test, s.t unchanged) while its
+ * key lies below (s.t, axis of the last real step). */
+static Res unified_walk(const uint64_t* fine, int n, St s, float tlimit, Stats* st)
+{
+  Res r; memset(&r, 0, sizeof r);
+  const int nb = n >> 2;
+  const int plain = (s.F[0] != s.F[0]) || (s.F[1] != s.F[1]) || (s.F[2] != s.F[2]) || (n & 3);
+  float E[3] = {0, 0, 0};
+  if (!plain)
+    for (int a = 0; a < 3; a++) {
+      const int c = s.X[a] & 3, k = (s.dir[a] < 0) ? c : 3 - c;
+      float e = s.F[a];
+      for (int i = 0; i < k; i++) e += s.d[a];
+      E[a] = e;
+    }
+  int brick = 0, catchup = 0, alast = 0, have = 0;
+  int key[3] = {-1, -1, -1};
+  uint64_t m = 0;
+  while (s.t < tlimit) {
+    const int bx = s.X[0] >> 2, by = s.X[1] >> 2, bz = s.X[2] >> 2;
+    if (!have || bx != key[0] || by != key[1] || bz != key[2]) {
+      m = brick_mask(fine, nb, s.X); key[0] = bx; key[1] = by; key[2] = bz; have = 1;
+      const int was = brick;
+      brick = (m == 0) && !plain;
+      if (was && !brick) { catchup = 1; st->to_cell++; }
+      if (!was && brick) st->to_brick++;
+    }
+    const float* v = brick ? E : s.F;
+    const int a = pick(v);
+    const float T = v[a];
+    const int silent = !brick && catchup && (T < s.t || (T == s.t && a > alast));
+    if (brick) st->brick_steps++; else st->cell_steps++;
+    if (!brick && !silent) {
+      catchup = 0;
+      if (mask_bit(m, s.X)) { r.hit = 1; r.t = s.t; memcpy(r.X, s.X, sizeof r.X); return r; }
+    }
+    const int c = s.X[a] & 3, k = (s.dir[a] < 0) ? c : 3 - c;
+    const int cross = brick || k == 0;
+    const float f = T + s.d[a];
+    const float e = ((f + s.d[a]) + s.d[a]) + s.d[a];
+    if (brick) s.X[a] = (s.dir[a] < 0) ? (s.X[a] & ~3) : (s.X[a] | 3);
+    s.X[a] += s.dir[a];
+    if (!silent) { s.t = T; alast = a; }
+    if ((unsigned)s.X[a] >= (unsigned)n) return r;
+    s.F[a] = f;
+    if (cross) E[a] = e;
+  }
+  return r;
+}
+
+/* fine[bx + nb*(by + nb*bz)] bit (x&3)|(y&3)<<2|(z&3)<<4 */
+void bw_build_fine(const uint8_t* grid, int n, uint64_t* fine)
+{
+  const int nb = n >> 2;
+  memset(fine, 0, sizeof(uint64_t) * (size_t)nb * nb * nb);
+  for (int z = 0; z < n; z++) for (int y = 0; y < n; y++) for (int x = 0; x < n; x++)
+    if (grid[x + n * (y + n * z)] != 255)
+      fine[(x >> 2) + nb * ((y >> 2) + nb * (z >> 2))] |= 1ull << ((x & 3) | ((y & 3) << 2) | ((z & 3) << 4));
+}
+
+/* rays: O[3], D[3] per ray (object space of the unit cube), tlimit per ray.  Returns the number of mismatching rays;
+ * first_bad = index of the first one (or -1).  out (optional): per ray {hit, t bits, cell} of the cell walk. */
+int64_t bw_compare(const uint8_t* grid, const uint64_t* fine, int n, const float* O, const float* D, const float* tlimit, int64_t count,
+                   int mode, Stats* st, int64_t* first_bad, uint32_t* out)
+{
+  int64_t bad = 0;
+  *first_bad = -1;
+  memset(st, 0, sizeof *st);
+  for (int64_t i = 0; i < count; i++) {
+    St s;
+    Res a, b;
+    memset(&a, 0, sizeof a); memset(&b, 0, sizeof b);
+    if (setup(O + 3 * i, D + 3 * i, n, &s)) {
+      st->rays++;
+      a = cell_walk(grid, n, s, tlimit[i]);
+      b = mode ? unified_walk(fine, n, s, tlimit[i], st) : brick_walk(grid, fine, n, s, tlimit[i], st);
+      st->ref_steps += a.steps;
+    }
+    uint32_t ta, tb; memcpy(&ta, &a.t, 4); memcpy(&tb, &b.t, 4);
+    const int same = a.hit == b.hit && (!a.hit || (ta == tb && a.X[0] == b.X[0] && a.X[1] == b.X[1] && a.X[2] == b.X[2]));
+    if (!same) { if (*first_bad < 0) *first_bad = i; bad++; }
+    if (out) { out[3 * i] = (uint32_t)a.hit; out[3 * i + 1] = ta; out[3 * i + 2] = a.hit ? (uint32_t)(a.X[0] + n * (a.X[1] + n * a.X[2])) : 0u; }
+  }
+  return bad;
+}
