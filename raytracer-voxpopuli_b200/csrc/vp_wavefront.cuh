@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
   const unsigned long long* fine = nullptr;
   DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
   Occ o; occ_reset(o);
-  BW bw; bw.ex = bw.ey = bw.ez = 0; bw.pos = bw.alast = 0; bw.brick = bw.catchup = bw.plain = false;
+  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.pos = bw.ac = bw.brick = bw.plain = 0;
   unsigned long long steps = 0, steps_er = 0, steps_eb = 0;
   unsigned int nrays = 0;
   for (;;) {
@@ -285,11 +285,10 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
           if (s.t < tbest) {
             if ((s.P ^ o.key) >> 6) {
               occ_fetch(region, fine, o, s.P);
-              const bool nb = o.m == 0ull && !bw.plain;
-              bw.catchup = bw.catchup || (bw.brick && !nb);
-              bw.brick = nb;
+              bw.brick = (o.m == 0ull ? 1u : 0u) & ~bw.plain;
             }
-            if (uw_step(s, bw, o.m)) { tbest = s.t; s.t = __uint_as_float(kHitTag); }  // NaN tag: stops the walk, recovered below
+            const float t0 = s.t;
+            if (uw_step(s, bw, o.m, __uint_as_float(kHitTag))) tbest = t0;  // NaN tag: stops the walk, recovered below
           }
         }
         if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) < thr) break;
@@ -627,7 +626,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __gr
   const unsigned long long* fine = nullptr;
   DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
   Occ o; occ_reset(o);
-  BW bw; bw.ex = bw.ey = bw.ez = 0; bw.pos = bw.alast = 0; bw.brick = bw.catchup = bw.plain = false;
+  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.pos = bw.ac = bw.brick = bw.plain = 0;
   unsigned long long steps = 0;
   unsigned int nrays = 0;
   for (;;) {
@@ -718,11 +717,9 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __gr
           if (s.t < tmaxray) {
             if ((s.P ^ o.key) >> 6) {
               occ_fetch(region, fine, o, s.P);
-              const bool nb = o.m == 0ull && !bw.plain;
-              bw.catchup = bw.catchup || (bw.brick && !nb);
-              bw.brick = nb;
+              bw.brick = (o.m == 0ull ? 1u : 0u) & ~bw.plain;
             }
-            if (uw_step(s, bw, o.m)) { occluded = true; s.t = 3.0e38f; }
+            if (uw_step(s, bw, o.m, 3.0e38f)) occluded = true;
           }
         }
         if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) < thr) break;
