@@ -256,18 +256,14 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ BatchP
 __global__ void k_fine(const uint8_t* __restrict__ grid, uint32_t n, uint32_t jr, unsigned long long* __restrict__ fine)
 {
   const uint32_t total = 64u << (3 * jr);
-  const uint32_t rmask = (1u << jr) - 1u;
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < total; b += gridDim.x * blockDim.x) {
-    const uint32_t rg = b >> 6;
-    const uint32_t bx = (b & 3u) | ((rg & rmask) << 2);
-    const uint32_t by = ((b >> 2) & 3u) | (((rg >> jr) & rmask) << 2);
-    const uint32_t bz = ((b >> 4) & 3u) | (((rg >> (2 * jr)) & rmask) << 2);
+    const uint32_t bx = compact3(b), by = compact3(b >> 1), bz = compact3(b >> 2);  // b = Morton index of the brick (P >> 6)
     unsigned long long m = 0;
     for (uint32_t z = 0; z < 4; z++)
       for (uint32_t y = 0; y < 4; y++)
         for (uint32_t x = 0; x < 4; x++) {
           const uint32_t X = bx * 4 + x, Y = by * 4 + y, Z = bz * 4 + z;
-          if (X < n && Y < n && Z < n && grid[X + (Y + Z * n) * n] != VP_MAT_NONE) m |= 1ull << (x + 4 * y + 16 * z);
+          if (X < n && Y < n && Z < n && grid[X + (Y + Z * n) * n] != VP_MAT_NONE) m |= 1ull << (dilate3(x) | (dilate3(y) << 1) | (dilate3(z) << 2));
         }
     fine[b] = m;
   }

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
   const unsigned long long* fine = nullptr;
   DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
   Occ o; occ_reset(o);
-  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.pos = bw.ac = bw.brick = bw.plain = 0;
+  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.F = bw.flip = bw.ac = bw.brick = bw.plain = 0;
   unsigned long long steps = 0, steps_er = 0, steps_eb = 0;
   unsigned int nrays = 0;
   for (;;) {
@@ -283,12 +283,13 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
 #pragma unroll
         for (int u = 0; u < 2; u++) {
           if (s.t < tbest) {
-            if ((s.P ^ o.key) >> 6) {
-              occ_fetch(region, fine, o, s.P);
+            const uint32_t Pr = s.P ^ bw.flip;  // the walk is mirrored: real cell
+            if ((Pr ^ o.key) >> 6) {
+              occ_fetch(region, fine, o, Pr);
               bw.brick = (o.m == 0ull ? 1u : 0u) & ~bw.plain;
             }
             const float t0 = s.t;
-            if (uw_step(s, bw, o.m, __uint_as_float(kHitTag))) tbest = t0;  // NaN tag: stops the walk, recovered below
+            if (uw_step(s, bw, o.m, Pr, __uint_as_float(kHitTag))) tbest = t0;  // NaN tag: stops the walk, recovered below
           }
         }
         if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) < thr) break;
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
         if (act < thr) break;
       }
     }
-    if (__float_as_uint(s.t) == kHitTag) { pbest = s.P; volbest = vi - 1; s.t = 3.0e38f; }  // the cell the walk stopped on
+    if (__float_as_uint(s.t) == kHitTag) { pbest = BWK ? (s.P ^ bw.flip) : s.P; volbest = vi - 1; s.t = 3.0e38f; }  // the cell the walk stopped on
     in_dda = s.t < tbest;
   }
   wf_add_counter(p.counters + 0, nrays);
@@ -626,7 +627,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __gr
   const unsigned long long* fine = nullptr;
   DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
   Occ o; occ_reset(o);
-  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.pos = bw.ac = bw.brick = bw.plain = 0;
+  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.F = bw.flip = bw.ac = bw.brick = bw.plain = 0;
   unsigned long long steps = 0;
   unsigned int nrays = 0;
   for (;;) {
@@ -715,11 +716,12 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __gr
 #pragma unroll
         for (int u = 0; u < 2; u++) {
           if (s.t < tmaxray) {
-            if ((s.P ^ o.key) >> 6) {
-              occ_fetch(region, fine, o, s.P);
+            const uint32_t Pr = s.P ^ bw.flip;
+            if ((Pr ^ o.key) >> 6) {
+              occ_fetch(region, fine, o, Pr);
               bw.brick = (o.m == 0ull ? 1u : 0u) & ~bw.plain;
             }
-            if (uw_step(s, bw, o.m, 3.0e38f)) occluded = true;
+            if (uw_step(s, bw, o.m, Pr, 3.0e38f)) occluded = true;
           }
         }
         if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) < thr) break;
