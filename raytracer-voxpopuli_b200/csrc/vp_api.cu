@@ -127,6 +127,8 @@ struct vp_ctx {
   int tune_refill = kRefill;  // VP_REFILL
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
   int tune_brickwalk = 1;     // VP_BRICKWALK: 0 = cell walk only (A/B)
+  int tune_bands = 4;         // VP_BANDS: row bands a vp_render call is cut into (1 = off)
+  long long tune_band_min_pixels = 1 << 18;  // VP_BAND_MIN_PIXELS: smaller calls are not cut
   int tune_persistent = 0;    // VP_PERSISTENT=1: persistent kernel instead of per-stage kernels
   int wf_blocks_persistent = 0;
   uint32_t last_error_word = 0;  // error word of the last persistent launch (valid after a stream sync)
@@ -662,6 +664,8 @@ vp_ctx* vp_create(int device)
   if (const char* e = getenv("VP_BULK_LANES")) c->tune_bulk = atoi(e);
   if (const char* e = getenv("VP_REFILL")) c->tune_refill = atoi(e);
   if (const char* e = getenv("VP_BRICKWALK")) c->tune_brickwalk = atoi(e);
+  if (const char* e = getenv("VP_BANDS")) c->tune_bands = atoi(e) < 1 ? 1 : atoi(e);
+  if (const char* e = getenv("VP_BAND_MIN_PIXELS")) c->tune_band_min_pixels = atoll(e);
   if (const char* e = getenv("VP_BLOCKS_EXTEND")) { c->wf_blocks_extend = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
   if (const char* e = getenv("VP_BLOCKS_SHADOW")) { c->wf_blocks_shadow = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
   return c;
@@ -942,6 +946,60 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
   CU(cudaEventRecord(c->ev_copy, c->copy));
   c->wait_copy = true;
   VpStats local;
+  // Row bands: a synchronous call cannot keep several frames in flight, so the frame itself is cut into bands of rows that
+  // run as deferred passes on the context's lanes (their latency-bound tails overlap like those of successive frames), and
+  // the rows of a band travel back while the later bands are still being traced.  Pixels are independent and seeded per
+  // pixel: the result does not depend on the cut.
+  int nb = c->nlanes > 1 ? c->tune_bands : 1;  // more bands than lanes queue up on the lanes in turn
+  if (nb > kCallRing) nb = kCallRing;
+  const bool wavefront = fp->max_bounces >= 0 && c->sc.area_samples <= kMaxAreaSamples && !c->tune_persistent &&
+                         !(fp->flags & (VP_FLAG_MEGAKERNEL | VP_FLAG_PERSISTENT | VP_FLAG_COUNT_STEPS | VP_FLAG_TIME_STAGES));
+  if (tiled || !wavefront || fp->spp < 1 || (long long)(re - rb) * fp->width < c->tune_band_min_pixels || re - rb < 8 * nb) nb = 1;
+  if (nb > 1) {
+    VpStats* st = stats ? stats : &local;
+    unsigned long long before[8] = {0}, after[8] = {0};
+    if (int rc = join_lanes(c, c->stream)) return rc;
+    if (stats) {
+      CU(cudaMemcpyAsync(before, c->d_counters.p, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
+    const unsigned long long launches_before = c->host_launches;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    const int rows = ((re - rb + nb - 1) / nb + 7) & ~7;
+    cudaEvent_t done[kCallRing];
+    int nband = 0;
+    for (int r0 = rb; r0 < re; r0 += rows, nband++) {
+      VpFrameParams b = *fp;
+      b.row_begin = r0; b.row_end = r0 + rows < re ? r0 + rows : re; b.flags |= VP_FLAG_DEFER;
+      done[nband] = c->ev_call[c->ncalls % kCallRing];  // the completion event launch_render records for this call
+      if (int rc = launch_render(c, cam, &b, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, nullptr, true)) return rc;
+    }
+    // copies after all launches: a copy into pageable memory blocks the host until its band is done
+    for (int k = 0; k < nband; k++) {
+      const int r0 = rb + k * rows, r1 = r0 + rows < re ? r0 + rows : re;
+      CU(cudaStreamWaitEvent(c->copy, done[k], 0));
+      const size_t off = (size_t)r0 * W, cnt = (size_t)(r1 - r0) * W;
+      CU(cudaMemcpyAsync(accum + off * 4, (const char*)c->d_accum.p + off * sizeof(float4), cnt * sizeof(float4), cudaMemcpyDeviceToHost, c->copy));
+      if (rgb8) CU(cudaMemcpyAsync(rgb8 + off, c->d_rgb8.p + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copy));
+    }
+    if (int rc = join_lanes(c, c->stream)) return rc;
+    CU(cudaEventRecord(c->ev1, c->stream));
+    if (stats) CU(cudaMemcpyAsync(after, c->d_counters.p, sizeof(after), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    for (int k = 0; k < 8; k++) after[k] -= before[k];
+    st->primary_rays = after[4];
+    st->secondary_rays = after[0] - after[4];
+    st->shadow_rays = after[1];
+    st->exit_rays = after[2];
+    st->dda_steps = after[3];
+    st->sky_samples = after[6];
+    st->device_ms = ms;
+    st->kernel_launches = c->host_launches - launches_before;
+    return 0;
+  }
   if (int rc = launch_render(c, cam, fp, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, stats ? stats : &local, false)) return rc;
   if (c->wait_copy) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->wait_copy = false; }  // spp == 0: nothing consumed the upload
   CU(xfer(accum, c->d_accum.p, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));

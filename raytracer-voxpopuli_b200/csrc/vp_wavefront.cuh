@@ -26,6 +26,10 @@ constexpr int kWfBlock = 128;
 #ifndef VP_WF_MINBLOCKS
 #define VP_WF_MINBLOCKS 8
 #endif
+#ifndef VP_BW_UNROLL
+#define VP_BW_UNROLL 2
+#endif
+constexpr int kBwUnroll = VP_BW_UNROLL;        // brick-walk steps between two votes on the number of walking lanes
 constexpr int kWfMinBlocks = VP_WF_MINBLOCKS;  // resident blocks per SM the traversal kernels are compiled for (64 registers at 8)
 constexpr int kRefill = 20;           // refill when fewer lanes than this are still stepping
 constexpr int kBulkLanes = 12;        // with at most this many lanes walking, lanes in empty 8^3/16^3 blocks bulk-advance
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
       // reference's cell step with the occupancy bit test): vp_device.cuh "brick walk"
       for (;;) {
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < kBwUnroll; u++) {
           if (s.t < tbest) {
             const uint32_t Pr = s.P ^ bw.flip;  // the walk is mirrored: real cell
             if ((Pr ^ o.key) >> 6) {
@@ -714,7 +718,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __gr
       // brick lanes / cell lanes as in k_wf_extend; an occupied cell ends the sample
       for (;;) {
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < kBwUnroll; u++) {
           if (s.t < tmaxray) {
             const uint32_t Pr = s.P ^ bw.flip;
             if ((Pr ^ o.key) >> 6) {

@@ -473,3 +473,31 @@ def test_reprojection_row_sharded(product, oracle, world):
             assert np.array_equal(bits(merged_h), bits(want[f][0])), f"frame {f}: merged history differs"
             assert np.array_equal(merged_rgb, want[f][1]), f"frame {f}: merged rgb8 differs"
             hist = merged_h
+
+
+def test_render_row_bands(product, oracle, monkeypatch):
+    """vp_render cuts a call into row bands that run as deferred passes on the library's lanes, the rows of a band
+    travelling back while later bands are traced (VP_BANDS / VP_BAND_MIN_PIXELS; large frames only by default).
+    Forced on for a small frame here: accumulator, RGB8 and ray counters must equal the oracle's un-banded frame,
+    for one and for several samples per call, with an accumulator carried over between calls and with a row range."""
+    sc, cam, fpd = small_config(3, 128, 72)
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        w1, w1_rgb, st1 = s.render(cam, params(fpd, spp=1))
+        w3, w3_rgb, st3 = s.render(cam, params(fpd, spp=3, frame_index=1), accum=w1.copy())
+        wr, wr_rgb, str_ = s.render(cam, params(fpd, spp=2, frame_index=7, row_begin=10, row_end=61))
+    for bands in ("4", "3", "1"):
+        monkeypatch.setenv("VP_BANDS", bands)
+        monkeypatch.setenv("VP_BAND_MIN_PIXELS", "0")
+        with vp.Session(product) as s:  # the knobs are read when the context is created
+            s.set_scene(sc)
+            g1, g1_rgb, gs1 = s.render(cam, params(fpd, spp=1))
+            g3, g3_rgb, gs3 = s.render(cam, params(fpd, spp=3, frame_index=1), accum=g1.copy())
+            gr, gr_rgb, gsr = s.render(cam, params(fpd, spp=2, frame_index=7, row_begin=10, row_end=61))
+        for a, b, what in ((w1, g1, "1 spp"), (w3, g3, "3 spp carried"), (wr, gr, "row range")):
+            assert np.count_nonzero(bits(a) != bits(b)) == 0, f"bands={bands} {what}: accumulator differs"
+        for a, b in ((w1_rgb, g1_rgb), (w3_rgb, g3_rgb), (wr_rgb, gr_rgb)):
+            assert np.count_nonzero(a != b) == 0
+        assert (gs1.rays, gs3.rays, gsr.rays) == (st1.rays, st3.rays, str_.rays)
+        if bands != "1":
+            assert gs1.kernel_launches > 2 * (3 * (fpd["max_bounces"] + 1) + 2)  # really several passes
