@@ -52,6 +52,7 @@ struct WfState {
   float4* sq0;      // [level][path]: origin.xyz, w = bits nsamp(8) | level(8) << 8 | area(1) << 16 | mat(8) << 24
   float4* sqd;      // [level][sample][path]: dir.xyz, w = dist
   float4* sql;      // [level][sample][path]: li.xyz (single lights: final contribution), w = valid
+  float4* ps[3];        // prepared walks [queue position]: 0 = tmax.xyz, t; 1 = tdelta.xyz, P' bits; 2 = E.xyz, flags (k_wf_prepare)
   uint32_t* q[2];       // active-path queues (ping-pong)
   uint32_t* qs[2];      // shadow-request queues (bounce parity)
   uint32_t* counts;     // [iter][4]: 0 = active count entering iter, 1 = shadow count of iter, 2 = extend cursor, 3 = shadow cursor
@@ -197,6 +198,40 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant_
   wf_add_counter(p.counters + 4, launched);
 }
 
+// ---- K2a: prepare = the part of Renderer::FindNearest that precedes the walk ------------------------------------------
+// (renderer.cpp:958-975: world -> object ray, Scene::Setup3DDDA) for the first volume each ray of the bounce enters, one
+// lane per ray at full width - inside the extend stage the same ~240 instructions run with a quarter of the lanes, because
+// only the lanes that refill execute them.  The record is indexed by queue position, so writes here and reads by the
+// refilling lanes are coalesced.  flags: bits 0..15 = index + 1 of the volume entered (0: the ray enters none),
+// bit 16 = ray excluded from brick mode, bits 17..19 = mirrored axes.
+__global__ void __launch_bounds__(kWfBlock) k_wf_prepare(const __grid_constant__ WfParams p)
+{
+  const uint32_t* queue = p.st.q[p.iter & 1];
+  const uint32_t n = p.st.counts[4 * p.iter];
+  const int nvol = p.sc.nvol;
+  for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
+    const uint32_t path = queue[qi];
+    const float4 a = p.st.r0[path], b = p.st.r1[path];
+    const f3 O = v3(a.x, a.y, a.z), D = v3(b.x, b.y, b.z);
+    DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = 0;
+    BW bw; bw.ex = bw.ey = bw.ez = 0; bw.plain = 0; bw.flip = 0; bw.F = 0;
+    uint32_t flags = 0;
+    for (int vi = 0; vi < nvol; vi++) {
+      const DVolume& v = p.sc.vol[vi];
+      if (nvol > 1 && !volume_may_hit(v, O, D)) continue;
+      const ORay r = make_oray(xform_pos_sse(O, v.iM), xform_vec_sse(D, v.iM));
+      if (setup_dda(v, r, s)) {
+        bw_init(v, s, bw);
+        flags = (uint32_t)(vi + 1) | (bw.plain << 16) | ((s.Sx != 1u ? 1u : 0u) << 17) | ((s.Sy != 2u ? 1u : 0u) << 18) | ((s.Sz != 4u ? 1u : 0u) << 19);
+        break;
+      }
+    }
+    p.st.ps[0][qi] = make_float4(s.tx, s.ty, s.tz, s.t);
+    p.st.ps[1][qi] = make_float4(s.dx, s.dy, s.dz, __uint_as_float(s.P));
+    p.st.ps[2][qi] = make_float4(bw.ex, bw.ey, bw.ez, __uint_as_float(flags));
+  }
+}
+
 // ---- K2: extend = Renderer::FindNearest (renderer.cpp:946-1018), persistent warps with lane refill ----
 // Writes per path: t, the winning volume and the hit cell (as P).  The face normal and the
 // material byte are produced by the shade stage where all 32 lanes are busy, not here where
@@ -213,6 +248,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
   uint32_t* cnt = p.st.counts + 4 * p.iter;
   const uint32_t n = cnt[0];
   const int nvol = p.sc.nvol;
+  const bool need_world = nvol > 1 || p.sc.nsph + p.sc.ntri > 0;  // the world-space ray is only needed past the first volume
   bool has_ray = false, in_dda = false, exhausted = false;
   uint32_t path = 0;
   f3 O = v3s(0), D = v3s(0);
@@ -238,11 +274,33 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
         const uint32_t qi = base + (uint32_t)__popc(nm & ((1u << lane) - 1u));
         if (qi < n) {
           path = queue[qi];
-          const float4 a = p.st.r0[path], b = p.st.r1[path];
-          O = v3(a.x, a.y, a.z); D = v3(b.x, b.y, b.z);
           tbest = 1e34f; pbest = 0; volbest = -2;
           vi = 0; has_ray = true; in_dda = false;
           nrays++;
+          if (BWK) {
+            // the walk through the first volume the ray enters was set up by k_wf_prepare
+            const float4 w0 = __ldcs(p.st.ps[0] + qi), w1 = __ldcs(p.st.ps[1] + qi), w2 = __ldcs(p.st.ps[2] + qi);
+            const uint32_t fl = __float_as_uint(w2.w);
+            vi = (fl & 0xFFFFu) ? (int)(fl & 0xFFFFu) : nvol;
+            if (fl & 0xFFFFu) {
+              const DVolume& v = svol[vi - 1];
+              s.tx = w0.x; s.ty = w0.y; s.tz = w0.z; s.t = w0.w;
+              s.dx = w1.x; s.dy = w1.y; s.dz = w1.z; s.P = __float_as_uint(w1.w);
+              bw.ex = w2.x; bw.ey = w2.y; bw.ez = w2.z;
+              bw.F = axis_field(v.jr, 0);
+              bw.flip = ((fl >> 17) & 1u ? bw.F : 0u) | ((fl >> 18) & 1u ? bw.F << 1 : 0u) | ((fl >> 19) & 1u ? bw.F << 2 : 0u);
+              bw.plain = (fl >> 16) & 1u; bw.brick = 0u; bw.ac = 0u; bw.tc = __uint_as_float(0xFF800000u);
+              occ_reset(o); region = region_of(stg, v); fine = v.fine;
+              in_dda = true;
+            }
+            if (need_world) {
+              const float4 a = p.st.r0[path], b = p.st.r1[path];
+              O = v3(a.x, a.y, a.z); D = v3(b.x, b.y, b.z);
+            }
+          } else {
+            const float4 a = p.st.r0[path], b = p.st.r1[path];
+            O = v3(a.x, a.y, a.z); D = v3(b.x, b.y, b.z);
+          }
         } else exhausted = true;
       }
     }
