@@ -6,9 +6,11 @@ A "step" is one Renderer::Update() pass (1 spp) of the workload over the whole f
             time), accumulator resident in HBM, kernels enqueued on torch's current stream and
             timed with CUDA events around exactly K steps.
   e2e       the same metric through the reference-facing C-ABI call vp_render() with HOST
-            buffers: float4 accumulator in (pinned) + accumulator and RGB8 out, every step.
-  roofline  dominant kernel (k_render): algorithmic bytes (SURVEY.md 8d formula) / its
-            average device time, against the measured HBM copy bandwidth.
+            buffers: float4 accumulator in (pinned) + accumulator and RGB8 out, every step
+            (the library cuts such a call into row bands so that copies overlap the trace).
+  roofline  dominant kernel (k_wf_extend, the Renderer::FindNearest walk): algorithmic bytes
+            (SURVEY.md 8d formula) / its average device time measured by CUDA events inside
+            the timed region, against the measured HBM copy bandwidth.
   cpu_baseline  the reference's own CPU Trace (oracle/_ref) timed on this box's host cores.
 `--impl reference` times that CPU path alone with the same config/metric.
 Multi-GPU (torchrun): the frame is sharded as interleaved 8-row tiles (scene replicated,
@@ -385,7 +387,8 @@ def main():
             "config": {"workload": scenes.WORKLOAD_NAMES[args.config], "resolution": [W, H], "spp_per_step": 1,
                        "rays_per_step": rays_total / args.steps, "sharding": f"interleaved {ROW_TILE}-row tiles x{world}" if world > 1 else "none",
                        "l2": "flushed between timed iterations (160 MiB fill, inside the timed region)",
-                       "frames_in_flight": 4, "timed_region": "one CUDA-event pair around all steps incl. the L2 flushes; every "
+                       "frames_in_flight": 4, "traversal": "brick walk (one exact merge step per empty 4x4x4 brick), prepare stage",
+                       "timed_region": "one CUDA-event pair around all steps incl. the L2 flushes; every "
                        "20th step runs alone with stage events (VP_FLAG_TIME_STAGES)"},
             "ms_per_frame": total_ms / args.steps,
             "clocks": clocks,
