@@ -65,10 +65,26 @@ struct DevBuf {
 
 // One frame in flight of the wavefront pipeline: its own stream pair, stage events and HBM-resident path state, so
 // that the latency-bound tail of one Update() pass overlaps the wide first bounces of the next one.
+// The launches of one pass up to (not including) its resolve, captured once per lane as a CUDA graph: ~75 kernel launches
+// and ~60 event calls per pass become one cudaGraphLaunch plus one parameter update per kernel node.  What varies between
+// frames (camera, frame index, rows, accumulator, grid sizes of the persistent stages) lives in the kernels' WfParams
+// argument, which cudaGraphExecKernelNodeSetParams replaces; the topology only depends on what `key` holds.
+struct PassGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int max_bounces = -2, brickwalk = -1;
+  size_t smem = 0;
+  const void* counts = nullptr;  // the lane's buffers were (re)allocated: the memset node and every pointer changed
+  struct Node { cudaGraphNode_t node; cudaKernelNodeParams kp; int iter; int kind; };  // kind 1 = extend, 2 = shadow grid
+  std::vector<Node> nodes;
+};
+
 struct WfLane {
+  PassGraph pg;
   cudaStream_t main = nullptr;  // generate, extend(k) -> shade(k), resolve
   cudaStream_t side = nullptr;  // shadow stage
   cudaEvent_t ev_done = nullptr;  // recorded after the lane's resolve
+  cudaEvent_t ev_mid = nullptr;   // recorded after the shade stage of bounce c->tune_band_stagger (row bands start one after the other)
   cudaEvent_t ev_shade[VP_MAX_LEVELS] = {}, ev_shadow[VP_MAX_LEVELS] = {};
   WfState wf{};
   DevBuf<unsigned char> d_wf;
@@ -127,6 +143,11 @@ struct vp_ctx {
   int tune_refill = kRefill;  // VP_REFILL
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
   int tune_brickwalk = 1;     // VP_BRICKWALK: 0 = cell walk only (A/B)
+  int tune_graph = 1;         // VP_GRAPH: 0 = launch every kernel of a pass from the host
+  int tune_band_ramp = 0;     // VP_BAND_RAMP: band heights 1 : 2 : ... : n instead of equal
+  int tune_band_stagger = 0;  // VP_BAND_STAGGER: band k+1 of a vp_render call starts when band k has shaded this bounce (-1: all at once)
+  int band_last_lane = -1;    // lane the most recent pass went to
+  int band_wait_lane = -1;    // lane whose ev_mid the next pass has to wait for (set by vp_render between its bands)
   int tune_bands = 4;         // VP_BANDS: row bands a vp_render call is cut into (1 = off)
   long long tune_band_min_pixels = 1 << 18;  // VP_BAND_MIN_PIXELS: smaller calls are not cut
   int tune_persistent = 0;    // VP_PERSISTENT=1: persistent kernel instead of per-stage kernels
@@ -313,8 +334,9 @@ struct RpArgs {
   float* hist_out;
 };
 
+// generate .. shadow(max_bounces) of one pass, the side stream joined back into L.main; issued directly or under capture
 template <bool CS>
-int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
+int enqueue_trace(vp_ctx* c, WfLane& L, WfParams& p, bool timing, bool capturing)
 {
   cudaStream_t stream = L.main;
   const size_t sm = smem_bytes(c);
@@ -325,7 +347,7 @@ int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
   for (int it = 0; it <= p.max_bounces; it++) {
     p.iter = it;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (c->time_stages_now) {
+    if (timing) {
       if (c->tev_used + 2 > c->tev.size()) {
         for (int k = 0; k < 64; k++) { cudaEvent_t e; CU(cudaEventCreate(&e)); c->tev.push_back(e); }
       }
@@ -342,6 +364,8 @@ int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
     if (it >= 2) CU(cudaStreamWaitEvent(stream, L.ev_shadow[it - 2], 0));  // shade(k) reuses the id queue of shadow(k-2)
     k_wf_shade<CS><<<wide, kWfBlock, sm, stream>>>(p);
     CU(cudaEventRecord(L.ev_shade[it], stream));
+    if (it == c->tune_band_stagger || (it == p.max_bounces && p.max_bounces < c->tune_band_stagger))
+      CU(cudaEventRecordWithFlags(L.ev_mid, stream, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));  // a node of its own when the pass is a graph
     CU(cudaStreamWaitEvent(L.side, L.ev_shade[it], 0));
     if (!CS && c->tune_brickwalk) k_wf_shadow<false, true><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
     else k_wf_shadow<CS, false><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
@@ -349,6 +373,77 @@ int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
     c->host_launches += 3;
   }
   for (int it = (p.max_bounces >= 1 ? p.max_bounces - 1 : 0); it <= p.max_bounces; it++) CU(cudaStreamWaitEvent(stream, L.ev_shadow[it], 0));
+  return 0;
+}
+
+void drop_graph(PassGraph& G)
+{
+  if (G.exec) cudaGraphExecDestroy(G.exec);
+  if (G.graph) cudaGraphDestroy(G.graph);
+  G.exec = nullptr; G.graph = nullptr; G.nodes.clear(); G.max_bounces = -2;
+}
+
+// the trace part of a pass through the lane's graph; returns 1 when graphs are unusable (caller launches directly)
+int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
+{
+  PassGraph& G = L.pg;
+  const size_t sm = smem_bytes(c);
+  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk && G.smem == sm && G.counts == (const void*)p.st.counts);
+  if (fresh) {
+    drop_graph(G);
+    const unsigned long long before = c->host_launches;
+    if (cudaStreamBeginCapture(L.main, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return 1; }
+    const int rc = enqueue_trace<false>(c, L, p, false, true);
+    const cudaError_t e = cudaStreamEndCapture(L.main, &G.graph);
+    c->host_launches = before;
+    if (rc || e != cudaSuccess || !G.graph || cudaGraphInstantiate(&G.exec, G.graph, 0) != cudaSuccess) { cudaGetLastError(); drop_graph(G); return 1; }
+    size_t n = 0;
+    cudaGraphGetNodes(G.graph, nullptr, &n);
+    std::vector<cudaGraphNode_t> all(n);
+    cudaGraphGetNodes(G.graph, all.data(), &n);
+    for (cudaGraphNode_t nd : all) {
+      cudaGraphNodeType ty;
+      if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+      PassGraph::Node x; x.node = nd;
+      if (cudaGraphKernelNodeGetParams(nd, &x.kp) != cudaSuccess) { cudaGetLastError(); drop_graph(G); return 1; }
+      x.iter = reinterpret_cast<const WfParams*>(x.kp.kernelParams[0])->iter;
+      x.kind = (x.kp.func == (void*)k_wf_extend<false, true> || x.kp.func == (void*)k_wf_extend<false, false>) ? 1
+             : (x.kp.func == (void*)k_wf_shadow<false, true> || x.kp.func == (void*)k_wf_shadow<false, false>) ? 2 : 0;
+      G.nodes.push_back(x);
+    }
+    G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk; G.smem = sm; G.counts = (const void*)p.st.counts;
+  } else {
+    for (PassGraph::Node& x : G.nodes) {
+      WfParams q = p;
+      q.iter = x.iter;
+      void* args[1] = {&q};
+      cudaKernelNodeParams kp = x.kp;
+      kp.kernelParams = args;
+      if (x.kind == 1) kp.gridDim = dim3((unsigned)c->wf_grid_extend);
+      if (x.kind == 2) kp.gridDim = dim3((unsigned)c->wf_grid_shadow);
+      CU(cudaGraphExecKernelNodeSetParams(G.exec, x.node, &kp));
+    }
+  }
+  CU(cudaGraphLaunch(G.exec, L.main));
+  c->host_launches += G.nodes.size();
+  return 0;
+}
+
+template <bool CS>
+int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
+{
+  cudaStream_t stream = L.main;
+  const size_t sm = smem_bytes(c);
+  const int wide = c->sm_count * 8;
+  bool traced = false;
+  if (!CS && c->tune_graph && !c->time_stages_now) {
+    const int rc = graph_trace(c, L, p);
+    if (rc < 0) return rc;
+    if (rc == 1) c->tune_graph = 0;  // capture is not possible here: launch from the host from now on
+    traced = rc == 0;
+  }
+  if (!traced)
+    if (int rc = enqueue_trace<CS>(c, L, p, c->time_stages_now, false)) return rc;
   if (c->wait_copy) { CU(cudaStreamWaitEvent(stream, c->ev_copy, 0)); c->wait_copy = false; }
   if (c->ev_last && c->ev_last != L.ev_done) CU(cudaStreamWaitEvent(stream, c->ev_last, 0));
   k_wf_resolve<<<wide, kWfBlock, 0, stream>>>(p);
@@ -489,6 +584,8 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
       const int li = (overlap || fp->spp > 1) ? (c->next_lane++ % c->lanes_now) : 0;
       WfLane& L = c->lane[li];
       if ((rc = wf_reserve(L, tiles * 32u, levels, samples))) return rc;
+      if (c->band_wait_lane >= 0 && c->band_wait_lane != li) CU(cudaStreamWaitEvent(L.main, c->lane[c->band_wait_lane].ev_mid, 0));
+      c->band_last_lane = li;
       if (!entered[li]) {
         CU(cudaStreamWaitEvent(L.main, c->ev_in, 0));
         if (c->direct_recorded) CU(cudaStreamWaitEvent(L.main, c->ev_direct, 0));
@@ -613,7 +710,8 @@ vp_ctx* vp_create(int device)
   for (WfLane& L : c->lane) {
     evok = evok && cudaStreamCreateWithFlags(&L.main, cudaStreamNonBlocking) == cudaSuccess &&
            cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking) == cudaSuccess &&
-           cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming) == cudaSuccess;
+           cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&L.ev_mid, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < VP_MAX_LEVELS && evok; i++)
       evok = cudaEventCreateWithFlags(&L.ev_shade[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&L.ev_shadow[i], cudaEventDisableTiming) == cudaSuccess;
@@ -670,6 +768,9 @@ vp_ctx* vp_create(int device)
   if (const char* e = getenv("VP_BULK_LANES")) c->tune_bulk = atoi(e);
   if (const char* e = getenv("VP_REFILL")) c->tune_refill = atoi(e);
   if (const char* e = getenv("VP_BRICKWALK")) c->tune_brickwalk = atoi(e);
+  if (const char* e = getenv("VP_GRAPH")) c->tune_graph = atoi(e);
+  if (const char* e = getenv("VP_BAND_RAMP")) c->tune_band_ramp = atoi(e);
+  if (const char* e = getenv("VP_BAND_STAGGER")) c->tune_band_stagger = atoi(e);
   if (const char* e = getenv("VP_BANDS")) c->tune_bands = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("VP_BAND_MIN_PIXELS")) c->tune_band_min_pixels = atoll(e);
   if (const char* e = getenv("VP_BLOCKS_EXTEND")) { c->wf_blocks_extend = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
@@ -695,6 +796,8 @@ void vp_destroy(vp_ctx* c)
       if (L.ev_shadow[i]) cudaEventDestroy(L.ev_shadow[i]);
     }
     if (L.ev_done) cudaEventDestroy(L.ev_done);
+    if (L.ev_mid) cudaEventDestroy(L.ev_mid);
+    drop_graph(L.pg);
     if (L.side) cudaStreamDestroy(L.side);
     if (L.main) cudaStreamDestroy(L.main);
   }
@@ -971,20 +1074,35 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
     }
     const unsigned long long launches_before = c->host_launches;
     CU(cudaEventRecord(c->ev0, c->stream));
-    const int rows = ((re - rb + nb - 1) / nb + 7) & ~7;
-    cudaEvent_t done[kCallRing];
-    int nband = 0;
-    for (int r0 = rb; r0 < re; r0 += rows, nband++) {
-      VpFrameParams b = *fp;
-      b.row_begin = r0; b.row_end = r0 + rows < re ? r0 + rows : re; b.flags |= VP_FLAG_DEFER;
-      done[nband] = c->ev_call[c->ncalls % kCallRing];  // the completion event launch_render records for this call
-      if (int rc = launch_render(c, cam, &b, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, nullptr, true)) return rc;
+    // Bands of growing height (1 : 2 : ... : nb): passes that start together advance bounce by bounce at the speed of
+    // their own size, so the small bands finish first - their rows travel while the larger ones are still being traced,
+    // and the latency-bound tails of the bands do not coincide.  Boundaries on multiples of 8 rows.
+    int edge[kCallRing + 1];
+    const int tri = nb * (nb + 1) / 2;
+    edge[0] = rb;
+    for (int k = 1, acc = 0; k <= nb; k++) {
+      acc += c->tune_band_ramp ? k : 0;
+      const long long cut = c->tune_band_ramp ? (long long)(re - rb) * acc / tri : (long long)(re - rb) * k / nb;
+      edge[k] = k == nb ? re : rb + (int)((cut + 7) & ~7ll);
+      if (edge[k] > re) edge[k] = re;
+      if (edge[k] < edge[k - 1]) edge[k] = edge[k - 1];
     }
+    cudaEvent_t done[kCallRing];
+    for (int k = 0; k < nb; k++) {
+      if (edge[k + 1] <= edge[k]) { done[k] = nullptr; continue; }
+      VpFrameParams b = *fp;
+      b.row_begin = edge[k]; b.row_end = edge[k + 1]; b.flags |= VP_FLAG_DEFER;
+      done[k] = c->ev_call[c->ncalls % kCallRing];  // the completion event launch_render records for this call
+      const int rc = launch_render(c, cam, &b, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, nullptr, true);
+      c->band_wait_lane = (c->tune_band_stagger >= 0 && b.spp == 1) ? c->band_last_lane : -1;  // the next band starts behind this one
+      if (rc) { c->band_wait_lane = -1; return rc; }
+    }
+    c->band_wait_lane = -1;
     // copies after all launches: a copy into pageable memory blocks the host until its band is done
-    for (int k = 0; k < nband; k++) {
-      const int r0 = rb + k * rows, r1 = r0 + rows < re ? r0 + rows : re;
+    for (int k = 0; k < nb; k++) {
+      if (!done[k]) continue;
       CU(cudaStreamWaitEvent(c->copy, done[k], 0));
-      const size_t off = (size_t)r0 * W, cnt = (size_t)(r1 - r0) * W;
+      const size_t off = (size_t)edge[k] * W, cnt = (size_t)(edge[k + 1] - edge[k]) * W;
       CU(cudaMemcpyAsync(accum + off * 4, (const char*)c->d_accum.p + off * sizeof(float4), cnt * sizeof(float4), cudaMemcpyDeviceToHost, c->copy));
       if (rgb8) CU(cudaMemcpyAsync(rgb8 + off, c->d_rgb8.p + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copy));
     }

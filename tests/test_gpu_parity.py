@@ -501,3 +501,38 @@ def test_render_row_bands(product, oracle, monkeypatch):
         assert (gs1.rays, gs3.rays, gsr.rays) == (st1.rays, st3.rays, str_.rays)
         if bands != "1":
             assert gs1.kernel_launches > 2 * (3 * (fpd["max_bounces"] + 1) + 2)  # really several passes
+
+
+@pytest.mark.parametrize("n", [20, 50, 100])
+def test_grid_sizes_off_the_brick_lattice(product, oracle, n):
+    """Grid sizes that are neither a power of two nor a multiple of the 4-cell brick: the brick walk runs in the
+    padded power-of-two domain (mirrored coordinates) and walks the empty padding before it leaves.  Rotated, scaled
+    volume with a floor and random voxels; primary hits, accumulator, batched nearest / any-hit queries against the
+    oracle, bit for bit."""
+    from _util import host
+    rng = np.random.default_rng(n)
+    g = np.full((n, n, n), 255, np.uint8)  # [z, y, x]
+    g[:, 0, :] = 3
+    fill = rng.uniform(size=(n, n, n)) < 0.04
+    g[fill] = rng.integers(0, 8, int(fill.sum())).astype(np.uint8)
+    M, iM, a, b = host.make_transform((0.25, 0.0, 0.5), (0.0, 0.6, 0.0), (1.5, 1.0, 1.25))
+    sc = vp.SceneDesc(volumes=[vp.Volume(np.ascontiguousarray(g.reshape(-1)), n, a, b, M, iM)], materials=host.default_materials(),
+                      point_lights=[((0.5, 2.5, -0.5), (6, 6, 6)), ((2.0, 1.5, 2.5), (3, 3, 4))])
+    cam = host.look_at((0.2, 1.4, -1.6), (1.0, 0.3, 1.2), 96, 54)
+    fp = vp.frame_params(96, 54, max_bounces=6, spp=2)
+    o = rng.uniform(-0.5, 2.5, (4096, 3)).astype(np.float32)
+    d = rng.normal(size=(4096, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[::7, 1] = 0.0  # some rays parallel to an axis plane of the world
+    rays = vp.make_rays(o, d)
+    res = []
+    for lib in (oracle, product):
+        with vp.Session(lib) as s:
+            s.set_scene(sc)
+            res.append((s.trace_primary(cam, fp), s.render(cam, fp), s.find_nearest(rays), s.is_occluded(rays)))
+    assert_hits_equal(res[0][0], res[1][0], f"n={n} primary")
+    assert np.count_nonzero(bits(res[0][1][0]) != bits(res[1][1][0])) == 0
+    assert res[0][1][2].rays == res[1][1][2].rays
+    assert_hits_equal(res[0][2], res[1][2], f"n={n} nearest")
+    assert np.array_equal(res[0][3], res[1][3])
+    assert np.count_nonzero(res[1][0]["volume"] >= 0) > 500  # the camera really sees the volume

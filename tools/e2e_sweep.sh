@@ -1,5 +1,7 @@
 #!/bin/bash
-# end-to-end (vp_render, host buffers) with different numbers of row bands and lane priorities (GPU box)
-run() { python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1  device', round(d['ms_per_step'],3), 'ms   e2e', round(d['e2e']['ms_per_step'],3), 'ms', round(d['e2e']['value']), 'Mrays/s')"; }
-for b in 1 4; do VP_BANDS=$b run "bands=$b prio=0"; done
-for b in 2 3 4 6 8; do VP_LANE_PRIO=1 VP_BANDS=$b run "bands=$b prio=1"; done
+# end-to-end (vp_render, host buffers): staggered band starts (GPU box)
+run() { python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1  device', round(d['ms_per_step'],3), 'ms', round(d['value']), 'Mrays/s   e2e', round(d['e2e']['ms_per_step'],3), 'ms', round(d['e2e']['value']), 'Mrays/s')"; }
+VP_BAND_STAGGER=-1 run "bands=4 no stagger"
+for g in 0 1 2 3 5; do VP_BAND_STAGGER=$g run "bands=4 stagger=$g"; done
+for g in 0 1 2; do VP_BANDS=8 VP_BAND_STAGGER=$g run "bands=8 stagger=$g"; done
+VP_BANDS=6 VP_BAND_STAGGER=1 run "bands=6 stagger=1"
