@@ -143,6 +143,7 @@ struct vp_ctx {
   int tune_refill = kRefill;  // VP_REFILL
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
   int tune_brickwalk = 1;     // VP_BRICKWALK: 0 = cell walk only (A/B)
+  int wf_grid_shade = 0;      // blocks of the shade stage: what is resident at once (VP_BLOCKS_SHADE per SM)
   int tune_graph = 1;         // VP_GRAPH: 0 = launch every kernel of a pass from the host
   int tune_band_ramp = 0;     // VP_BAND_RAMP: band heights 1 : 2 : ... : n instead of equal
   int tune_band_stagger = 0;  // VP_BAND_STAGGER: band k+1 of a vp_render call starts when band k has shaded this bounce (-1: all at once)
@@ -362,7 +363,7 @@ int enqueue_trace(vp_ctx* c, WfLane& L, WfParams& p, bool timing, bool capturing
     else k_wf_extend<CS, false><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
     if (e1) CU(cudaEventRecord(e1, stream));
     if (it >= 2) CU(cudaStreamWaitEvent(stream, L.ev_shadow[it - 2], 0));  // shade(k) reuses the id queue of shadow(k-2)
-    k_wf_shade<CS><<<wide, kWfBlock, sm, stream>>>(p);
+    k_wf_shade<CS><<<c->wf_grid_shade, kWfBlock, sm, stream>>>(p);  // one resident wave: the stage is a grid-stride loop
     CU(cudaEventRecord(L.ev_shade[it], stream));
     if (it == c->tune_band_stagger || (it == p.max_bounces && p.max_bounces < c->tune_band_stagger))
       CU(cudaEventRecordWithFlags(L.ev_mid, stream, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));  // a node of its own when the pass is a graph
@@ -757,6 +758,9 @@ vp_ctx* vp_create(int device)
   c->wf_blocks_extend = occ * c->sm_count;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shadow<false, true>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
   c->wf_blocks_shadow = occ * c->sm_count;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shade<false>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 6;
+  c->wf_grid_shade = occ * c->sm_count;
+  if (const char* e = getenv("VP_BLOCKS_SHADE")) c->wf_grid_shade = atoi(e) * c->sm_count;
   // tuning knobs for experiments (defaults are the shipped values)
   cudaFuncSetAttribute(k_wf_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);

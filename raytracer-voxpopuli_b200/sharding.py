@@ -44,7 +44,13 @@ class FrameGather:
         v = frame.view((self.ntile, ROW_TILE) + self.tail)
         self.pack[: self.counts[self.rank]] = v[self.rank::self.world]
         dist.all_gather_into_tensor(self.out.view(-1), self.pack.view(-1))
+        # de-interleave: tile t of rank r is frame tile t * world + r.  The tile counts of the ranks differ by at most
+        # one, so one permuted copy places every rank's first `full` tiles (this rank's own among them: same bytes) and
+        # the ranks that own one more tile add it.
+        full = min(self.counts)
+        if full:
+            v[: full * self.world].view((full, self.world, ROW_TILE) + self.tail).copy_(self.out[:, :full].transpose(0, 1))
         for r in range(self.world):
-            if r != self.rank:
-                v[r::self.world] = self.out[r, : self.counts[r]]
+            if self.counts[r] > full and r != self.rank:
+                v[full * self.world + r] = self.out[r, full]
         return frame

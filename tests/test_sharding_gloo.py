@@ -117,3 +117,27 @@ def test_tile_ownership_partitions_the_frame():
             assert owned == list(range((H + sharding.ROW_TILE - 1) // sharding.ROW_TILE))
             sizes = [len(sharding.tiles_of_rank(H, world, r)) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_frame_gather_deinterleave_ragged(monkeypatch):
+    """FrameGather's de-interleave (one permuted copy + the ranks that own one tile more) for tile counts that do not
+    divide by the number of ranks; the collective is replaced by a function that fills the gathered buffer."""
+    import torch
+    import torch.distributed as dist
+    sharding = importlib.import_module("raytracer-voxpopuli_b200.sharding")
+    for world, ntile in ((3, 7), (8, 135), (2, 4), (4, 5), (8, 3)):
+        H, W = ntile * sharding.ROW_TILE, 5
+        truth = torch.arange(H * W, dtype=torch.int32).view(H, W)
+        tv = truth.view(ntile, sharding.ROW_TILE, W)
+        for rank in range(world):
+            frame = torch.zeros((H, W), dtype=torch.int32)
+            frame.view(ntile, sharding.ROW_TILE, W)[rank::world] = tv[rank::world]
+            g = sharding.FrameGather(frame, world, rank)
+
+            def fake(out, inp, g=g, world=world):
+                o = out.view(world, g.max_tiles, sharding.ROW_TILE, W)
+                for r in range(world):
+                    o[r].zero_()
+                    o[r, : g.counts[r]] = tv[r::world]
+            monkeypatch.setattr(dist, "all_gather_into_tensor", fake)
+            assert torch.equal(g(frame), truth), (world, ntile, rank)
