@@ -536,3 +536,21 @@ def test_grid_sizes_off_the_brick_lattice(product, oracle, n):
     assert_hits_equal(res[0][2], res[1][2], f"n={n} nearest")
     assert np.array_equal(res[0][3], res[1][3])
     assert np.count_nonzero(res[1][0]["volume"] >= 0) > 500  # the camera really sees the volume
+
+
+@pytest.mark.parametrize("env", [{"VP_GRAPH": "0"}, {"VP_BRICKWALK": "0"}, {"VP_GRAPH": "0", "VP_BRICKWALK": "0", "VP_BANDS": "1"}])
+def test_fallback_paths(product, oracle, monkeypatch, env):
+    """The A/B switches keep working: kernels launched from the host instead of the per-lane CUDA graph, the cell walk
+    instead of the brick walk, no row bands.  Multi-volume config with area lights, several samples (lanes rotate)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sc, cam, fpd = small_config(4, 128, 72)
+    res = []
+    for lib in (oracle, product):
+        with vp.Session(lib) as s:
+            s.set_scene(sc)
+            res.append((s.trace_primary(cam, params(fpd)), s.render(cam, params(fpd, spp=5))))
+    assert_hits_equal(res[0][0], res[1][0], str(env))
+    assert np.count_nonzero(bits(res[0][1][0]) != bits(res[1][1][0])) == 0
+    assert np.count_nonzero(res[0][1][1] != res[1][1][1]) == 0
+    assert res[0][1][2].rays == res[1][1][2].rays
