@@ -144,7 +144,10 @@ struct vp_ctx {
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
   int tune_brickwalk = 1;     // VP_BRICKWALK: 0 = cell walk only (A/B)
   int wf_grid_shade = 0;      // blocks of the shade stage: what is resident at once (VP_BLOCKS_SHADE per SM)
-  int tune_graph = 1;         // VP_GRAPH: 0 = launch every kernel of a pass from the host
+  int tune_graph = 1;         // VP_GRAPH: 0 = launch every kernel of a pass from the host, 2 = graph + prepare stage for lone passes too
+  int tune_prepare = 1;       // VP_PREPARE: 0 = the extend stage sets up every walk itself
+  bool graph_now = false;     // this call's passes go through the lane graphs
+  bool in_bands = false;      // vp_render is launching its row bands
   int tune_band_ramp = 0;     // VP_BAND_RAMP: band heights 1 : 2 : ... : n instead of equal
   int tune_band_stagger = 0;  // VP_BAND_STAGGER: band k+1 of a vp_render call starts when band k has shaded this bounce (-1: all at once)
   int band_last_lane = -1;    // lane the most recent pass went to
@@ -354,7 +357,7 @@ int enqueue_trace(vp_ctx* c, WfLane& L, WfParams& p, bool timing, bool capturing
       }
       e0 = c->tev[c->tev_used++]; e1 = c->tev[c->tev_used++];
     }
-    if (!CS && c->tune_brickwalk) {
+    if (!CS && p.prepared) {
       k_wf_prepare<<<wide, kWfBlock, 0, stream>>>(p);  // outside the extend stage's event pair: bench.py's roofline times k_wf_extend alone
       c->host_launches++;
     }
@@ -389,7 +392,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
 {
   PassGraph& G = L.pg;
   const size_t sm = smem_bytes(c);
-  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk && G.smem == sm && G.counts == (const void*)p.st.counts);
+  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared && G.smem == sm && G.counts == (const void*)p.st.counts);
   if (fresh) {
     drop_graph(G);
     const unsigned long long before = c->host_launches;
@@ -412,7 +415,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
              : (x.kp.func == (void*)k_wf_shadow<false, true> || x.kp.func == (void*)k_wf_shadow<false, false>) ? 2 : 0;
       G.nodes.push_back(x);
     }
-    G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk; G.smem = sm; G.counts = (const void*)p.st.counts;
+    G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared; G.smem = sm; G.counts = (const void*)p.st.counts;
   } else {
     for (PassGraph::Node& x : G.nodes) {
       WfParams q = p;
@@ -437,7 +440,7 @@ int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
   const size_t sm = smem_bytes(c);
   const int wide = c->sm_count * 8;
   bool traced = false;
-  if (!CS && c->tune_graph && !c->time_stages_now) {
+  if (!CS && c->tune_graph && c->graph_now && !c->time_stages_now) {
     const int rc = graph_trace(c, L, p);
     if (rc < 0) return rc;
     if (rc == 1) c->tune_graph = 0;  // capture is not possible here: launch from the host from now on
@@ -501,6 +504,8 @@ int mark_direct(vp_ctx* c, cudaStream_t stream)
   return 0;
 }
 
+static inline int cs_flag_for_prepare(const VpFrameParams* fp) { return (fp->flags & VP_FLAG_COUNT_STEPS) != 0; }
+
 int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream, bool overlap,
                      const RpArgs* rp = nullptr)
 {
@@ -524,6 +529,13 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   p.hist_in = rp ? rp->hist_in : nullptr; p.hist_out = rp ? rp->hist_out : nullptr;
   if (rp) p.prev = rp->prev; else memset(&p.prev, 0, sizeof(p.prev));
   c->time_stages_now = (fp->flags & VP_FLAG_TIME_STAGES) != 0;
+  // Graph replay and the separate prepare stage pay off when passes overlap (deferred frames, several samples per call,
+  // the row bands of vp_render): the host runs ahead and the extra kernel boundaries hide under other passes.  A pass the
+  // caller waits for (a reprojection frame, a lone Update) is latency-bound: it is launched directly and its extend
+  // stage sets up the walks itself (reprojection cfg 2: 5.94 against 6.32 ms per frame).
+  const bool piped = overlap || fp->spp > 1 || c->tune_graph >= 2;
+  c->graph_now = c->tune_graph != 0 && piped;
+  p.prepared = c->tune_prepare && piped && c->tune_brickwalk && !cs_flag_for_prepare(fp);
   // Persistent grids follow the number of paths this call can have: a warp that gets only ~1 ray per lane never refills
   // and ends at the SIMD efficiency of its longest ray, so small shards run fewer, longer-lived warps (>= 3 blocks per SM
   // to keep latency hidden; measured on 1/8 frame shares, profiles/README.md).
@@ -773,6 +785,7 @@ vp_ctx* vp_create(int device)
   if (const char* e = getenv("VP_REFILL")) c->tune_refill = atoi(e);
   if (const char* e = getenv("VP_BRICKWALK")) c->tune_brickwalk = atoi(e);
   if (const char* e = getenv("VP_GRAPH")) c->tune_graph = atoi(e);
+  if (const char* e = getenv("VP_PREPARE")) c->tune_prepare = atoi(e);
   if (const char* e = getenv("VP_BAND_RAMP")) c->tune_band_ramp = atoi(e);
   if (const char* e = getenv("VP_BAND_STAGGER")) c->tune_band_stagger = atoi(e);
   if (const char* e = getenv("VP_BANDS")) c->tune_bands = atoi(e) < 1 ? 1 : atoi(e);
@@ -1092,6 +1105,7 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
       if (edge[k] < edge[k - 1]) edge[k] = edge[k - 1];
     }
     cudaEvent_t done[kCallRing];
+    c->in_bands = true;
     for (int k = 0; k < nb; k++) {
       if (edge[k + 1] <= edge[k]) { done[k] = nullptr; continue; }
       VpFrameParams b = *fp;
@@ -1099,9 +1113,10 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
       done[k] = c->ev_call[c->ncalls % kCallRing];  // the completion event launch_render records for this call
       const int rc = launch_render(c, cam, &b, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, nullptr, true);
       c->band_wait_lane = (c->tune_band_stagger >= 0 && b.spp == 1) ? c->band_last_lane : -1;  // the next band starts behind this one
-      if (rc) { c->band_wait_lane = -1; return rc; }
+      if (rc) { c->band_wait_lane = -1; c->in_bands = false; return rc; }
     }
     c->band_wait_lane = -1;
+    c->in_bands = false;
     // copies after all launches: a copy into pageable memory blocks the host until its band is done
     for (int k = 0; k < nb; k++) {
       if (!done[k]) continue;

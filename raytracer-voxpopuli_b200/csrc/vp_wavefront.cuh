@@ -75,6 +75,7 @@ struct WfParams {
   int refill;            // lanes still walking below which idle lanes refill from the queue
   int bulk;              // with at most this many lanes walking, lanes in empty 8^3/16^3 blocks bulk-advance
   int persistent;        // 1: generate feeds the persistent kernel's extend queue
+  int prepared;          // 1: k_wf_prepare has set up the first walk of every ray of the bounce
   int write_rgb8;
   float4* accum;
   uint32_t* rgb8;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
   uint32_t* cnt = p.st.counts + 4 * p.iter;
   const uint32_t n = cnt[0];
   const int nvol = p.sc.nvol;
-  const bool need_world = nvol > 1 || p.sc.nsph + p.sc.ntri > 0;  // the world-space ray is only needed past the first volume
+  const bool need_world = nvol > 1 || p.sc.nsph + p.sc.ntri > 0 || !p.prepared;  // the world-space ray is only needed past the first volume
   bool has_ray = false, in_dda = false, exhausted = false;
   uint32_t path = 0;
   f3 O = v3s(0), D = v3s(0);
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
           tbest = 1e34f; pbest = 0; volbest = -2;
           vi = 0; has_ray = true; in_dda = false;
           nrays++;
-          if (BWK) {
+          if (BWK && p.prepared) {
             // the walk through the first volume the ray enters was set up by k_wf_prepare
             const float4 w0 = __ldcs(p.st.ps[0] + qi), w1 = __ldcs(p.st.ps[1] + qi), w2 = __ldcs(p.st.ps[2] + qi);
             const uint32_t fl = __float_as_uint(w2.w);
@@ -293,11 +294,8 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
               occ_reset(o); region = region_of(stg, v); fine = v.fine;
               in_dda = true;
             }
-            if (need_world) {
-              const float4 a = p.st.r0[path], b = p.st.r1[path];
-              O = v3(a.x, a.y, a.z); D = v3(b.x, b.y, b.z);
-            }
-          } else {
+          }
+          if (!(BWK && p.prepared) || need_world) {
             const float4 a = p.st.r0[path], b = p.st.r1[path];
             O = v3(a.x, a.y, a.z); D = v3(b.x, b.y, b.z);
           }
