@@ -182,8 +182,8 @@ def main():
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     # frames in flight: a step is enqueued with VP_FLAG_DEFER, so its latency-bound tail overlaps the next step's wide
     # first bounces; with several ranks the finished image of step k is gathered on a second stream meanwhile, hence
-    # one RGB8 image per frame in flight
-    NBUF = 3 if world > 1 else 1
+    # one RGB8 image per frame in flight, and two more so that a frame never waits for the gather that last read its image
+    NBUF = int(os.environ.get("VP_BENCH_IMAGES", "6")) if world > 1 else 1
     rgb8s = [torch.zeros((H, W), dtype=torch.int32, device=dev) for _ in range(NBUF)]
     rgb8 = rgb8s[0]
     stream = torch.cuda.current_stream(dev)
