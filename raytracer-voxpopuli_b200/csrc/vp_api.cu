@@ -394,6 +394,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
   const size_t sm = smem_bytes(c);
   const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared && G.smem == sm && G.counts == (const void*)p.st.counts);
   if (fresh) {
+    if (G.exec) CU(cudaStreamSynchronize(L.main));  // the old graph may still be running on this lane
     drop_graph(G);
     const unsigned long long before = c->host_launches;
     if (cudaStreamBeginCapture(L.main, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return 1; }

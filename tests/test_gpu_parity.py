@@ -554,3 +554,40 @@ def test_fallback_paths(product, oracle, monkeypatch, env):
     assert np.count_nonzero(bits(res[0][1][0]) != bits(res[1][1][0])) == 0
     assert np.count_nonzero(res[0][1][1] != res[1][1][1]) == 0
     assert res[0][1][2].rays == res[1][1][2].rays
+
+
+def test_graph_recapture(product, oracle):
+    """Deferred frames go through a per-lane CUDA graph whose topology depends on the bounce count and whose nodes point
+    into the lane's buffers: alternate bounce counts, then a larger frame (the lanes reallocate), then a scene with
+    another volume count, all with frames in flight, and compare every accumulator with the oracle."""
+    import torch
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream(dev)
+
+    def run_gpu(s, cam, fpd, plan, W, H):
+        acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+        rgb = torch.zeros((H, W), dtype=torch.int32, device=dev)
+        cc = cam.to_c()
+        for i, mb in enumerate(plan):
+            fp = params(fpd, spp=1, frame_index=i, max_bounces=mb, flags=abi.VP_FLAG_DEFER)
+            product.check(product.c_render_device(s.ctx, C.byref(cc), C.byref(fp), acc.data_ptr(), rgb.data_ptr(), stream.cuda_stream, None),
+                          "render_device")
+        product.check(product.c_render_fence(s.ctx, stream.cuda_stream, 0), "render_fence")
+        return acc.cpu().numpy()
+
+    def run_cpu(sc, cam, fpd, plan, W, H):
+        acc = np.zeros((H, W, 4), np.float32)
+        with vp.Session(oracle) as s:
+            s.set_scene(sc)
+            for i, mb in enumerate(plan):
+                acc, _, _ = s.render(cam, params(fpd, spp=1, frame_index=i, max_bounces=mb), accum=acc)
+        return acc
+
+    plan = [3, 3, 5, 3, 5, 5, 3, 0, 5, 3, 3]
+    with vp.Session(product) as s:
+        for idx, (W, H) in ((2, (96, 54)), (2, (160, 90)), (4, (128, 72)), (2, (64, 36))):
+            sc, cam, fpd = small_config(idx, W, H)
+            s.set_scene(sc)
+            got = run_gpu(s, cam, fpd, plan, W, H)
+            want = run_cpu(sc, cam, fpd, plan, W, H)
+            assert np.count_nonzero(bits(got) != bits(want)) == 0, f"cfg {idx} {W}x{H}"
