@@ -536,7 +536,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   // stage sets up the walks itself (reprojection cfg 2: 5.94 against 6.32 ms per frame).
   const bool piped = overlap || fp->spp > 1 || c->tune_graph >= 2;
   c->graph_now = c->tune_graph != 0 && piped;
-  p.prepared = c->tune_prepare && piped && c->tune_brickwalk && !cs_flag_for_prepare(fp);
+  p.prepared = c->tune_prepare && piped && c->tune_brickwalk && !cs_flag_for_prepare(fp) && c->sc.nvol <= 60;
   // Persistent grids follow the number of paths this call can have: a warp that gets only ~1 ray per lane never refills
   // and ends at the SIMD efficiency of its longest ray, so small shards run fewer, longer-lived warps (>= 3 blocks per SM
   // to keep latency hidden; measured on 1/8 frame shares, profiles/README.md).

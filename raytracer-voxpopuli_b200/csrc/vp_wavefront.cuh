@@ -33,6 +33,7 @@ constexpr int kBwUnroll = VP_BW_UNROLL;        // brick-walk steps between two v
 constexpr int kWfMinBlocks = VP_WF_MINBLOCKS;  // resident blocks per SM the traversal kernels are compiled for (64 registers at 8)
 constexpr int kRefill = 20;           // refill when fewer lanes than this are still stepping
 constexpr int kBulkLanes = 12;        // with at most this many lanes walking, lanes in empty 8^3/16^3 blocks bulk-advance
+constexpr int kMaskVolumes = 23;      // scenes up to this size carry the bounding-sphere candidates of a ray in its prepared record
 constexpr int kMaxAreaSamples = 8;    // numCheckShadowsAreaLight supported by the wavefront path (reference default 3)
 
 // Per-path state, structure of arrays over `cap` paths.
@@ -203,8 +204,10 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant_
 // (renderer.cpp:958-975: world -> object ray, Scene::Setup3DDDA) for the first volume each ray of the bounce enters, one
 // lane per ray at full width - inside the extend stage the same ~240 instructions run with a quarter of the lanes, because
 // only the lanes that refill execute them.  The record is indexed by queue position, so writes here and reads by the
-// refilling lanes are coalesced.  flags: bits 0..15 = index + 1 of the volume entered (0: the ray enters none),
-// bit 16 = ray excluded from brick mode, bits 17..19 = mirrored axes.
+// refilling lanes are coalesced.  flags: bits 0..5 = index + 1 of the volume entered (0: the ray enters none),
+// bit 6 = ray excluded from brick mode, bits 7..9 = mirrored axes, bits 10..31 = which of the next 22 volumes pass the
+// bounding-sphere pre-test (scenes of up to kMaskVolumes volumes: the extend stage then jumps from candidate to
+// candidate instead of repeating the test on a few lanes).
 __global__ void __launch_bounds__(kWfBlock) k_wf_prepare(const __grid_constant__ WfParams p)
 {
   const uint32_t* queue = p.st.q[p.iter & 1];
@@ -223,7 +226,10 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_prepare(const __grid_constant__
       const ORay r = make_oray(xform_pos_sse(O, v.iM), xform_vec_sse(D, v.iM));
       if (setup_dda(v, r, s)) {
         bw_init(v, s, bw);
-        flags = (uint32_t)(vi + 1) | (bw.plain << 16) | ((s.Sx != 1u ? 1u : 0u) << 17) | ((s.Sy != 2u ? 1u : 0u) << 18) | ((s.Sz != 4u ? 1u : 0u) << 19);
+        flags = (uint32_t)(vi + 1) | (bw.plain << 6) | ((s.Sx != 1u ? 1u : 0u) << 7) | ((s.Sy != 2u ? 1u : 0u) << 8) | ((s.Sz != 4u ? 1u : 0u) << 9);
+        if (nvol > 1 && nvol <= kMaskVolumes)
+          for (int vj = vi + 1; vj < nvol; vj++)
+            if (volume_may_hit(p.sc.vol[vj], O, D)) flags |= 1u << (10 + vj - vi - 1);
         break;
       }
     }
@@ -250,6 +256,8 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
   const uint32_t n = cnt[0];
   const int nvol = p.sc.nvol;
   const bool need_world = nvol > 1 || p.sc.nsph + p.sc.ntri > 0 || !p.prepared;  // the world-space ray is only needed past the first volume
+  const bool use_mask = BWK && p.prepared && nvol > 1 && nvol <= kMaskVolumes;
+  uint32_t cand = 0;
   bool has_ray = false, in_dda = false, exhausted = false;
   uint32_t path = 0;
   f3 O = v3s(0), D = v3s(0);
@@ -282,15 +290,16 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
             // the walk through the first volume the ray enters was set up by k_wf_prepare
             const float4 w0 = __ldcs(p.st.ps[0] + qi), w1 = __ldcs(p.st.ps[1] + qi), w2 = __ldcs(p.st.ps[2] + qi);
             const uint32_t fl = __float_as_uint(w2.w);
-            vi = (fl & 0xFFFFu) ? (int)(fl & 0xFFFFu) : nvol;
-            if (fl & 0xFFFFu) {
+            vi = (fl & 63u) ? (int)(fl & 63u) : nvol;
+            cand = fl >> 10;
+            if (fl & 63u) {
               const DVolume& v = svol[vi - 1];
               s.tx = w0.x; s.ty = w0.y; s.tz = w0.z; s.t = w0.w;
               s.dx = w1.x; s.dy = w1.y; s.dz = w1.z; s.P = __float_as_uint(w1.w);
               bw.ex = w2.x; bw.ey = w2.y; bw.ez = w2.z;
               bw.F = axis_field(v.jr, 0);
-              bw.flip = ((fl >> 17) & 1u ? bw.F : 0u) | ((fl >> 18) & 1u ? bw.F << 1 : 0u) | ((fl >> 19) & 1u ? bw.F << 2 : 0u);
-              bw.plain = (fl >> 16) & 1u; bw.brick = 0u; bw.ac = 0u; bw.tc = __uint_as_float(0xFF800000u);
+              bw.flip = ((fl >> 7) & 1u ? bw.F : 0u) | ((fl >> 8) & 1u ? bw.F << 1 : 0u) | ((fl >> 9) & 1u ? bw.F << 2 : 0u);
+              bw.plain = (fl >> 6) & 1u; bw.brick = 0u; bw.ac = 0u; bw.tc = __uint_as_float(0xFF800000u);
               occ_reset(o); region = region_of(stg, v); fine = v.fine;
               in_dda = true;
             }
@@ -306,8 +315,14 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
     // 2. lanes between volumes: set up the next volume the ray enters, or finish the ray
     if (has_ray && !in_dda) {
       while (vi < nvol) {
+        if (use_mask) {
+          // bit 0 of cand <=> volume vi passes the bounding-sphere pre-test (k_wf_prepare): jump to the next candidate
+          if (cand == 0u) { vi = nvol; break; }
+          const int skip = __ffs(cand) - 1;
+          vi += skip;
+          cand = (cand >> skip) >> 1;
+        } else if (nvol > 1 && !volume_may_hit(svol[vi], O, D)) { vi++; continue; }
         const DVolume& v = svol[vi];
-        if (nvol > 1 && !volume_may_hit(v, O, D)) { vi++; continue; }
         const ORay r = make_oray(xform_pos_sse(O, v.iM), xform_vec_sse(D, v.iM));
         vi++;
         if (setup_dda(v, r, s)) {
