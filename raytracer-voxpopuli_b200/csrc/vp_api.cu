@@ -304,6 +304,7 @@ int wf_reserve(WfLane& L, uint32_t cap, int levels, int samples, size_t* bytes_o
   const size_t o_pq = take(3 * pq_len * 4), o_pctl = take(kCtlWords * 4);
   const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_qs = take(2 * cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
   const size_t o_ps = take(3 * cap * f4);  // prepared walks of the bounce being extended, by queue position
+  const size_t o_sm = take((size_t)samples * cap * 4);  // bounding-sphere candidates of the bounce's shadow rays
   if (bytes_only) { *bytes_only = off; return 0; }  // what growing this lane would take
   CU(cudaDeviceSynchronize());
   CU(L.d_wf.reserve(off));
@@ -318,6 +319,7 @@ int wf_reserve(WfLane& L, uint32_t cap, int levels, int samples, size_t* bytes_o
   for (int k = 0; k < 3; k++) w.pq[k] = (uint32_t*)(b + o_pq) + (size_t)k * pq_len;
   w.pctl = (uint32_t*)(b + o_pctl);
   for (int k = 0; k < 3; k++) w.ps[k] = (float4*)(b + o_ps) + (size_t)k * cap;
+  w.smask = (uint32_t*)(b + o_sm);
   CU(cudaMemset(b + o_pq, 0xFF, 3 * pq_len * 4));  // all slots empty
   CU(cudaMemset(w.pctl, 0, kCtlWords * 4));
   L.cap = cap; L.levels = levels; L.samples = samples;
@@ -371,6 +373,10 @@ int enqueue_trace(vp_ctx* c, WfLane& L, WfParams& p, bool timing, bool capturing
     if (it == c->tune_band_stagger || (it == p.max_bounces && p.max_bounces < c->tune_band_stagger))
       CU(cudaEventRecordWithFlags(L.ev_mid, stream, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));  // a node of its own when the pass is a graph
     CU(cudaStreamWaitEvent(L.side, L.ev_shade[it], 0));
+    if (!CS && p.prepared && p.sc.nvol > 1 && p.sc.nvol <= 32) {
+      k_wf_shadow_mask<<<wide, kWfBlock, 0, L.side>>>(p);
+      c->host_launches++;
+    }
     if (!CS && c->tune_brickwalk) k_wf_shadow<false, true><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
     else k_wf_shadow<CS, false><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
     CU(cudaEventRecord(L.ev_shadow[it], L.side));

@@ -53,6 +53,7 @@ struct WfState {
   float4* sq0;      // [level][path]: origin.xyz, w = bits nsamp(8) | level(8) << 8 | area(1) << 16 | mat(8) << 24
   float4* sqd;      // [level][sample][path]: dir.xyz, w = dist
   float4* sql;      // [level][sample][path]: li.xyz (single lights: final contribution), w = valid
+  uint32_t* smask;      // [sample][path]: volumes that pass the bounding-sphere pre-test for the shadow ray (k_wf_shadow_mask)
   float4* ps[3];        // prepared walks [queue position]: 0 = tmax.xyz, t; 1 = tdelta.xyz, P' bits; 2 = E.xyz, flags (k_wf_prepare)
   uint32_t* q[2];       // active-path queues (ping-pong)
   uint32_t* qs[2];      // shadow-request queues (bounce parity)
@@ -674,6 +675,35 @@ __global__ void __launch_bounds__(kWfBlock, 6) k_wf_shade(const __grid_constant_
   if (CS) wf_add_counter(p.counters + 3, cn.steps);
 }
 
+// ---- K4a: bounding-sphere pre-test of every shadow ray of the bounce against every volume, one lane per request at full
+// width (multi-volume scenes of up to 32 volumes): the shadow stage then jumps from candidate to candidate instead of
+// repeating the test on the few lanes that are between volumes.
+__global__ void __launch_bounds__(kWfBlock) k_wf_shadow_mask(const __grid_constant__ WfParams p)
+{
+  const uint32_t n = p.st.counts[4 * p.iter + 1];
+  const uint32_t cap = p.st.cap;
+  const int nvol = p.sc.nvol;
+  const uint32_t* queue = p.st.qs[p.iter & 1];
+  const float4* const sq0 = p.st.sq0 + (size_t)p.iter * cap;
+  const float4* const sqd = p.st.sqd + (size_t)p.iter * p.st.nsamp * cap;
+  const float4* const sql = p.st.sql + (size_t)p.iter * p.st.nsamp * cap;
+  for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
+    const uint32_t path = queue[qi];
+    const float4 q0 = sq0[path];
+    const f3 org = v3(q0.x, q0.y, q0.z);
+    const int nsamp = (int)(__float_as_uint(q0.w) & 255u);
+    for (int sample = 0; sample < nsamp; sample++) {
+      if (sql[(size_t)sample * cap + path].w == 0.0f) continue;
+      const float4 d4 = sqd[(size_t)sample * cap + path];
+      const f3 D = normalize3(v3(d4.x, d4.y, d4.z));  // as the shadow stage builds the ray
+      uint32_t m = 0;
+      for (int vi = 0; vi < nvol; vi++)
+        if (volume_may_hit(p.sc.vol[vi], org, D)) m |= 1u << vi;
+      p.st.smask[(size_t)sample * cap + path] = m;
+    }
+  }
+}
+
 // ---- K4: shadow = Renderer::IsOccluded per light sample (renderer.cpp:209-243), lane refill -------
 template <bool CS, bool BWK>
 __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __grid_constant__ WfParams p)
@@ -693,6 +723,8 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __gr
   const float4* const sq0 = p.st.sq0 + (size_t)p.iter * cap;  // staged pipeline: the request level is the bounce index
   const float4* const sqd = p.st.sqd + (size_t)p.iter * p.st.nsamp * cap;
   const float4* const sql = p.st.sql + (size_t)p.iter * p.st.nsamp * cap;
+  const bool use_mask = BWK && p.prepared && nvol > 1 && nvol <= 32;  // k_wf_shadow_mask ran for this bounce
+  uint32_t cand = 0;
   bool has_req = false, has_ray = false, in_dda = false, exhausted = false;
   uint32_t path = 0, bits = 0;
   int nsamp = 0, sample = 0, vi = 0;
@@ -733,8 +765,12 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __gr
         if (has_ray) {
           bool entered = false;
           while (vi < nvol) {
+            if (use_mask) {
+              const uint32_t rest = cand >> vi;  // bit v of cand <=> volume v passes the bounding-sphere pre-test
+              if (rest == 0u) { vi = nvol; break; }
+              vi += __ffs(rest) - 1;
+            } else if (nvol > 1 && !volume_may_hit(svol[vi], org, D)) { vi++; continue; }
             const DVolume& v = svol[vi];
-            if (nvol > 1 && !volume_may_hit(v, org, D)) { vi++; continue; }
             const ORay r = make_oray(xform_scalar(org, 1.0f, v.iM), xform_scalar(D, 0.0f, v.iM));
             vi++;
             if (setup_dda(v, r, s)) {
@@ -760,6 +796,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __gr
             D = normalize3(v3(d4.x, d4.y, d4.z));  // normalising Ray ctor of the shadow ray
             tmaxray = d4.w;
             li = v3(l4.x, l4.y, l4.z);
+            if (use_mask) cand = p.st.smask[(size_t)sample * cap + path];
             vi = 0; has_ray = true; found = true;
             nrays++;
             break;
