@@ -743,6 +743,7 @@ vp_ctx* vp_create(int device)
     delete c;
     return nullptr;
   }
+  k_fwd_table<<<1, 512, 0, c->stream>>>();  // forward boxes of the brick walk (vp_device.cuh); the same values for every context
   // default tables: 256 white diffuse materials (reference renderer.cpp:434-441), zero directional light
   std::vector<VpMaterial> mats(256);
   for (auto& m : mats) { m.albedo[0] = m.albedo[1] = m.albedo[2] = 1.0f; m.roughness = 1.0f; m.emissive = 0.0f; m.ior = 1.5f; }

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
   const unsigned long long* fine = nullptr;
   DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
   Occ o; occ_reset(o);
-  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.F = bw.flip = bw.ac = bw.brick = bw.plain = 0;
+  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.F = bw.flip = bw.ac = bw.plain = 0;
   unsigned long long steps = 0, steps_er = 0, steps_eb = 0;
   unsigned int nrays = 0;
   for (;;) {
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
               bw.ex = w2.x; bw.ey = w2.y; bw.ez = w2.z;
               bw.F = axis_field(v.jr, 0);
               bw.flip = ((fl >> 7) & 1u ? bw.F : 0u) | ((fl >> 8) & 1u ? bw.F << 1 : 0u) | ((fl >> 9) & 1u ? bw.F << 2 : 0u);
-              bw.plain = (fl >> 6) & 1u; bw.brick = 0u; bw.ac = 0u; bw.tc = __uint_as_float(0xFF800000u);
+              bw.plain = (fl >> 6) & 1u; bw.ac = 0u; bw.tc = __uint_as_float(0xFF800000u);
               occ_reset(o); region = region_of(stg, v); fine = v.fine;
               in_dda = true;
             }
@@ -360,10 +360,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __gr
         for (int u = 0; u < kBwUnroll; u++) {
           if (s.t < tbest) {
             const uint32_t Pr = s.P ^ bw.flip;  // the walk is mirrored: real cell
-            if ((Pr ^ o.key) >> 6) {
-              occ_fetch(region, fine, o, Pr);
-              bw.brick = (o.m == 0ull ? 1u : 0u) & ~bw.plain;
-            }
+            if ((Pr ^ o.key) >> 6) occ_fetch(region, fine, o, Pr);
             const float t0 = s.t;
             if (uw_step(s, bw, o.m, Pr, __uint_as_float(kHitTag))) tbest = t0;  // NaN tag: stops the walk, recovered below
           }
@@ -734,7 +731,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __gr
   const unsigned long long* fine = nullptr;
   DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
   Occ o; occ_reset(o);
-  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.F = bw.flip = bw.ac = bw.brick = bw.plain = 0;
+  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.F = bw.flip = bw.ac = bw.plain = 0;
   unsigned long long steps = 0;
   unsigned int nrays = 0;
   for (;;) {
@@ -829,10 +826,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __gr
         for (int u = 0; u < kBwUnroll; u++) {
           if (s.t < tmaxray) {
             const uint32_t Pr = s.P ^ bw.flip;
-            if ((Pr ^ o.key) >> 6) {
-              occ_fetch(region, fine, o, Pr);
-              bw.brick = (o.m == 0ull ? 1u : 0u) & ~bw.plain;
-            }
+            if ((Pr ^ o.key) >> 6) occ_fetch(region, fine, o, Pr);
             if (uw_step(s, bw, o.m, Pr, 3.0e38f)) occluded = true;
           }
         }

@@ -168,7 +168,19 @@ static Res brick_walk(const uint8_t* grid, const uint64_t* fine, int n, St s, fl
  * explicit catch-up either: the deferred elements of the other two axes are the smallest heads, so the ordinary cell
  * steps that follow consume them first, in merge order; such a step is SILENT (no cell test, s.t unchanged) while its
  * key lies below (s.t, axis of the last real step). */
-static Res unified_walk(const uint64_t* fine, int n, St s, float tlimit, Stats* st)
+/* occupancy bits of the cells of a brick the ray can still reach from cell c: it never moves against its direction */
+static inline uint64_t forward_box(const int X[3], const int dir[3])
+{
+  uint64_t m = 0;
+  for (int z = 0; z < 4; z++) for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) {
+    const int ok = (dir[0] > 0 ? x >= (X[0] & 3) : x <= (X[0] & 3)) && (dir[1] > 0 ? y >= (X[1] & 3) : y <= (X[1] & 3)) &&
+                   (dir[2] > 0 ? z >= (X[2] & 3) : z <= (X[2] & 3));
+    if (ok) m |= 1ull << (x | (y << 2) | (z << 4));
+  }
+  return m;
+}
+
+static Res unified_walk(const uint64_t* fine, int n, St s, float tlimit, Stats* st, int forward)
 {
   Res r; memset(&r, 0, sizeof r);
   const int nb = n >> 2;
@@ -181,7 +193,8 @@ static Res unified_walk(const uint64_t* fine, int n, St s, float tlimit, Stats* 
       for (int i = 0; i < k; i++) e += s.d[a];
       E[a] = e;
     }
-  int brick = 0, catchup = 0, alast = 0, have = 0;
+  int brick = 0, ac = 0, have = 0;
+  float tc = -INFINITY;  /* key (tc, ac) of the lane's last brick step: cell steps below it are silent */
   int key[3] = {-1, -1, -1};
   uint64_t m = 0;
   while (s.t < tlimit) {
@@ -190,25 +203,26 @@ static Res unified_walk(const uint64_t* fine, int n, St s, float tlimit, Stats* 
       m = brick_mask(fine, nb, s.X); key[0] = bx; key[1] = by; key[2] = bz; have = 1;
       const int was = brick;
       brick = (m == 0) && !plain;
-      if (was && !brick) { catchup = 1; st->to_cell++; }
+      if (was && !brick) st->to_cell++;
       if (!was && brick) st->to_brick++;
     }
+    /* forward box: nothing the ray can still reach in this brick is occupied -> the rest of the brick is empty for it.
+     * X may lag behind the true position on axes with deferred steps: the box from X contains the true one. */
+    if (forward && !brick && !plain && (m & forward_box(s.X, s.dir)) == 0) { brick = 1; st->to_brick++; }
     const float* v = brick ? E : s.F;
     const int a = pick(v);
     const float T = v[a];
-    const int silent = !brick && catchup && (T < s.t || (T == s.t && a > alast));
+    const int silent = !brick && (T < tc || (T == tc && a > ac));
     if (brick) st->brick_steps++; else st->cell_steps++;
-    if (!brick && !silent) {
-      catchup = 0;
-      if (mask_bit(m, s.X)) { r.hit = 1; r.t = s.t; memcpy(r.X, s.X, sizeof r.X); return r; }
-    }
+    if (!brick && !silent && mask_bit(m, s.X)) { r.hit = 1; r.t = s.t; memcpy(r.X, s.X, sizeof r.X); return r; }
+    if (brick) { tc = T; ac = a; }
     const int c = s.X[a] & 3, k = (s.dir[a] < 0) ? c : 3 - c;
     const int cross = brick || k == 0;
     const float f = T + s.d[a];
     const float e = ((f + s.d[a]) + s.d[a]) + s.d[a];
     if (brick) s.X[a] = (s.dir[a] < 0) ? (s.X[a] & ~3) : (s.X[a] | 3);
     s.X[a] += s.dir[a];
-    if (!silent) { s.t = T; alast = a; }
+    if (!silent) s.t = T;
     if ((unsigned)s.X[a] >= (unsigned)n) return r;
     s.F[a] = f;
     if (cross) E[a] = e;
@@ -241,7 +255,7 @@ int64_t bw_compare(const uint8_t* grid, const uint64_t* fine, int n, const float
     if (setup(O + 3 * i, D + 3 * i, n, &s)) {
       st->rays++;
       a = cell_walk(grid, n, s, tlimit[i]);
-      b = mode ? unified_walk(fine, n, s, tlimit[i], st) : brick_walk(grid, fine, n, s, tlimit[i], st);
+      b = mode ? unified_walk(fine, n, s, tlimit[i], st, mode == 2) : brick_walk(grid, fine, n, s, tlimit[i], st);
       st->ref_steps += a.steps;
     }
     uint32_t ta, tb; memcpy(&ta, &a.t, 4); memcpy(&tb, &b.t, 4);

@@ -1,8 +1,8 @@
 """CPU model of the kernels' brick walk (tests/brickwalk_model.c) against the reference's cell walk:
 hit / no hit, hit cell and the bits of t must be identical on every ray - random rays, rays with a
 stopping distance (shadow rays), axis-parallel and grid-aligned rays (inf / NaN tmax), -0 directions and
-exact diagonals (ties between axes).  Both formulations: explicit catch-up (mode 0) and the unified step
-the kernels use (mode 1)."""
+exact diagonals (ties between axes).  Three formulations: explicit catch-up (mode 0), the unified step
+(mode 1) and the unified step with the forward-box rule, which is what the kernels use (mode 2)."""
 import ctypes as C
 import os
 import subprocess
@@ -54,7 +54,7 @@ def _ray_sets(n, count, rng):
 
 
 @pytest.mark.parametrize("name", ["room", "monu2", "player"])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_brick_walk_equals_cell_walk(model, name, mode):
     grid, n, _ = scenes.load_grid(name)
     grid = np.ascontiguousarray(grid.reshape(-1))
