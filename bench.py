@@ -195,13 +195,18 @@ def main():
     def fence(on, back=0):
         lib.check(lib.c_render_fence(sess.ctx, on.cuda_stream, back), "render_fence")
 
+    lone_ms = [0.0]
+
     def step(i, flags=abi.VP_FLAG_DEFER):
         img = rgb8s[i % NBUF]
         if gathered[i % NBUF] is not None:
             stream.wait_event(gathered[i % NBUF])  # the gather that last read this image
         fp = frame_params(fpd, frame_index=i, flags=flags, **shard)
-        lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp), accum.data_ptr(), img.data_ptr(), stream.cuda_stream, None),
-                  "render_device")
+        st1 = abi.VpStats() if (flags & abi.VP_FLAG_TIME_STAGES) else None  # a step that runs alone also reports its own device time
+        lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp), accum.data_ptr(), img.data_ptr(), stream.cuda_stream,
+                                      C.byref(st1) if st1 is not None else None), "render_device")
+        if st1 is not None:
+            lone_ms[0] += st1.device_ms
         if world > 1:
             with torch.cuda.stream(comm):
                 fence(comm)   # this frame resolved
@@ -350,7 +355,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "k_wf_extend", "peak_source": peak_src,
                 "launches_per_step": int(ext_launches_per_frame), "kernel_ms_per_step": ext_ms_frame, "steps_with_stage_events": timed_steps,
-                "kernel_share_of_step": ext_ms_frame / (total_ms / args.steps),
+                "kernel_share_of_step": ext_ms.value / lone_ms[0] if lone_ms[0] > 0 else None,
+                "kernel_share_note": "k_wf_extend time / device time of the same steps (the steps that run alone with stage events); "
+                                     "against the average pipelined step it is kernel_ms_per_step / ms_per_step",
                 "algorithmic_bytes_per_launch": int(ext_bytes_frame / ext_launches_per_frame),
                 "algorithmic_bytes_per_step_all_stages": int(frame_bytes),
                 "dda_steps_per_step": int(inst.dda_steps), "l2_sector_view": l2,
