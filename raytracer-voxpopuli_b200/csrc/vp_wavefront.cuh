@@ -5,11 +5,14 @@
 // and the optional shadow ray all diverge inside one warp.  Here every pixel-sample is a
 // "path" whose state lives in HBM (SoA, 128-bit records) and each stage is its own kernel:
 //
-//   K1 wf_generate : seed, AA jitter, primary ray                     (1 lane per path)
-//   K2 wf_extend   : Renderer::FindNearest over all volumes            (persistent warps, lane refill)
-//   K3 wf_shade    : material switch, RNG, next ray, light sample      (1 lane per active path)
-//   K4 wf_shadow   : Renderer::IsOccluded for the light samples        (persistent warps, lane refill)
-//   K6 wf_resolve  : exact back-to-front colour fold, accumulate, tonemap, RGB8
+//   K1  wf_generate : seed, AA jitter, primary ray                     (1 lane per path)
+//   K2a wf_prepare  : world -> object ray + Setup3DDDA of the first volume each ray enters, bounding-sphere
+//                     candidates of the others                         (1 lane per ray; passes that overlap others)
+//   K2  wf_extend   : Renderer::FindNearest over all volumes            (persistent warps, lane refill, brick walk)
+//   K3  wf_shade    : material switch, RNG, next ray, light sample      (1 lane per active path)
+//   K4a wf_shadow_mask : bounding-sphere candidates of the shadow rays  (1 lane per request; multi-volume scenes)
+//   K4  wf_shadow   : Renderer::IsOccluded for the light samples        (persistent warps, lane refill, brick walk)
+//   K6  wf_resolve  : exact back-to-front colour fold, accumulate, tonemap, RGB8
 //
 // K2/K4 are the hot loops: a warp keeps all lanes inside the DDA stepping loop and, when
 // fewer than kRefill lanes are still walking, idle lanes pull the next ray from the stage
