@@ -136,6 +136,7 @@ struct vp_ctx {
   bool have_volumes = false;
   int blocks_per_sm = 0;
   int wf_blocks_extend = 0, wf_blocks_shadow = 0;  // persistent grids at full load (occupancy x SMs)
+  int wf_blocks_extend_mv = 0, wf_blocks_shadow_mv = 0;  // ... of the kernel variants multi-volume scenes run
   int wf_grid_extend = 0, wf_grid_shadow = 0;      // grids of the current call (smaller for small shards)
   bool wf_blocks_fixed = false;                    // VP_BLOCKS_* given: no per-call sizing
   unsigned long long host_launches = 0;
@@ -364,7 +365,8 @@ int enqueue_trace(vp_ctx* c, WfLane& L, WfParams& p, bool timing, bool capturing
       c->host_launches++;
     }
     if (e0) CU(cudaEventRecord(e0, stream));
-    if (!CS && c->tune_brickwalk) k_wf_extend<false, true><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
+    if (!CS && c->tune_brickwalk && p.sc.nvol > 1) k_wf_extend<false, true, kWfMinBlocksMulti><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
+    else if (!CS && c->tune_brickwalk) k_wf_extend<false, true><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
     else k_wf_extend<CS, false><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
     if (e1) CU(cudaEventRecord(e1, stream));
     if (it >= 2) CU(cudaStreamWaitEvent(stream, L.ev_shadow[it - 2], 0));  // shade(k) reuses the id queue of shadow(k-2)
@@ -377,7 +379,8 @@ int enqueue_trace(vp_ctx* c, WfLane& L, WfParams& p, bool timing, bool capturing
       k_wf_shadow_mask<<<wide, kWfBlock, 0, L.side>>>(p);
       c->host_launches++;
     }
-    if (!CS && c->tune_brickwalk) k_wf_shadow<false, true><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
+    if (!CS && c->tune_brickwalk && p.sc.nvol > 1) k_wf_shadow<false, true, kWfMinBlocksMulti><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
+    else if (!CS && c->tune_brickwalk) k_wf_shadow<false, true><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
     else k_wf_shadow<CS, false><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
     CU(cudaEventRecord(L.ev_shadow[it], L.side));
     c->host_launches += 3;
@@ -418,8 +421,10 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
       PassGraph::Node x; x.node = nd;
       if (cudaGraphKernelNodeGetParams(nd, &x.kp) != cudaSuccess) { cudaGetLastError(); drop_graph(G); return 1; }
       x.iter = reinterpret_cast<const WfParams*>(x.kp.kernelParams[0])->iter;
-      x.kind = (x.kp.func == (void*)k_wf_extend<false, true> || x.kp.func == (void*)k_wf_extend<false, false>) ? 1
-             : (x.kp.func == (void*)k_wf_shadow<false, true> || x.kp.func == (void*)k_wf_shadow<false, false>) ? 2 : 0;
+      x.kind = (x.kp.func == (void*)k_wf_extend<false, true> || x.kp.func == (void*)k_wf_extend<false, false> ||
+                x.kp.func == (void*)k_wf_extend<false, true, kWfMinBlocksMulti>) ? 1
+             : (x.kp.func == (void*)k_wf_shadow<false, true> || x.kp.func == (void*)k_wf_shadow<false, false> ||
+                x.kp.func == (void*)k_wf_shadow<false, true, kWfMinBlocksMulti>) ? 2 : 0;
       G.nodes.push_back(x);
     }
     G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared; G.smem = sm; G.counts = (const void*)p.st.counts;
@@ -554,11 +559,13 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
     const long long per_sm = (long long)kWfBlock * 8 * c->sm_count;
     long long want = (paths + per_sm - 1) / per_sm;
     if (want < 3) want = 3;
-    const long long we = want * c->sm_count < c->wf_blocks_extend ? want * c->sm_count : c->wf_blocks_extend;
-    const long long ws = want * c->sm_count < c->wf_blocks_shadow ? want * c->sm_count : c->wf_blocks_shadow;
+    const int be = c->sc.nvol > 1 ? c->wf_blocks_extend_mv : c->wf_blocks_extend;  // the kernel variant this scene runs
+    const int bs = c->sc.nvol > 1 ? c->wf_blocks_shadow_mv : c->wf_blocks_shadow;
+    const long long we = want * c->sm_count < be ? want * c->sm_count : be;
+    const long long ws = want * c->sm_count < bs ? want * c->sm_count : bs;
     const bool full = c->wf_blocks_fixed || !(overlap || fp->spp > 1);  // a lone pass wants the lowest latency: full grid
-    c->wf_grid_extend = full ? c->wf_blocks_extend : (int)we;
-    c->wf_grid_shadow = full ? c->wf_blocks_shadow : (int)ws;
+    c->wf_grid_extend = full ? be : (int)we;
+    c->wf_grid_shadow = full ? bs : (int)ws;
   }
   const bool staged = rp || !((fp->flags & VP_FLAG_PERSISTENT) != 0 || c->tune_persistent);
   const bool cs = (fp->flags & VP_FLAG_COUNT_STEPS) != 0;
@@ -766,11 +773,13 @@ vp_ctx* vp_create(int device)
   c->blocks_per_sm = occ;
   cudaFuncSetAttribute(k_wf_extend<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_extend<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_extend<false, true, kWfMinBlocksMulti>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_extend<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_shadow<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_shadow<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_shadow<false, true, kWfMinBlocksMulti>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_shadow<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_reproject<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_reproject<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -778,6 +787,10 @@ vp_ctx* vp_create(int device)
   c->wf_blocks_extend = occ * c->sm_count;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shadow<false, true>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
   c->wf_blocks_shadow = occ * c->sm_count;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_extend<false, true, kWfMinBlocksMulti>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
+  c->wf_blocks_extend_mv = occ * c->sm_count;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shadow<false, true, kWfMinBlocksMulti>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
+  c->wf_blocks_shadow_mv = occ * c->sm_count;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shade<false>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 6;
   c->wf_grid_shade = occ * c->sm_count;
   if (const char* e = getenv("VP_BLOCKS_SHADE")) c->wf_grid_shade = atoi(e) * c->sm_count;
@@ -798,8 +811,8 @@ vp_ctx* vp_create(int device)
   if (const char* e = getenv("VP_BAND_STAGGER")) c->tune_band_stagger = atoi(e);
   if (const char* e = getenv("VP_BANDS")) c->tune_bands = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("VP_BAND_MIN_PIXELS")) c->tune_band_min_pixels = atoll(e);
-  if (const char* e = getenv("VP_BLOCKS_EXTEND")) { c->wf_blocks_extend = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
-  if (const char* e = getenv("VP_BLOCKS_SHADOW")) { c->wf_blocks_shadow = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
+  if (const char* e = getenv("VP_BLOCKS_EXTEND")) { c->wf_blocks_extend = c->wf_blocks_extend_mv = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
+  if (const char* e = getenv("VP_BLOCKS_SHADOW")) { c->wf_blocks_shadow = c->wf_blocks_shadow_mv = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
   return c;
 }
 

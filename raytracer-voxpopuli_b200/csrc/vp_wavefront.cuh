@@ -27,13 +27,19 @@ namespace vp {
 
 constexpr int kWfBlock = 128;
 #ifndef VP_WF_MINBLOCKS
-#define VP_WF_MINBLOCKS 8
+#define VP_WF_MINBLOCKS 7
 #endif
 #ifndef VP_BW_UNROLL
 #define VP_BW_UNROLL 2
 #endif
 constexpr int kBwUnroll = VP_BW_UNROLL;        // brick-walk steps between two votes on the number of walking lanes
-constexpr int kWfMinBlocks = VP_WF_MINBLOCKS;  // resident blocks per SM the traversal kernels are compiled for (64 registers at 8)
+#ifndef VP_WF_MINBLOCKS_SHADOW
+#define VP_WF_MINBLOCKS_SHADOW VP_WF_MINBLOCKS
+#endif
+constexpr int kWfMinBlocksShadow = VP_WF_MINBLOCKS_SHADOW;
+constexpr int kWfMinBlocks = VP_WF_MINBLOCKS;  // resident blocks per SM the traversal kernels are compiled for: 72 registers at 7 (no spills in
+                                               // the brick-walk kernels); single-volume scenes: 8 blocks / 64 registers is 2.4 % slower, 6 / 80 slower again
+constexpr int kWfMinBlocksMulti = 8;           // multi-volume scenes (more time between volumes, more latency to hide) prefer the extra warps
 constexpr int kRefill = 20;           // refill when fewer lanes than this are still stepping
 constexpr int kBulkLanes = 12;        // with at most this many lanes walking, lanes in empty 8^3/16^3 blocks bulk-advance
 constexpr int kMaskVolumes = 23;      // scenes up to this size carry the bounding-sphere candidates of a ray in its prepared record
@@ -247,8 +253,8 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_prepare(const __grid_constant__
 // Writes per path: t, the winning volume and the hit cell (as P).  The face normal and the
 // material byte are produced by the shade stage where all 32 lanes are busy, not here where
 // a hit is a single-lane event inside the stepping loop.
-template <bool CS, bool BWK>
-__global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_extend(const __grid_constant__ WfParams p)
+template <bool CS, bool BWK, int MINB = kWfMinBlocks>
+__global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   if (!wf_block_has_work(p.st.counts + 4 * p.iter + 2, p.st.counts[4 * p.iter])) return;
@@ -705,8 +711,8 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow_mask(const __grid_consta
 }
 
 // ---- K4: shadow = Renderer::IsOccluded per light sample (renderer.cpp:209-243), lane refill -------
-template <bool CS, bool BWK>
-__global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_wf_shadow(const __grid_constant__ WfParams p)
+template <bool CS, bool BWK, int MINB = kWfMinBlocksShadow>
+__global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   if (!wf_block_has_work(p.st.counts + 4 * p.iter + 3, p.st.counts[4 * p.iter + 1])) return;
