@@ -39,6 +39,10 @@ constexpr int kBwUnroll = VP_BW_UNROLL;        // brick-walk steps between two v
 constexpr int kWfMinBlocksShadow = VP_WF_MINBLOCKS_SHADOW;
 constexpr int kWfMinBlocks = VP_WF_MINBLOCKS;  // resident blocks per SM the traversal kernels are compiled for: 72 registers at 7 (no spills in
                                                // the brick-walk kernels); single-volume scenes: 8 blocks / 64 registers is 2.4 % slower, 6 / 80 slower again
+#ifndef VP_WF_MINBLOCKS_SHADE
+#define VP_WF_MINBLOCKS_SHADE 6
+#endif
+constexpr int kWfMinBlocksShade = VP_WF_MINBLOCKS_SHADE;
 constexpr int kWfMinBlocksMulti = 8;           // multi-volume scenes (more time between volumes, more latency to hide) prefer the extra warps
 constexpr int kRefill = 20;           // refill when fewer lanes than this are still stepping
 constexpr int kBulkLanes = 12;        // with at most this many lanes walking, lanes in empty 8^3/16^3 blocks bulk-advance
@@ -648,7 +652,7 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
 }
 
 template <bool CS>
-__global__ void __launch_bounds__(kWfBlock, 6) k_wf_shade(const __grid_constant__ WfParams p)
+__global__ void __launch_bounds__(kWfBlock, kWfMinBlocksShade) k_wf_shade(const __grid_constant__ WfParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   if (blockIdx.x * blockDim.x >= p.st.counts[4 * p.iter]) return;  // grid-stride loop below would be empty
