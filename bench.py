@@ -96,18 +96,26 @@ class ClockSampler(threading.Thread):
 
 
 def load_checker():
-    """The reference itself when its build travelled with the repo, else the plain-C port."""
+    """The reference itself when its build travelled with the repo, else the plain-C port.  The CPU path gets every core
+    this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for its workers)."""
     ref = os.path.join(ROOT, "oracle", "_ref", "libvpref.so")
     if os.path.exists(ref):
-        lib = abi.Lib(ref, "vpref_")
-        lib.dll.vpref_threads.restype = C.c_int
-        return lib, "reference", lib.dll.vpref_threads()
-    so = os.path.join(ROOT, "oracle", "libvporacle.so")
-    if not os.path.exists(so):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libvporacle.so"])
-    lib = abi.Lib(so, "vpo_")
-    lib.dll.vpo_threads.restype = C.c_int
-    return lib, "port", lib.dll.vpo_threads()
+        lib, kind = abi.Lib(ref, "vpref_"), "reference"
+    else:
+        so = os.path.join(ROOT, "oracle", "libvporacle.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libvporacle.so"])
+        lib, kind = abi.Lib(so, "vpo_"), "port"
+    threads = getattr(lib.dll, lib.prefix + "threads")
+    threads.restype = C.c_int
+    setter = getattr(lib.dll, lib.prefix + "set_threads", None)
+    try:
+        want = len(os.sched_getaffinity(0))
+    except AttributeError:
+        want = os.cpu_count() or 1
+    if setter is not None and want > 0:
+        setter(want)
+    return lib, kind, threads()
 
 
 def cpu_frame_times(lib, sc, cam, fpd, reps, first_frame=0):
