@@ -148,7 +148,6 @@ struct vp_ctx {
   int tune_graph = 1;         // VP_GRAPH: 0 = launch every kernel of a pass from the host, 2 = graph + prepare stage for lone passes too
   int tune_prepare = 1;       // VP_PREPARE: 0 = the extend stage sets up every walk itself
   bool graph_now = false;     // this call's passes go through the lane graphs
-  bool in_bands = false;      // vp_render is launching its row bands
   int tune_band_ramp = 0;     // VP_BAND_RAMP: band heights 1 : 2 : ... : n instead of equal
   int tune_band_stagger = 0;  // VP_BAND_STAGGER: band k+1 of a vp_render call starts when band k has shaded this bounce (-1: all at once)
   int band_last_lane = -1;    // lane the most recent pass went to
@@ -516,8 +515,6 @@ int mark_direct(vp_ctx* c, cudaStream_t stream)
   return 0;
 }
 
-static inline int cs_flag_for_prepare(const VpFrameParams* fp) { return (fp->flags & VP_FLAG_COUNT_STEPS) != 0; }
-
 int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream, bool overlap,
                      const RpArgs* rp = nullptr)
 {
@@ -547,7 +544,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   // stage sets up the walks itself (reprojection cfg 2: 5.94 against 6.32 ms per frame).
   const bool piped = overlap || fp->spp > 1 || c->tune_graph >= 2;
   c->graph_now = c->tune_graph != 0 && piped;
-  p.prepared = c->tune_prepare && piped && c->tune_brickwalk && !cs_flag_for_prepare(fp) && c->sc.nvol <= 60;
+  p.prepared = c->tune_prepare && piped && c->tune_brickwalk && !(fp->flags & VP_FLAG_COUNT_STEPS) && c->sc.nvol <= 60;
   // Persistent grids follow the number of paths this call can have: a warp that gets only ~1 ray per lane never refills
   // and ends at the SIMD efficiency of its longest ray, so small shards run fewer, longer-lived warps (>= 3 blocks per SM
   // to keep latency hidden; measured on 1/8 frame shares, profiles/README.md).
@@ -1126,7 +1123,6 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
       if (edge[k] < edge[k - 1]) edge[k] = edge[k - 1];
     }
     cudaEvent_t done[kCallRing];
-    c->in_bands = true;
     for (int k = 0; k < nb; k++) {
       if (edge[k + 1] <= edge[k]) { done[k] = nullptr; continue; }
       VpFrameParams b = *fp;
@@ -1134,10 +1130,9 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
       done[k] = c->ev_call[c->ncalls % kCallRing];  // the completion event launch_render records for this call
       const int rc = launch_render(c, cam, &b, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, nullptr, true);
       c->band_wait_lane = (c->tune_band_stagger >= 0 && b.spp == 1) ? c->band_last_lane : -1;  // the next band starts behind this one
-      if (rc) { c->band_wait_lane = -1; c->in_bands = false; return rc; }
+      if (rc) { c->band_wait_lane = -1; return rc; }
     }
     c->band_wait_lane = -1;
-    c->in_bands = false;
     // copies after all launches: a copy into pageable memory blocks the host until its band is done
     for (int k = 0; k < nb; k++) {
       if (!done[k]) continue;
