@@ -108,8 +108,8 @@ typedef struct VpFrameParams {
                                   cuda_stream wait for it, so the latency-bound tail of this frame overlaps the start of the next
                                   call's.  Frames still resolve in call order (the accumulator is a running average).  Consume
                                   accum/rgb8 only behind vp_render_fence; any non-deferred call also waits for all earlier ones. */
-#define VP_FLAG_PERSISTENT 4u  /* all stages of a pass inside ONE persistent kernel with device-side queues instead of one
-                                  kernel per stage and bounce (lower fixed latency on very small frames, slower at full load) */
+#define VP_FLAG_PERSISTENT 4u  /* retired (round 2): the single persistent-kernel formulation lost its A/B against the staged
+                                  launches at every frame size; the flag is accepted and ignored */
 
 /* Result of one Renderer::FindNearest call (renderer.cpp:946-1018). */
 typedef struct VpHit {
@@ -146,6 +146,18 @@ typedef struct vp_ctx vp_ctx;
 /* Renderer::Init replacement (renderer.cpp:688-736, minus asset/game setup).
  * device < 0 selects the current CUDA device. */
 vp_ctx* vp_create(int device);
+/* The same for several GPUs of one box inside ONE process: the row fan-out of Renderer::Update
+ * (renderer.cpp:1646-1665: rows handed to a thread pool) becomes interleaved 8-row tiles, tile k on devices[k mod ndev].
+ * The context replicates the scene on every device (vp_set_* / vp_update_* go to all of them) and shards every
+ * vp_render / vp_render_async / vp_render_device / vp_render_resident call itself (leave row_tile* unset):
+ *  - host-buffer calls: every GPU moves only its own rows, over its own PCIe link, in and out of the caller's ONE
+ *    accumulator and ONE image;
+ *  - device-buffer calls: the buffers live on devices[0]; the other GPUs' resolve stage reads / writes the accumulator of
+ *    its tiles and stores its RGB8 pixels straight into them over NVLink (peer access) - no pack buffer, no collective,
+ *    no de-interleave.  cuda_stream must belong to devices[0].
+ * Ray-batch seams, the reprojection mode and the gameplay queries run on devices[0].  ndev == 1 is vp_create. */
+vp_ctx* vp_create_multi(const int* devices, int ndev);
+int vp_device_count(vp_ctx* ctx);
 void vp_destroy(vp_ctx* ctx);
 const char* vp_last_error(void);
 
@@ -174,6 +186,22 @@ int vp_set_sky(vp_ctx* ctx, const float* rgb, int w, int h, float contribution, 
  * (screen->pixels), may be NULL.  HOST pointers; copies are part of the call. */
 int vp_render(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, float* accum_rgba, uint32_t* rgb8,
               VpStats* stats);
+/* Asynchronous Update(): the reference's Tick only needs frame k's pixels when it blits them (renderer.cpp:1972-2217), so
+ * the call returns once the frame is enqueued - upload of accum_in (host, W*H float4; NULL = continue from the device copy
+ * of the previous call's result), the trace, download into accum_out / rgb8_out (host; accum_out may equal accum_in) - and
+ * vp_render_wait(ticket) blocks until that frame's downloads have landed.  Successive calls overlap like VP_FLAG_DEFER
+ * frames: their copies are ordered (upload k+1 after download k), so the caller may pass the same accumulator every
+ * frame, or alternate two (frame k: in A, out B; frame k+1: in B, out A) and read B while frame k+1 is in flight.  The
+ * buffers of a call must stay untouched until its ticket has been waited for; at most 16 tickets are kept (the call
+ * blocks on the oldest beyond that).  Page-locked buffers (vp_host_register) keep the copies asynchronous.  Results are
+ * bit-identical to vp_render frame by frame. */
+int vp_render_async(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, const float* accum_in, float* accum_out,
+                    uint32_t* rgb8_out, uint64_t* ticket);
+int vp_render_wait(vp_ctx* ctx, uint64_t ticket);
+/* cudaHostRegister / cudaHostUnregister for hosts that do not link the CUDA runtime (Renderer::accumulator is MALLOC64
+ * memory, renderer.cpp:699). */
+int vp_host_register(vp_ctx* ctx, void* ptr, uint64_t bytes);
+int vp_host_unregister(vp_ctx* ctx, void* ptr);
 /* Same work on DEVICE buffers owned by the caller (accumulator resident in HBM across
  * calls, e.g. a torch tensor that NCCL gathers afterwards).  accum_rgba_dev: W*H float4,
  * rgb8_dev: W*H uint32 or NULL.  cuda_stream: a cudaStream_t (NULL = default stream).
@@ -252,6 +280,24 @@ int vp_stats_end(vp_ctx* ctx, VpStats* stats);
 /* Sum of the device time of the extend-stage (k_wf_extend) launches made with VP_FLAG_TIME_STAGES since
  * the previous call, and their number; synchronises the device. */
 int vp_stage_times(vp_ctx* ctx, double* extend_ms, uint64_t* extend_launches);
+
+/* ---- one image shared by several PROCESSES (one rank per GPU) ----------------------------------------
+ * The display rank allocates the image in its GPU's HBM (vp_share_create) and hands the 128-byte VpShareInfo to the other
+ * ranks by any transport; they map it (vp_share_open: CUDA IPC + peer access over NVLink) and pass vp_share_ptr() as the
+ * rgb8_dev of vp_render_device, so their resolve stage stores its tiles straight into the display GPU's image - the
+ * replacement for pack -> ncclAllGather -> de-interleave.  64 flag words in front of the payload order the ranks:
+ * vp_share_signal(stream, slot, v) publishes v in flag `slot` (system scope) after everything the stream holds;
+ * vp_share_wait(stream, first, n, v, timeout_s) makes the stream wait until the flags first..first+n-1 are >= v (it gives
+ * up after timeout_s seconds - default 5 - and sets the word vp_share_error reads: a dead peer must not hang the GPU). */
+typedef struct VpShareInfo { unsigned char handle[64]; uint64_t bytes; int32_t device; int32_t pad[13]; } VpShareInfo;
+typedef struct vp_share vp_share;
+vp_share* vp_share_create(vp_ctx* ctx, uint64_t bytes, VpShareInfo* info_out);
+vp_share* vp_share_open(vp_ctx* ctx, const VpShareInfo* info);
+void* vp_share_ptr(vp_share* share);
+int vp_share_signal(vp_share* share, void* cuda_stream, int slot, uint32_t value);
+int vp_share_wait(vp_share* share, void* cuda_stream, int first_slot, int nslots, uint32_t value, double timeout_s);
+int vp_share_error(vp_share* share, uint32_t* error);
+int vp_share_close(vp_share* share);
 
 /* Build/runtime facts for the harness: fills up to `cap` bytes of a JSON string. */
 int vp_info(vp_ctx* ctx, char* buf, int cap);

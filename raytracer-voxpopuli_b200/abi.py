@@ -64,6 +64,10 @@ class VpFrameParams(C.Structure):
                 ("row_tile_stride", C.c_int32), ("row_tile_phase", C.c_int32), ("flags", C.c_uint32)]
 
 
+class VpShareInfo(C.Structure):
+    _fields_ = [("handle", C.c_ubyte * 64), ("bytes", C.c_uint64), ("device", C.c_int32), ("pad", C.c_int32 * 13)]
+
+
 class VpStats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("secondary_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("exit_rays", C.c_uint64), ("dda_steps", C.c_uint64), ("sky_samples", C.c_uint64), ("device_ms", C.c_double),
@@ -95,6 +99,8 @@ ABI_SYMBOLS = [
     "set_materials", "set_lights", "set_prims", "set_sky", "render", "render_resident", "accum_reset",
     "accum_download", "render_device", "trace_primary", "find_nearest", "is_occluded", "trace", "info", "stats_begin", "stats_end", "stage_times",
     "render_fence", "render_reproject", "render_reproject_device", "in_light", "find_nearest_player", "focus_distance",
+    "create_multi", "device_count", "render_async", "render_wait", "host_register", "host_unregister",
+    "share_create", "share_open", "share_ptr", "share_signal", "share_wait", "share_error", "share_close",
 ]
 
 
@@ -153,6 +159,20 @@ class Lib:
         f("stats_end", C.c_int, [C.c_void_p, C.POINTER(VpStats)], optional=True)
         f("stage_times", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)], optional=True)
         f("render_fence", C.c_int, [C.c_void_p, C.c_void_p, C.c_int], optional=True)
+        f("create_multi", C.c_void_p, [C.POINTER(C.c_int), C.c_int], optional=True)
+        f("device_count", C.c_int, [C.c_void_p], optional=True)
+        f("render_async", C.c_int, [C.c_void_p, C.POINTER(VpCamera), C.POINTER(VpFrameParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_uint64)], optional=True)
+        f("render_wait", C.c_int, [C.c_void_p, C.c_uint64], optional=True)
+        f("host_register", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64], optional=True)
+        f("host_unregister", C.c_int, [C.c_void_p, C.c_void_p], optional=True)
+        f("share_create", C.c_void_p, [C.c_void_p, C.c_uint64, C.POINTER(VpShareInfo)], optional=True)
+        f("share_open", C.c_void_p, [C.c_void_p, C.POINTER(VpShareInfo)], optional=True)
+        f("share_ptr", C.c_void_p, [C.c_void_p], optional=True)
+        f("share_signal", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32], optional=True)
+        f("share_wait", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_double], optional=True)
+        f("share_error", C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)], optional=True)
+        f("share_close", C.c_int, [C.c_void_p], optional=True)
 
     def _f(self, name, restype, argtypes, optional=False):
         try:

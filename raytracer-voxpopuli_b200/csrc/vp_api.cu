@@ -12,7 +12,6 @@
 
 #include "vp_kernels.cuh"
 #include "vp_wavefront.cuh"
-#include "vp_persistent.cuh"
 
 using namespace vp;
 
@@ -72,11 +71,15 @@ struct DevBuf {
 struct PassGraph {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
-  int max_bounces = -2, brickwalk = -1;
+  // what the captured topology depends on: bounce count, kernel variants (brick walk / prepare stage, single- or
+  // multi-volume functions, the candidate-mask stage), the node that records ev_mid, dynamic shared memory, and the lane's buffers
+  int max_bounces = -2, brickwalk = -1, nvol = -1, stagger = -99;
   size_t smem = 0;
   const void* counts = nullptr;  // the lane's buffers were (re)allocated: the memset node and every pointer changed
-  struct Node { cudaGraphNode_t node; cudaKernelNodeParams kp; int iter; int kind; };  // kind 1 = extend, 2 = shadow grid
+  // kind 0 = other, 1 = extend grid, 2 = shadow grid, 3 = generate (the only graphed stage that reads per-frame fields)
+  struct Node { cudaGraphNode_t node; cudaKernelNodeParams kp; int iter; int kind; WfParams last; unsigned grid; };
   std::vector<Node> nodes;
+  unsigned long long updates = 0, replays = 0;  // node parameter updates issued / graph launches (vp_info)
 };
 
 struct WfLane {
@@ -90,19 +93,30 @@ struct WfLane {
   DevBuf<unsigned char> d_wf;
   uint32_t cap = 0;
   int levels = 0, samples = 0;
+  bool prims = false, prepared = false, masks = false;  // optional parts laid out
+  size_t bytes = 0;
 };
 constexpr int kLanes = 6;       // most frames in flight (c->nlanes are used: 4 unless VP_LANES says otherwise)
 constexpr int kCallRing = 8;    // completion events kept for vp_render_fence
 
+constexpr int kTickets = 16;     // vp_render_async calls whose completion events are kept
 struct vp_ctx {
+  // ---- multi-device context (vp_create_multi): owns one single-device context per GPU, the scene replicated on each;
+  // render calls shard the frame as interleaved 8-row tiles (tile k -> kids[k mod n]) ----
+  bool group = false;
+  bool peer_ok = false;            // every device can store into kids[0]'s memory (NVLink / PCIe peer access)
+  std::vector<vp_ctx*> kids;
+  cudaEvent_t gev_in = nullptr;    // recorded on the caller's stream (device of kids[0]) when a device-buffer call enters
+  unsigned long long gtickets[kTickets][16] = {};
+  // ---- asynchronous host-buffer frames (vp_render_async / vp_render_wait) ----
+  cudaEvent_t ev_ticket[kTickets] = {};
+  unsigned long long nticket = 0;
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   WfLane lane[kLanes];
   int next_lane = 0;
-  int nlanes = 4;      // frames in flight wanted (VP_LANES)
-  int lanes_now = 4;   // ... and what the free HBM allows for the current frame size
-  bool lanes_sized = false;
+  int nlanes = 4;      // frames in flight (VP_LANES); lowered only when a lane's path state cannot be allocated
   cudaEvent_t ev_in = nullptr;      // recorded on the caller's stream when a render call enters
   cudaEvent_t ev_direct = nullptr;  // recorded after a launch made directly on the caller's stream (single-kernel formulations)
   bool direct_recorded = false;
@@ -154,9 +168,8 @@ struct vp_ctx {
   int band_wait_lane = -1;    // lane whose ev_mid the next pass has to wait for (set by vp_render between its bands)
   int tune_bands = 4;         // VP_BANDS: row bands a vp_render call is cut into (1 = off)
   long long tune_band_min_pixels = 1 << 18;  // VP_BAND_MIN_PIXELS: smaller calls are not cut
-  int tune_persistent = 0;    // VP_PERSISTENT=1: persistent kernel instead of per-stage kernels
-  int wf_blocks_persistent = 0;
-  uint32_t last_error_word = 0;  // error word of the last persistent launch (valid after a stream sync)
+  int tune_paths_per_thread = 8;  // VP_PATHS_PER_THREAD: paths of a call per thread of the persistent traversal grids (small shards: fewer, longer-lived warps)
+  int tune_min_blocks = 3;        // VP_MIN_BLOCKS: ... but at least this many blocks per SM
   // VP_FLAG_TIME_STAGES: CUDA-event pairs around every k_wf_extend launch, summed by vp_stage_times
   std::vector<cudaEvent_t> tev;
   size_t tev_used = 0;
@@ -257,6 +270,8 @@ int check_frame(const vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp)
   if (fp->width <= 0 || fp->height <= 0 || (long long)fp->width * fp->height > 0x7FFFFFFFll) return fail(VP_EINVAL, "bad resolution %dx%d", fp->width, fp->height);
   if (fp->max_bounces >= VP_MAX_LEVELS) return fail(VP_EINVAL, "max_bounces %d exceeds the supported %d", fp->max_bounces, VP_MAX_LEVELS - 1);
   if (fp->spp < 0) return fail(VP_EINVAL, "negative spp");
+  if (!(fp->row_begin == 0 && fp->row_end == 0) && (fp->row_begin < 0 || fp->row_begin > fp->row_end || fp->row_end > fp->height))
+    return fail(VP_EINVAL, "bad row range [%d,%d) for a frame of %d rows", fp->row_begin, fp->row_end, fp->height);
   if (fp->row_tile > 0 && (fp->row_tile_stride <= 0 || fp->row_tile_phase < 0 || fp->row_tile_phase >= fp->row_tile_stride))
     return fail(VP_EINVAL, "bad row tile interleave %d/%d/%d", fp->row_tile, fp->row_tile_stride, fp->row_tile_phase);
   if (!c->have_volumes) return fail(VP_ESTATE, "vp_set_volumes has not been called");
@@ -286,25 +301,29 @@ int grid_blocks(const vp_ctx* c, long long work_warps)
   return (int)(need < full ? need : full);
 }
 
-// path state of one lane (HBM-resident, sized for the largest frame / depth seen)
-int wf_reserve(WfLane& L, uint32_t cap, int levels, int samples, size_t* bytes_only = nullptr)
+// path state of one lane (HBM-resident, sized for the largest pass / depth seen).  Optional parts are only laid out when
+// a scene needs them: primitive normals (spheres / triangles), prepared walks (passes that overlap), candidate masks
+// (multi-volume scenes).
+struct WfNeed { uint32_t cap; int levels, samples; bool prims, prepared, masks; };
+int wf_reserve(WfLane& L, const WfNeed& nd, size_t* bytes_only = nullptr)
 {
   if (bytes_only) *bytes_only = 0;
-  if (cap <= L.cap && levels <= L.levels && samples <= L.samples && L.d_wf.p) return 0;
-  cap = cap > L.cap ? cap : L.cap;
-  levels = levels > L.levels ? levels : L.levels;
-  samples = samples > L.samples ? samples : L.samples;
+  if (nd.cap <= L.cap && nd.levels <= L.levels && nd.samples <= L.samples && (!nd.prims || L.prims) && (!nd.prepared || L.prepared) &&
+      (!nd.masks || L.masks) && L.d_wf.p)
+    return 0;
+  const uint32_t cap = nd.cap > L.cap ? nd.cap : L.cap;
+  const int levels = nd.levels > L.levels ? nd.levels : L.levels;
+  const int samples = nd.samples > L.samples ? nd.samples : L.samples;
+  const bool prims = nd.prims || L.prims, prepared = nd.prepared || L.prepared, masks = nd.masks || L.masks;
   const size_t f4 = sizeof(float4);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  const size_t o_r0 = take(cap * f4), o_r1 = take(cap * f4), o_h0 = take(cap * 8), o_h1 = take(cap * 4), o_hn = take(cap * f4), o_term = take(cap * f4);
-  const size_t o_lm = take((size_t)levels * cap * f4), o_la = take((size_t)levels * cap * f4);
-  const size_t o_sq0 = take((size_t)levels * cap * f4), o_sqd = take((size_t)levels * samples * cap * f4), o_sql = take((size_t)levels * samples * cap * f4);
-  const size_t pq_len = (size_t)levels * cap + (size_t)64 * 1024 * 32;  // + one window per warp that may be handed out past the last id
-  const size_t o_pq = take(3 * pq_len * 4), o_pctl = take(kCtlWords * 4);
+  const size_t o_r0 = take(cap * f4), o_r1 = take(cap * f4), o_h0 = take(cap * 8), o_h1 = take(cap * 4), o_hn = take(prims ? cap * f4 : 0), o_term = take(cap * f4);
+  const size_t o_lv = take((size_t)levels * cap * f4);
+  const size_t o_sq0 = take((size_t)2 * cap * f4), o_sqd = take((size_t)2 * samples * cap * f4), o_sql = take((size_t)2 * samples * cap * f4);
   const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_qs = take(2 * cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
-  const size_t o_ps = take(3 * cap * f4);  // prepared walks of the bounce being extended, by queue position
-  const size_t o_sm = take((size_t)samples * cap * 4);  // bounding-sphere candidates of the bounce's shadow rays
+  const size_t o_ps = take(prepared ? 3 * cap * f4 : 0);  // prepared walks of the bounce being extended, by queue position
+  const size_t o_sm = take(masks ? (size_t)samples * cap * 4 : 0);  // bounding-sphere candidates of the bounce's shadow rays
   if (bytes_only) { *bytes_only = off; return 0; }  // what growing this lane would take
   CU(cudaDeviceSynchronize());
   CU(L.d_wf.reserve(off));
@@ -312,17 +331,14 @@ int wf_reserve(WfLane& L, uint32_t cap, int levels, int samples, size_t* bytes_o
   WfState& w = L.wf;
   w.cap = cap;
   w.r0 = (float4*)(b + o_r0); w.r1 = (float4*)(b + o_r1); w.h0 = (float2*)(b + o_h0); w.h1 = (uint32_t*)(b + o_h1); w.hn = (float4*)(b + o_hn);
-  w.term = (float4*)(b + o_term); w.lm = (float4*)(b + o_lm); w.la = (float4*)(b + o_la);
+  w.term = (float4*)(b + o_term); w.lv = (float4*)(b + o_lv);
   w.sq0 = (float4*)(b + o_sq0); w.sqd = (float4*)(b + o_sqd); w.sql = (float4*)(b + o_sql); w.nsamp = (uint32_t)samples;
   for (int k = 0; k < 2; k++) w.qs[k] = (uint32_t*)(b + o_qs) + (size_t)k * cap;
   w.q[0] = (uint32_t*)(b + o_q0); w.q[1] = (uint32_t*)(b + o_q1); w.counts = (uint32_t*)(b + o_cnt);
-  for (int k = 0; k < 3; k++) w.pq[k] = (uint32_t*)(b + o_pq) + (size_t)k * pq_len;
-  w.pctl = (uint32_t*)(b + o_pctl);
   for (int k = 0; k < 3; k++) w.ps[k] = (float4*)(b + o_ps) + (size_t)k * cap;
   w.smask = (uint32_t*)(b + o_sm);
-  CU(cudaMemset(b + o_pq, 0xFF, 3 * pq_len * 4));  // all slots empty
-  CU(cudaMemset(w.pctl, 0, kCtlWords * 4));
-  L.cap = cap; L.levels = levels; L.samples = samples;
+  L.cap = cap; L.levels = levels; L.samples = samples; L.prims = prims; L.prepared = prepared; L.masks = masks;
+  L.bytes = off;
   return 0;
 }
 
@@ -396,11 +412,16 @@ void drop_graph(PassGraph& G)
 }
 
 // the trace part of a pass through the lane's graph; returns 1 when graphs are unusable (caller launches directly)
+// Replay cost: of the ~77 kernel nodes only k_wf_generate reads what changes from frame to frame (camera, frame index,
+// seed, rows); the traversal / shade nodes see the same arguments every frame unless the frame size or the grids of
+// the persistent stages change.  A node's arguments are therefore compared with what it holds and only written on a
+// difference: one cudaGraphExecKernelNodeSetParams per frame in steady state instead of one per node.
 int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
 {
   PassGraph& G = L.pg;
   const size_t sm = smem_bytes(c);
-  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared && G.smem == sm && G.counts == (const void*)p.st.counts);
+  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared && G.smem == sm &&
+                       G.counts == (const void*)p.st.counts && G.nvol == p.sc.nvol && G.stagger == c->tune_band_stagger);
   if (fresh) {
     if (G.exec) CU(cudaStreamSynchronize(L.main));  // the old graph may still be running on this lane
     drop_graph(G);
@@ -419,27 +440,45 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
       if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
       PassGraph::Node x; x.node = nd;
       if (cudaGraphKernelNodeGetParams(nd, &x.kp) != cudaSuccess) { cudaGetLastError(); drop_graph(G); return 1; }
-      x.iter = reinterpret_cast<const WfParams*>(x.kp.kernelParams[0])->iter;
+      memcpy(&x.last, x.kp.kernelParams[0], sizeof(WfParams));
+      x.iter = x.last.iter;
+      x.grid = x.kp.gridDim.x;
       x.kind = (x.kp.func == (void*)k_wf_extend<false, true> || x.kp.func == (void*)k_wf_extend<false, false> ||
                 x.kp.func == (void*)k_wf_extend<false, true, kWfMinBlocksMulti>) ? 1
              : (x.kp.func == (void*)k_wf_shadow<false, true> || x.kp.func == (void*)k_wf_shadow<false, false> ||
-                x.kp.func == (void*)k_wf_shadow<false, true, kWfMinBlocksMulti>) ? 2 : 0;
+                x.kp.func == (void*)k_wf_shadow<false, true, kWfMinBlocksMulti>) ? 2
+             : (x.kp.func == (void*)k_wf_generate) ? 3 : 0;
       G.nodes.push_back(x);
     }
     G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared; G.smem = sm; G.counts = (const void*)p.st.counts;
+    G.nvol = p.sc.nvol; G.stagger = c->tune_band_stagger;
   } else {
     for (PassGraph::Node& x : G.nodes) {
-      WfParams q = p;
+      WfParams q;
+      memcpy(&q, &p, sizeof(q));
       q.iter = x.iter;
+      if (x.kind != 3 && !p.reproject) {
+        // fields these stages never read keep the values the node already holds (see WfParams: per-frame fields)
+        q.cam = x.last.cam; q.frame = x.last.frame; q.seed = x.last.seed; q.aa = x.last.aa;
+        q.row_begin = x.last.row_begin; q.row_end = x.last.row_end; q.row_tile = x.last.row_tile;
+        q.row_tile_stride = x.last.row_tile_stride; q.row_tile_phase = x.last.row_tile_phase;
+        q.cmode = x.last.cmode; q.ctrow0 = x.last.ctrow0; q.ck = x.last.ck;
+        q.accum = x.last.accum; q.rgb8 = x.last.rgb8; q.write_rgb8 = x.last.write_rgb8;
+      }
+      const unsigned grid = x.kind == 1 ? (unsigned)c->wf_grid_extend : (x.kind == 2 ? (unsigned)c->wf_grid_shadow : x.grid);
+      if (grid == x.grid && memcmp(&q, &x.last, sizeof(q)) == 0) continue;
       void* args[1] = {&q};
       cudaKernelNodeParams kp = x.kp;
       kp.kernelParams = args;
-      if (x.kind == 1) kp.gridDim = dim3((unsigned)c->wf_grid_extend);
-      if (x.kind == 2) kp.gridDim = dim3((unsigned)c->wf_grid_shadow);
+      kp.gridDim = dim3(grid);
       CU(cudaGraphExecKernelNodeSetParams(G.exec, x.node, &kp));
+      memcpy(&x.last, &q, sizeof(q));
+      x.grid = grid;
+      G.updates++;
     }
   }
   CU(cudaGraphLaunch(G.exec, L.main));
+  G.replays++;
   c->host_launches += G.nodes.size();
   return 0;
 }
@@ -473,24 +512,6 @@ int launch_wavefront_pass(vp_ctx* c, WfLane& L, WfParams& p)
   return 0;
 }
 
-// One Update() pass with the persistent kernel: clear the queues, generate, one persistent launch, resolve.
-template <bool CS>
-int launch_persistent_pass(vp_ctx* c, WfParams& p, cudaStream_t stream)
-{
-  const size_t sm = smem_bytes(c);
-  const int wide = c->sm_count * 8;
-  p.persistent = 1;
-  k_wf_pclear<<<wide, 256, 0, stream>>>(p);
-  CU(cudaMemsetAsync(p.st.pctl, 0, 256 * sizeof(uint32_t), stream));  // heads, tails, pending, error (kPrevTails kept for the clear above)
-  k_wf_generate<<<wide, kWfBlock, 0, stream>>>(p);
-  k_wf_persistent<CS><<<c->wf_blocks_persistent, kWfBlock, sm, stream>>>(p);
-  if (c->wait_copy) { CU(cudaStreamWaitEvent(stream, c->ev_copy, 0)); c->wait_copy = false; }
-  k_wf_resolve<<<wide, kWfBlock, 0, stream>>>(p);
-  c->host_launches += 4;
-  CU(cudaGetLastError());
-  return 0;
-}
-
 // the caller's stream waits for every pass enqueued so far (resolves are chained, the last one covers all)
 int join_lanes(vp_ctx* c, cudaStream_t stream)
 {
@@ -503,6 +524,40 @@ int quiesce(vp_ctx* c)
 {
   for (WfLane& L : c->lane)
     if (L.main) CU(cudaStreamSynchronize(L.main));
+  if (c->copy) CU(cudaStreamSynchronize(c->copy));  // downloads of asynchronous frames
+  return 0;
+}
+
+// Moves the rows of a [H][W] array of `elem`-byte pixels that a call with these frame parameters renders between host and
+// device: a contiguous row range, or - with interleaved row tiles - one strided 2-D copy over the owned full tiles plus
+// the ragged last tile when it is owned; tiles combined with a row range go tile by tile.  Rows a call does not own are
+// never touched, so several devices can assemble one frame in one host buffer.
+int copy_rows(const VpFrameParams* fp, void* dst, const void* src, size_t elem, cudaMemcpyKind kind, cudaStream_t st)
+{
+  const int H = fp->height;
+  const size_t W = (size_t)fp->width;
+  const bool whole = fp->row_begin == 0 && fp->row_end == 0;
+  const int rb = whole ? 0 : fp->row_begin, re = whole ? H : fp->row_end;
+  auto rows = [&](int y0, int y1) -> cudaError_t {
+    if (y1 <= y0) return cudaSuccess;
+    const size_t off = (size_t)y0 * W * elem;
+    return cudaMemcpyAsync((char*)dst + off, (const char*)src + off, (size_t)(y1 - y0) * W * elem, kind, st);
+  };
+  if (fp->row_tile > 0 && fp->row_tile_stride > 1) {
+    const int T = fp->row_tile, S = fp->row_tile_stride, ph = fp->row_tile_phase;
+    if (rb == 0 && re == H) {
+      const int nfull = H / T;
+      const int owned = nfull > ph ? (nfull - ph + S - 1) / S : 0;
+      const size_t chunk = (size_t)T * W * elem, pitch = chunk * (size_t)S, off = chunk * (size_t)ph;
+      if (owned > 0) CU(cudaMemcpy2DAsync((char*)dst + off, pitch, (const char*)src + off, pitch, chunk, (size_t)owned, kind, st));
+      if (H % T != 0 && nfull % S == ph) CU(rows(nfull * T, H));
+      return 0;
+    }
+    for (int t = rb / T; t * T < re; t++)
+      if (t % S == ph) CU(rows(t * T > rb ? t * T : rb, (t + 1) * T < re ? (t + 1) * T : re));
+    return 0;
+  }
+  CU(rows(rb, re));
   return 0;
 }
 
@@ -515,13 +570,34 @@ int mark_direct(vp_ctx* c, cudaStream_t stream)
   return 0;
 }
 
+// tile rows (4 pixel rows each) that get path ids for this call, and how ids map to them (WfParams.cmode)
+struct Compact { int mode, trow0, k; uint32_t trows; };
+Compact compact_rows(const VpFrameParams* fp, int rb, int re, bool halo)
+{
+  Compact cp;
+  const int H = fp->height;
+  cp.mode = 0; cp.trow0 = 0; cp.k = 1; cp.trows = (uint32_t)((H + 3) / 4);
+  if (halo || re <= rb) return cp;
+  const bool whole = rb <= 0 && re >= H;
+  if (fp->row_tile > 0 && fp->row_tile_stride > 1) {
+    if (!whole || fp->row_tile % 4 != 0) return cp;
+    const int ntile = (H + fp->row_tile - 1) / fp->row_tile;
+    const int owned = ntile > fp->row_tile_phase ? (ntile - fp->row_tile_phase + fp->row_tile_stride - 1) / fp->row_tile_stride : 0;
+    cp.mode = 2; cp.k = fp->row_tile / 4; cp.trows = (uint32_t)(owned > 0 ? owned : 1) * (uint32_t)cp.k;
+    return cp;
+  }
+  if (whole) return cp;
+  cp.mode = 1; cp.trow0 = rb / 4; cp.trows = (uint32_t)((re - 1) / 4 - rb / 4 + 1);
+  return cp;
+}
+
 int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float4* accum, uint32_t* rgb8, cudaStream_t stream, bool overlap,
                      const RpArgs* rp = nullptr)
 {
-  const uint32_t tiles = (uint32_t)((fp->width + 7) / 8) * (uint32_t)((fp->height + 3) / 4);
   const int levels = fp->max_bounces + 1 > 1 ? fp->max_bounces + 1 : 1;
   const int samples = c->sc.area_samples > 1 ? c->sc.area_samples : 1;
   WfParams p;
+  memset(&p, 0, sizeof(p));  // node arguments are compared bytewise (graph_trace): no indeterminate padding
   p.sc = c->sc; p.cam = *cam;
   p.W = fp->width; p.H = fp->height; p.max_bounces = fp->max_bounces;
   p.seed = fp->seed; p.aa = fp->aa_strength;
@@ -531,12 +607,14 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   p.accum = accum; p.rgb8 = rgb8; p.counters = c->d_counters.p; p.iter = 0;
   p.refill = c->tune_refill;
   p.bulk = c->tune_bulk;
-  p.persistent = 0;
   p.reproject = rp ? 1 : 0;
   p.halo = rp ? 1 : 0;  // no effect on whole frames
   p.rp_alb = c->d_rp_alb.p; p.rp_ill = c->d_rp_ill.p; p.rp_ray = c->d_rp_ray.p;
   p.hist_in = rp ? rp->hist_in : nullptr; p.hist_out = rp ? rp->hist_out : nullptr;
-  if (rp) p.prev = rp->prev; else memset(&p.prev, 0, sizeof(p.prev));
+  if (rp) p.prev = rp->prev;
+  const Compact cp = compact_rows(fp, p.row_begin, p.row_end, p.halo != 0);
+  p.cmode = cp.mode; p.ctrow0 = cp.trow0; p.ck = cp.k;
+  const uint32_t cap = (uint32_t)((fp->width + 7) / 8) * cp.trows * 32u;  // paths of this call
   c->time_stages_now = (fp->flags & VP_FLAG_TIME_STAGES) != 0;
   // Graph replay and the separate prepare stage pay off when passes overlap (deferred frames, several samples per call,
   // the row bands of vp_render): the host runs ahead and the extra kernel boundaries hide under other passes.  A pass the
@@ -545,6 +623,9 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   const bool piped = overlap || fp->spp > 1 || c->tune_graph >= 2;
   c->graph_now = c->tune_graph != 0 && piped;
   p.prepared = c->tune_prepare && piped && c->tune_brickwalk && !(fp->flags & VP_FLAG_COUNT_STEPS) && c->sc.nvol <= 60;
+  WfNeed need;
+  need.cap = cap; need.levels = levels; need.samples = samples;
+  need.prims = c->sc.nsph + c->sc.ntri > 0; need.prepared = p.prepared != 0; need.masks = c->sc.nvol > 1 && c->sc.nvol <= 32;
   // Persistent grids follow the number of paths this call can have: a warp that gets only ~1 ray per lane never refills
   // and ends at the SIMD efficiency of its longest ray, so small shards run fewer, longer-lived warps (>= 3 blocks per SM
   // to keep latency hidden; measured on 1/8 frame shares, profiles/README.md).
@@ -553,9 +634,9 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
     for (int y = p.row_begin; y < p.row_end && y < fp->height; y++)
       if (y >= 0 && (p.row_tile <= 0 || ((y / p.row_tile) % p.row_tile_stride) == p.row_tile_phase)) rows++;
     const long long paths = rows * (long long)fp->width;
-    const long long per_sm = (long long)kWfBlock * 8 * c->sm_count;
+    const long long per_sm = (long long)kWfBlock * c->tune_paths_per_thread * c->sm_count;
     long long want = (paths + per_sm - 1) / per_sm;
-    if (want < 3) want = 3;
+    if (want < c->tune_min_blocks) want = c->tune_min_blocks;
     const int be = c->sc.nvol > 1 ? c->wf_blocks_extend_mv : c->wf_blocks_extend;  // the kernel variant this scene runs
     const int bs = c->sc.nvol > 1 ? c->wf_blocks_shadow_mv : c->wf_blocks_shadow;
     const long long we = want * c->sm_count < be ? want * c->sm_count : be;
@@ -564,72 +645,32 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
     c->wf_grid_extend = full ? be : (int)we;
     c->wf_grid_shadow = full ? bs : (int)ws;
   }
-  const bool staged = rp || !((fp->flags & VP_FLAG_PERSISTENT) != 0 || c->tune_persistent);
   const bool cs = (fp->flags & VP_FLAG_COUNT_STEPS) != 0;
-  if (staged) CU(cudaEventRecord(c->ev_in, stream));
-  else if (int rc = join_lanes(c, stream)) return rc;
+  CU(cudaEventRecord(c->ev_in, stream));
   bool entered[kLanes] = {};
-  if (staged && (overlap || fp->spp > 1)) {
-    // Frames in flight: size the lanes now rather than one per call (allocation synchronises the device), and only as
-    // many as fit: a lane of a 4K frame at depth 14 with area lights is ~20 GB.  New lanes may take 80 % of the free HBM.
-    int fit = 0;
-    size_t grow = 0, freeb = 0, totalb = 0;
-    bool steady = true;  // every lane in use already holds this frame size: no driver calls on the hot path
-    for (int i = 0; i < c->lanes_now && steady; i++) {
-      if (int rc = wf_reserve(c->lane[i], tiles * 32u, levels, samples, &grow)) return rc;
-      steady = grow == 0;
-    }
-    if (steady && c->lanes_sized) {
-      fit = c->lanes_now;
-    } else {
-      CU(cudaMemGetInfo(&freeb, &totalb));
-      size_t budget = (size_t)((double)freeb * 0.8);
-      for (int i = 0; i < c->nlanes; i++) {
-        if (int rc = wf_reserve(c->lane[i], tiles * 32u, levels, samples, &grow)) return rc;
-        const size_t held = c->lane[i].d_wf.p ? c->lane[i].d_wf.cap : 0;  // freed before the larger block is allocated
-        if (grow > budget + held && fit >= 1) break;
-        if (grow) budget = budget + held > grow ? budget + held - grow : 0;
-        fit++;
-      }
-      c->lanes_sized = true;
-    }
-    c->lanes_now = fit < 1 ? 1 : fit;
-    const int want = overlap ? c->lanes_now : (fp->spp < c->lanes_now ? fp->spp : c->lanes_now);
-    for (int i = 0; i < want; i++)
-      if (int rc = wf_reserve(c->lane[i], tiles * 32u, levels, samples)) return rc;
-  }
+  const bool rotate = overlap || fp->spp > 1;  // lanes rotate only when passes can overlap (several samples in this call, or a deferred call)
   const int passes = rp ? 1 : fp->spp;
   for (int s = 0; s < passes; s++) {
     p.frame = fp->frame_index + (uint32_t)s;
     p.write_rgb8 = (s == passes - 1);
-    int rc;
-    if (staged) {
-      // lanes rotate only when passes can overlap (several samples in this call, or a deferred call)
-      const int li = (overlap || fp->spp > 1) ? (c->next_lane++ % c->lanes_now) : 0;
-      WfLane& L = c->lane[li];
-      if ((rc = wf_reserve(L, tiles * 32u, levels, samples))) return rc;
-      if (c->band_wait_lane >= 0 && c->band_wait_lane != li) CU(cudaStreamWaitEvent(L.main, c->lane[c->band_wait_lane].ev_mid, 0));
-      c->band_last_lane = li;
-      if (!entered[li]) {
-        CU(cudaStreamWaitEvent(L.main, c->ev_in, 0));
-        if (c->direct_recorded) CU(cudaStreamWaitEvent(L.main, c->ev_direct, 0));
-        entered[li] = true;
-      }
-      p.st = L.wf;
-      p.st.cap = tiles * 32u;  // paths of this frame (strides use the frame's own cap)
-      rc = cs ? launch_wavefront_pass<true>(c, L, p) : launch_wavefront_pass<false>(c, L, p);
-    } else {
-      WfLane& L = c->lane[0];
-      if ((rc = wf_reserve(L, tiles * 32u, levels, samples))) return rc;
-      p.st = L.wf;
-      p.st.cap = tiles * 32u;
-      rc = cs ? launch_persistent_pass<true>(c, p, stream) : launch_persistent_pass<false>(c, p, stream);
+    int li = rotate ? (c->next_lane++ % c->nlanes) : 0;
+    if (int rc = wf_reserve(c->lane[li], need)) {  // grows the lane when this call needs more (synchronises the device then)
+      if (li == 0) return rc;
+      cudaGetLastError();  // out of memory for another lane: keep the frames in flight that fit
+      c->nlanes = li; c->next_lane = 1; li = 0;
+      if (int rc0 = wf_reserve(c->lane[0], need)) return rc0;
     }
-    if (rc) return rc;
-  }
-  if (!staged) {
-    CU(cudaMemcpyAsync(&c->last_error_word, c->lane[0].wf.pctl + kError, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    if (int rc = mark_direct(c, stream)) return rc;
+    WfLane& L = c->lane[li];
+    if (c->band_wait_lane >= 0 && c->band_wait_lane != li) CU(cudaStreamWaitEvent(L.main, c->lane[c->band_wait_lane].ev_mid, 0));
+    c->band_last_lane = li;
+    if (!entered[li]) {
+      CU(cudaStreamWaitEvent(L.main, c->ev_in, 0));
+      if (c->direct_recorded) CU(cudaStreamWaitEvent(L.main, c->ev_direct, 0));
+      entered[li] = true;
+    }
+    p.st = L.wf;
+    p.st.cap = cap;  // strides use the call's own cap
+    if (int rc = cs ? launch_wavefront_pass<true>(c, L, p) : launch_wavefront_pass<false>(c, L, p)) return rc;
   }
   return 0;
 }
@@ -687,7 +728,6 @@ int launch_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float
     CU(cudaStreamSynchronize(stream));
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    if (c->last_error_word) { const uint32_t e = c->last_error_word; c->last_error_word = 0; return fail(VP_ECUDA, "persistent render kernel gave up waiting (code %u)", e); }
     for (int k = 0; k < 8; k++) h[k] -= before[k];
     stats->primary_rays = h[4];
     stats->secondary_rays = h[0] - h[4];
@@ -702,6 +742,18 @@ int launch_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float
 }
 
 }  // namespace
+
+#include "vp_multi.cuh"
+
+// calls on a multi-device context: scene edits go to every device, queries of a single ray batch to the first one
+#define KIDS(call)                          \
+  if (c && c->group) {                      \
+    for (vp_ctx* k : c->kids)               \
+      if (int rc_ = (call)) return rc_;     \
+    return 0;                               \
+  }
+#define KID0(call) \
+  if (c && c->group) { vp_ctx* k = c->kids[0]; return (call); }
 
 extern "C" {
 
@@ -731,6 +783,7 @@ vp_ctx* vp_create(int device)
               cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->ev_direct, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < kCallRing && evok; i++) evok = cudaEventCreateWithFlags(&c->ev_call[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < kTickets && evok; i++) evok = cudaEventCreateWithFlags(&c->ev_ticket[i], cudaEventDisableTiming) == cudaSuccess;
   for (WfLane& L : c->lane) {
     evok = evok && cudaStreamCreateWithFlags(&L.main, cudaStreamNonBlocking) == cudaSuccess &&
            cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking) == cudaSuccess &&
@@ -792,12 +845,8 @@ vp_ctx* vp_create(int device)
   c->wf_grid_shade = occ * c->sm_count;
   if (const char* e = getenv("VP_BLOCKS_SHADE")) c->wf_grid_shade = atoi(e) * c->sm_count;
   // tuning knobs for experiments (defaults are the shipped values)
-  cudaFuncSetAttribute(k_wf_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  cudaFuncSetAttribute(k_wf_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_persistent<false>, kWfBlock, 8 * 1024) != cudaSuccess || occ < 1) occ = 3;
-  c->wf_blocks_persistent = occ * c->sm_count;
-  if (const char* e = getenv("VP_PERSISTENT")) c->tune_persistent = atoi(e);
-  if (const char* e = getenv("VP_BLOCKS_PERSISTENT")) c->wf_blocks_persistent = atoi(e) * c->sm_count;
+  if (const char* e = getenv("VP_PATHS_PER_THREAD")) c->tune_paths_per_thread = atoi(e) < 1 ? 1 : atoi(e);
+  if (const char* e = getenv("VP_MIN_BLOCKS")) c->tune_min_blocks = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("VP_LANES")) { const int n = atoi(e); c->nlanes = n < 1 ? 1 : (n > kLanes ? kLanes : n); }
   if (const char* e = getenv("VP_BULK_LANES")) c->tune_bulk = atoi(e);
   if (const char* e = getenv("VP_REFILL")) c->tune_refill = atoi(e);
@@ -816,6 +865,12 @@ vp_ctx* vp_create(int device)
 void vp_destroy(vp_ctx* c)
 {
   if (!c) return;
+  if (c->group) {
+    for (vp_ctx* k : c->kids) vp_destroy(k);
+    if (c->gev_in) { cudaSetDevice(c->device); cudaEventDestroy(c->gev_in); }
+    delete c;
+    return;
+  }
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (auto& v : c->vols) free_volume(v);
@@ -838,6 +893,8 @@ void vp_destroy(vp_ctx* c)
   }
   for (cudaEvent_t e : c->ev_call)
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_ticket)
+    if (e) cudaEventDestroy(e);
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_direct) cudaEventDestroy(c->ev_direct);
   if (c->copy) cudaStreamDestroy(c->copy);
@@ -850,11 +907,16 @@ void vp_destroy(vp_ctx* c)
 
 int vp_set_volumes(vp_ctx* c, const VpVolume* vols, int n)
 {
+  KIDS(vp_set_volumes(k, vols, n))
   if (!c || n < 0 || (n > 0 && !vols)) return fail(VP_EINVAL, "bad arguments to vp_set_volumes");
   if ((size_t)n * sizeof(DVolume) + 16 > 64 * 1024) return fail(VP_EINVAL, "too many volumes (%d)", n);
   if (bind(c) || quiesce(c)) return VP_ECUDA;
   for (int i = 0; i < n; i++)
     if (!vols[i].grid || vols[i].n == 0 || vols[i].n > 512) return fail(VP_EINVAL, "volume %d: bad grid pointer or size %u", i, vols[i].n);
+  // the old scene is gone from here on: a failure below must not leave a table that points at freed grids
+  c->have_volumes = false;
+  c->sc.nvol = 0; c->sc.vol = nullptr; c->sc.region_words = 0;
+  for (WfLane& L : c->lane) drop_graph(L.pg);  // the captured kernel variants and nodes depend on the volume count
   for (auto& v : c->vols) free_volume(v);
   c->vols.assign((size_t)n, HostVolume());
   size_t rwords = 0;
@@ -869,15 +931,24 @@ int vp_set_volumes(vp_ctx* c, const VpVolume* vols, int n)
     rwords += (size_t)1 << (3 * v.jr);
   }
   c->region_words = rwords;
-  CU(c->d_regions.reserve(rwords ? rwords : 1));
-  for (int i = 0; i < n; i++) {
-    HostVolume& v = c->vols[i];
-    const size_t bytes = (size_t)v.n * v.n * v.n;
-    CU(cudaMalloc(&v.grid, bytes));
-    CU(cudaMalloc(&v.fine, ((size_t)64 << (3 * v.jr)) * sizeof(unsigned long long)));
-    CU(cudaMemcpyAsync(v.grid, vols[i].grid, bytes, cudaMemcpyHostToDevice, c->stream));
-    if (build_masks(c, v)) return VP_ECUDA;
-    fill_dvolume(v, vols[i].matrix, vols[i].inv_matrix, vols[i].cube_min, vols[i].cube_max);
+  auto upload = [&]() -> int {
+    CU(c->d_regions.reserve(rwords ? rwords : 1));
+    for (int i = 0; i < n; i++) {
+      HostVolume& v = c->vols[i];
+      const size_t bytes = (size_t)v.n * v.n * v.n;
+      CU(cudaMalloc(&v.grid, bytes));
+      CU(cudaMalloc(&v.fine, ((size_t)64 << (3 * v.jr)) * sizeof(unsigned long long)));
+      CU(cudaMemcpyAsync(v.grid, vols[i].grid, bytes, cudaMemcpyHostToDevice, c->stream));
+      if (build_masks(c, v)) return VP_ECUDA;
+      fill_dvolume(v, vols[i].matrix, vols[i].inv_matrix, vols[i].cube_min, vols[i].cube_max);
+    }
+    return 0;
+  };
+  if (int rc = upload()) {  // partial allocations are released; the context stays without volumes (VP_ESTATE on render)
+    cudaStreamSynchronize(c->stream);
+    for (auto& v : c->vols) free_volume(v);
+    c->vols.clear();
+    return rc;
   }
   c->sc.regions = c->d_regions.p;
   // stage the region masks in shared memory when table + masks fit the 64 KB the kernels opt into
@@ -890,6 +961,7 @@ int vp_set_volumes(vp_ctx* c, const VpVolume* vols, int n)
 
 int vp_update_volume_grid(vp_ctx* c, int vi, uint32_t offset, uint32_t len, const uint8_t* bytes)
 {
+  KIDS(vp_update_volume_grid(k, vi, offset, len, bytes))
   if (!c || vi < 0 || vi >= (int)c->vols.size() || !bytes) return fail(VP_EINVAL, "bad arguments to vp_update_volume_grid");
   HostVolume& v = c->vols[vi];
   const size_t total = (size_t)v.n * v.n * v.n;
@@ -903,6 +975,7 @@ int vp_update_volume_grid(vp_ctx* c, int vi, uint32_t offset, uint32_t len, cons
 
 int vp_update_volume_transform(vp_ctx* c, int vi, const float M[16], const float iM[16], const float bmin[3], const float bmax[3])
 {
+  KIDS(vp_update_volume_transform(k, vi, M, iM, bmin, bmax))
   if (!c || vi < 0 || vi >= (int)c->vols.size() || !M || !iM || !bmin || !bmax) return fail(VP_EINVAL, "bad arguments to vp_update_volume_transform");
   if (bind(c) || quiesce(c)) return VP_ECUDA;
   fill_dvolume(c->vols[vi], M, iM, bmin, bmax);
@@ -911,6 +984,7 @@ int vp_update_volume_transform(vp_ctx* c, int vi, const float M[16], const float
 
 int vp_set_materials(vp_ctx* c, const VpMaterial* m, int n)
 {
+  KIDS(vp_set_materials(k, m, n))
   if (!c || !m || n < 0 || n > VP_MAX_MATERIALS) return fail(VP_EINVAL, "bad arguments to vp_set_materials (n=%d)", n);
   if (bind(c) || quiesce(c)) return VP_ECUDA;
   if (n > 0) CU(cudaMemcpyAsync(c->d_mat.p, m, sizeof(VpMaterial) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
@@ -921,6 +995,7 @@ int vp_set_materials(vp_ctx* c, const VpMaterial* m, int n)
 int vp_set_lights(vp_ctx* c, const VpPointLight* p, int np, const VpAreaLight* a, int na, const VpSpotLight* s, int ns,
                   const VpDirLight* d, int area_samples)
 {
+  KIDS(vp_set_lights(k, p, np, a, na, s, ns, d, area_samples))
   if (!c || np < 0 || na < 0 || ns < 0 || (np && !p) || (na && !a) || (ns && !s)) return fail(VP_EINVAL, "bad arguments to vp_set_lights");
   if (bind(c) || quiesce(c)) return VP_ECUDA;
   if (upload_array(c, c->d_pl, p, np) || upload_array(c, c->d_al, a, na) || upload_array(c, c->d_sl, s, ns)) return VP_ECUDA;
@@ -934,6 +1009,7 @@ int vp_set_lights(vp_ctx* c, const VpPointLight* p, int np, const VpAreaLight* a
 
 int vp_set_prims(vp_ctx* c, const VpSphere* s, int ns, const VpTriangle* t, int nt)
 {
+  KIDS(vp_set_prims(k, s, ns, t, nt))
   if (!c || ns < 0 || nt < 0 || (ns && !s) || (nt && !t)) return fail(VP_EINVAL, "bad arguments to vp_set_prims");
   if (bind(c) || quiesce(c)) return VP_ECUDA;
   if (upload_array(c, c->d_sph, s, ns) || upload_array(c, c->d_tri, t, nt)) return VP_ECUDA;
@@ -944,6 +1020,7 @@ int vp_set_prims(vp_ctx* c, const VpSphere* s, int ns, const VpTriangle* t, int 
 
 int vp_set_sky(vp_ctx* c, const float* rgb, int w, int h, float contribution, int active)
 {
+  KIDS(vp_set_sky(k, rgb, w, h, contribution, active))
   if (!c || w < 0 || h < 0) return fail(VP_EINVAL, "bad arguments to vp_set_sky");
   if (bind(c) || quiesce(c)) return VP_ECUDA;
   const bool have = rgb && w > 0 && h > 0;
@@ -965,6 +1042,7 @@ int vp_render_device(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, vo
 {
   if (int rc = check_frame(c, cam, fp)) return rc;
   if (!accum_dev) return fail(VP_EINVAL, "null accumulator");
+  if (c->group) return g_render_device(c, cam, fp, accum_dev, rgb8_dev, (cudaStream_t)stream, stats);
   if (bind(c)) return VP_ECUDA;
   return launch_render(c, cam, fp, (float4*)accum_dev, (uint32_t*)rgb8_dev, (cudaStream_t)stream, stats, true);
 }
@@ -972,6 +1050,7 @@ int vp_render_device(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, vo
 int vp_render_fence(vp_ctx* c, void* stream, int frames_back)
 {
   if (!c || frames_back < 0 || frames_back >= kCallRing) return fail(VP_EINVAL, "bad arguments to vp_render_fence (frames_back %d, at most %d)", frames_back, kCallRing - 1);
+  if (c->group) return g_render_fence(c, (cudaStream_t)stream, frames_back);
   if (bind(c)) return VP_ECUDA;
   if ((unsigned long long)frames_back >= c->ncalls) return 0;  // nothing that old was ever enqueued
   CU(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_call[(c->ncalls - 1 - (unsigned long long)frames_back) % kCallRing], 0));
@@ -990,6 +1069,7 @@ static int check_reproject(const vp_ctx* c, const VpCamera* cam, const VpPrevCam
 int vp_render_reproject_device(vp_ctx* c, const VpCamera* cam, const VpPrevCamera* prev, const VpFrameParams* fp, const void* history_in_dev,
                                void* history_out_dev, void* rgb8_dev, void* stream, VpStats* stats)
 {
+  KID0(vp_render_reproject_device(k, cam, prev, fp, history_in_dev, history_out_dev, rgb8_dev, stream, stats))
   if (int rc = check_reproject(c, cam, prev, fp)) return rc;
   if (!history_in_dev || !history_out_dev || history_in_dev == history_out_dev) return fail(VP_EINVAL, "history in/out must be two distinct buffers");
   if (bind(c)) return VP_ECUDA;
@@ -1006,6 +1086,7 @@ int vp_render_reproject_device(vp_ctx* c, const VpCamera* cam, const VpPrevCamer
 int vp_render_reproject(vp_ctx* c, const VpCamera* cam, const VpPrevCamera* prev, const VpFrameParams* fp, const float* history_in,
                         float* history_out, uint32_t* rgb8, float* albedo, float* illumination, VpStats* stats)
 {
+  KID0(vp_render_reproject(k, cam, prev, fp, history_in, history_out, rgb8, albedo, illumination, stats))
   if (int rc = check_reproject(c, cam, prev, fp)) return rc;
   if (!history_in || !history_out || history_in == history_out) return fail(VP_EINVAL, "history in/out must be two distinct buffers");
   if (bind(c) || quiesce(c)) return VP_ECUDA;
@@ -1026,6 +1107,7 @@ int vp_render_reproject(vp_ctx* c, const VpCamera* cam, const VpPrevCamera* prev
 
 int vp_accum_reset(vp_ctx* c, int w, int h)
 {
+  KID0(vp_accum_reset(k, w, h))
   if (!c || w <= 0 || h <= 0) return fail(VP_EINVAL, "bad arguments to vp_accum_reset");
   if (bind(c) || quiesce(c)) return VP_ECUDA;
   const size_t n = (size_t)w * h;
@@ -1041,6 +1123,11 @@ int vp_accum_reset(vp_ctx* c, int w, int h)
 int vp_render_resident(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, VpStats* stats)
 {
   if (int rc = check_frame(c, cam, fp)) return rc;
+  if (c->group) {  // the resident accumulator lives on the first device; the others reach it through peer access
+    vp_ctx* k = c->kids[0];
+    if (k->acc_w != fp->width || k->acc_h != fp->height) return fail(VP_ESTATE, "vp_accum_reset(%d,%d) must precede vp_render_resident", fp->width, fp->height);
+    return g_render_device(c, cam, fp, k->d_accum.p, k->d_rgb8.p, k->stream, stats);
+  }
   if (c->acc_w != fp->width || c->acc_h != fp->height) return fail(VP_ESTATE, "vp_accum_reset(%d,%d) must precede vp_render_resident", fp->width, fp->height);
   if (bind(c)) return VP_ECUDA;
   return launch_render(c, cam, fp, c->d_accum.p, c->d_rgb8.p, c->stream, stats, false);
@@ -1048,6 +1135,11 @@ int vp_render_resident(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, 
 
 int vp_accum_download(vp_ctx* c, float* accum, uint32_t* rgb8)
 {
+  if (c && c->group) {
+    for (vp_ctx* k : c->kids)
+      if (bind(k) || quiesce(k)) return VP_ECUDA;
+    return vp_accum_download(c->kids[0], accum, rgb8);
+  }
   if (!c || c->acc_w <= 0) return fail(VP_ESTATE, "no resident accumulator");
   if (bind(c) || quiesce(c)) return VP_ECUDA;
   const size_t n = (size_t)c->acc_w * c->acc_h;
@@ -1061,32 +1153,20 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
 {
   if (int rc = check_frame(c, cam, fp)) return rc;
   if (!accum) return fail(VP_EINVAL, "null accumulator");
+  if (c->group) return g_render(c, cam, fp, accum, rgb8, stats);
   if (bind(c) || quiesce(c)) return VP_ECUDA;
   const size_t n = (size_t)fp->width * fp->height;
   CU(c->d_accum.reserve(n));
   CU(c->d_rgb8.reserve(n));
   c->acc_w = fp->width; c->acc_h = fp->height;
-  // Only the rows this call renders are moved: a contiguous row range, or - with interleaved row tiles whose
-  // height divides the frame - one strided 2-D copy over the owned tiles (pitch = stride tiles).
+  // Only the rows this call renders are moved (copy_rows)
   const int rb = (fp->row_begin == 0 && fp->row_end == 0) ? 0 : fp->row_begin;
   const int re = (fp->row_begin == 0 && fp->row_end == 0) ? fp->height : fp->row_end;
-  const bool tiled = fp->row_tile > 0 && fp->row_tile_stride > 1 && rb == 0 && re == fp->height && fp->height % fp->row_tile == 0;
+  const bool tiled = fp->row_tile > 0 && fp->row_tile_stride > 1;
   const size_t W = (size_t)fp->width;
-  auto xfer = [&](void* dst, const void* src, size_t elem, cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
-    if (tiled) {
-      const size_t chunk = (size_t)fp->row_tile * W * elem, pitch = chunk * (size_t)fp->row_tile_stride;
-      const size_t ntile = (size_t)fp->height / fp->row_tile;
-      const size_t owned = (ntile - fp->row_tile_phase + fp->row_tile_stride - 1) / fp->row_tile_stride;
-      const size_t off = chunk * (size_t)fp->row_tile_phase;
-      if (owned == 0) return cudaSuccess;
-      return cudaMemcpy2DAsync((char*)dst + off, pitch, (const char*)src + off, pitch, chunk, owned, kind, st);
-    }
-    const size_t off = (size_t)rb * W * elem, bytes = (size_t)(re > rb ? re - rb : 0) * W * elem;
-    if (bytes == 0) return cudaSuccess;
-    return cudaMemcpyAsync((char*)dst + off, (const char*)src + off, bytes, kind, st);
-  };
+  auto xfer = [&](void* dst, const void* src, size_t elem, cudaMemcpyKind kind, cudaStream_t st) -> int { return copy_rows(fp, dst, src, elem, kind, st); };
   // the accumulator is only read by the resolve stage: upload it on the copy stream while the frame is traced
-  CU(xfer(c->d_accum.p, accum, sizeof(float4), cudaMemcpyHostToDevice, c->copy));
+  if (int rc = xfer(c->d_accum.p, accum, sizeof(float4), cudaMemcpyHostToDevice, c->copy)) return rc;
   CU(cudaEventRecord(c->ev_copy, c->copy));
   c->wait_copy = true;
   VpStats local;
@@ -1096,8 +1176,8 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
   // pixel: the result does not depend on the cut.
   int nb = c->nlanes > 1 ? c->tune_bands : 1;  // more bands than lanes queue up on the lanes in turn
   if (nb > kCallRing) nb = kCallRing;
-  const bool wavefront = fp->max_bounces >= 0 && c->sc.area_samples <= kMaxAreaSamples && !c->tune_persistent &&
-                         !(fp->flags & (VP_FLAG_MEGAKERNEL | VP_FLAG_PERSISTENT | VP_FLAG_COUNT_STEPS | VP_FLAG_TIME_STAGES));
+  const bool wavefront = fp->max_bounces >= 0 && c->sc.area_samples <= kMaxAreaSamples &&
+                         !(fp->flags & (VP_FLAG_MEGAKERNEL | VP_FLAG_COUNT_STEPS | VP_FLAG_TIME_STAGES));
   if (tiled || !wavefront || fp->spp < 1 || (long long)(re - rb) * fp->width < c->tune_band_min_pixels || re - rb < 8 * nb) nb = 1;
   if (nb > 1) {
     VpStats* st = stats ? stats : &local;
@@ -1161,14 +1241,16 @@ int vp_render(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, float* ac
   }
   if (int rc = launch_render(c, cam, fp, c->d_accum.p, rgb8 ? c->d_rgb8.p : nullptr, c->stream, stats ? stats : &local, false)) return rc;
   if (c->wait_copy) { CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->wait_copy = false; }  // spp == 0: nothing consumed the upload
-  CU(xfer(accum, c->d_accum.p, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-  if (rgb8) CU(xfer(rgb8, c->d_rgb8.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (int rc = xfer(accum, c->d_accum.p, sizeof(float4), cudaMemcpyDeviceToHost, c->stream)) return rc;
+  if (rgb8)
+    if (int rc = xfer(rgb8, c->d_rgb8.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream)) return rc;
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
 int vp_trace_primary(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, VpHit* hits)
 {
+  KID0(vp_trace_primary(k, cam, fp, hits))
   if (int rc = check_frame(c, cam, fp)) return rc;
   if (!hits) return fail(VP_EINVAL, "null hits");
   if (bind(c)) return VP_ECUDA;
@@ -1203,6 +1285,7 @@ static int batch_common(vp_ctx* c, const VpRay* rays, int n, BatchParams& p)
 
 int vp_find_nearest(vp_ctx* c, const VpRay* rays, int n, VpHit* hits)
 {
+  KID0(vp_find_nearest(k, rays, n, hits))
   BatchParams p;
   if (int rc = batch_common(c, rays, n, p)) return rc;
   if (n == 0) return 0;
@@ -1218,6 +1301,7 @@ int vp_find_nearest(vp_ctx* c, const VpRay* rays, int n, VpHit* hits)
 
 int vp_find_nearest_player(vp_ctx* c, const VpRay* rays, int n, int current_chunk, VpHit* hits)
 {
+  KID0(vp_find_nearest_player(k, rays, n, current_chunk, hits))
   BatchParams p;
   if (int rc = batch_common(c, rays, n, p)) return rc;
   if (n == 0) return 0;
@@ -1235,6 +1319,15 @@ int vp_find_nearest_player(vp_ctx* c, const VpRay* rays, int n, int current_chun
 int vp_in_light(vp_ctx* c, int* in_light)
 {
   if (!c || !in_light) return fail(VP_EINVAL, "bad arguments to vp_in_light");
+  if (c->group) {  // any device may have shaded the player-volume smoke hit
+    *in_light = 0;
+    for (vp_ctx* k : c->kids) {
+      int v = 0;
+      if (int rc = vp_in_light(k, &v)) return rc;
+      *in_light |= v;
+    }
+    return 0;
+  }
   if (bind(c) || quiesce(c)) return VP_ECUDA;
   CU(cudaDeviceSynchronize());
   unsigned long long now = 0;
@@ -1246,6 +1339,7 @@ int vp_in_light(vp_ctx* c, int* in_light)
 
 int vp_focus_distance(vp_ctx* c, const VpCamera* cam, int width, int height, uint32_t seed, float* focal_distance)
 {
+  KID0(vp_focus_distance(k, cam, width, height, seed, focal_distance))
   if (!c || !cam || !focal_distance || width <= 0 || height <= 0) return fail(VP_EINVAL, "bad arguments to vp_focus_distance");
   if (!c->have_volumes) return fail(VP_ESTATE, "vp_set_volumes has not been called");
   if (bind(c)) return VP_ECUDA;
@@ -1264,6 +1358,7 @@ int vp_focus_distance(vp_ctx* c, const VpCamera* cam, int width, int height, uin
 
 int vp_is_occluded(vp_ctx* c, const VpRay* rays, int n, uint8_t* out)
 {
+  KID0(vp_is_occluded(k, rays, n, out))
   BatchParams p;
   if (int rc = batch_common(c, rays, n, p)) return rc;
   if (n == 0) return 0;
@@ -1279,6 +1374,7 @@ int vp_is_occluded(vp_ctx* c, const VpRay* rays, int n, uint8_t* out)
 
 int vp_trace(vp_ctx* c, const VpRay* rays, const uint32_t* seeds, int n, int depth, float* rgb)
 {
+  KID0(vp_trace(k, rays, seeds, n, depth, rgb))
   BatchParams p;
   if (int rc = batch_common(c, rays, n, p)) return rc;
   if (n == 0) return 0;
@@ -1299,6 +1395,7 @@ int vp_trace(vp_ctx* c, const VpRay* rays, const uint32_t* seeds, int n, int dep
 
 int vp_stats_begin(vp_ctx* c)
 {
+  KIDS(vp_stats_begin(k))
   if (!c) return fail(VP_EINVAL, "null context");
   if (bind(c)) return VP_ECUDA;
   CU(cudaDeviceSynchronize());
@@ -1311,6 +1408,7 @@ int vp_stats_begin(vp_ctx* c)
 int vp_stats_end(vp_ctx* c, VpStats* stats)
 {
   if (!c || !stats) return fail(VP_EINVAL, "bad arguments to vp_stats_end");
+  if (c->group) return g_stats_end(c, stats);
   if (bind(c)) return VP_ECUDA;
   CU(cudaDeviceSynchronize());
   unsigned long long h[8];
@@ -1328,6 +1426,7 @@ int vp_stats_end(vp_ctx* c, VpStats* stats)
 
 int vp_stage_times(vp_ctx* c, double* extend_ms, uint64_t* extend_launches)
 {
+  KID0(vp_stage_times(k, extend_ms, extend_launches))
   if (!c || !extend_ms || !extend_launches) return fail(VP_EINVAL, "bad arguments to vp_stage_times");
   if (bind(c)) return VP_ECUDA;
   CU(cudaDeviceSynchronize());
@@ -1346,6 +1445,9 @@ int vp_stage_times(vp_ctx* c, double* extend_ms, uint64_t* extend_launches)
 int vp_info(vp_ctx* c, char* buf, int cap)
 {
   if (!c || !buf || cap <= 0) return fail(VP_EINVAL, "bad arguments to vp_info");
+  const int ndev = c->group ? (int)c->kids.size() : 1;
+  const bool peer = c->group ? c->peer_ok : false;
+  if (c->group) c = c->kids[0];  // the figures of the first device (all devices hold the same scene and lanes)
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) return fail(VP_ECUDA, "cudaGetDeviceProperties failed");
   cudaFuncAttributes fa, fe, fs, fh;
@@ -1354,16 +1456,27 @@ int vp_info(vp_ctx* c, char* buf, int cap)
   cudaFuncGetAttributes(&fs, k_wf_shadow<false, true>);
   cudaFuncGetAttributes(&fh, k_wf_shade<false>);
   unsigned long long dbg[16] = {0};
+  if (bind(c)) return VP_ECUDA;
   cudaDeviceSynchronize();
   cudaMemcpy(dbg, c->d_counters.p, sizeof(dbg), cudaMemcpyDeviceToHost);
+  // HBM held by this context on one device: scene, per-lane path state, frame buffers
+  size_t scene = c->d_regions.cap * 8 + c->d_sky.cap * 4 + 256 * sizeof(VpMaterial), lanes = 0, frames = 0;
+  for (const HostVolume& v : c->vols) scene += (size_t)v.n * v.n * v.n + ((size_t)64 << (3 * v.jr)) * 8;
+  int lanes_held = 0;
+  unsigned long long updates = 0, replays = 0;
+  for (const WfLane& L : c->lane) { lanes += L.d_wf.p ? L.d_wf.cap : 0; lanes_held += L.d_wf.p ? 1 : 0; updates += L.pg.updates; replays += L.pg.replays; }
+  frames = c->d_accum.cap * sizeof(float4) + c->d_rgb8.cap * 4 + (c->d_rp_alb.cap + c->d_rp_ill.cap + c->d_rp_hist_in.cap + c->d_rp_hist_out.cap) * 4 +
+           c->d_rp_ray.cap * sizeof(float4);
   snprintf(buf, (size_t)cap,
-           "{\"device\": %d, \"name\": \"%s\", \"sm\": \"%d.%d\", \"sm_count\": %d, \"blocks_per_sm\": %d, \"block\": %d, "
+           "{\"device\": %d, \"devices\": %d, \"peer_access\": %s, \"name\": \"%s\", \"sm\": \"%d.%d\", \"sm_count\": %d, \"blocks_per_sm\": %d, \"block\": %d, "
            "\"k_render_regs\": %d, \"k_render_local_bytes\": %zu, \"k_wf_extend_regs\": %d, \"k_wf_shadow_regs\": %d, "
-           "\"k_wf_shade_regs\": %d, \"wf_blocks_extend\": %d, \"wf_blocks_shadow\": %d, \"volumes\": %d, \"max_levels\": %d, "
-           "\"region_words_staged\": %d, \"dbg_extend_steps_in_empty_region\": %llu, \"dbg_extend_steps_in_empty_brick\": %llu, \"extend_steps\": %llu}",
-           c->device, prop.name, prop.major, prop.minor, c->sm_count, c->blocks_per_sm, kBlock, fa.numRegs, fa.localSizeBytes,
-           fe.numRegs, fs.numRegs, fh.numRegs, c->wf_blocks_extend, c->wf_blocks_shadow, c->sc.nvol, VP_MAX_LEVELS,
-           c->sc.region_words, dbg[9], dbg[10], dbg[11]);
+           "\"k_wf_shade_regs\": %d, \"k_wf_shade_local_bytes\": %zu, \"wf_blocks_extend\": %d, \"wf_blocks_shadow\": %d, \"volumes\": %d, \"max_levels\": %d, "
+           "\"region_words_staged\": %d, \"dbg_extend_steps_in_empty_region\": %llu, \"dbg_extend_steps_in_empty_brick\": %llu, \"extend_steps\": %llu, "
+           "\"hbm_scene_bytes\": %zu, \"hbm_lane_bytes\": %zu, \"hbm_frame_bytes\": %zu, \"hbm_in_use\": %zu, \"lanes\": %d, \"lanes_allocated\": %d, "
+           "\"graph_replays\": %llu, \"graph_node_updates\": %llu}",
+           c->device, ndev, peer ? "true" : "false", prop.name, prop.major, prop.minor, c->sm_count, c->blocks_per_sm, kBlock, fa.numRegs, fa.localSizeBytes,
+           fe.numRegs, fs.numRegs, fh.numRegs, fh.localSizeBytes, c->wf_blocks_extend, c->wf_blocks_shadow, c->sc.nvol, VP_MAX_LEVELS,
+           c->sc.region_words, dbg[9], dbg[10], dbg[11], scene, lanes, frames, scene + lanes + frames, c->nlanes, lanes_held, replays, updates);
   return 0;
 }
 

@@ -58,22 +58,21 @@ struct WfState {
   uint32_t* h1;  // hit: (vol + 2) << 8; primitive hits: mat (8) | 1 << 8 | inside << 30 | 1 << 31
   float4* hn;    // primitive hits only: normal
   float4* term;  // terminal radiance (sky / emissive / 0)
-  float4* lm;    // [level][path]: M.xyz, w = type bits
-  float4* la;    // [level][path]: A.xyz
-  // shadow requests, one slot per (level, path): the shadow stage of a bounce may run long after the
-  // path has been extended and shaded again (side stream / persistent kernel)
+  // fold levels, ONE record per (level, path): w = type (bits 0..2) | material (bits 8..15); xyz = M for type 0 (the
+  // multiplier is a computed colour), else A (the light term; M is then the material's albedo, looked up by the resolve
+  // stage) - half the bytes of separate M / A arrays
+  float4* lv;
+  // shadow requests, one slot per (bounce parity, path): shadow(k) runs on the lane's side stream while the path is
+  // extended and shaded again; shade(k + 2) waits for it before it reuses the slot
   uint32_t nsamp;   // samples allocated per request (>= area_samples)
-  float4* sq0;      // [level][path]: origin.xyz, w = bits nsamp(8) | level(8) << 8 | area(1) << 16 | mat(8) << 24
-  float4* sqd;      // [level][sample][path]: dir.xyz, w = dist
-  float4* sql;      // [level][sample][path]: li.xyz (single lights: final contribution), w = valid
+  float4* sq0;      // [parity][path]: origin.xyz, w = bits nsamp(8) | level(5) << 8 | type(3) << 13 | area(1) << 16 | mat(8) << 24
+  float4* sqd;      // [parity][sample][path]: dir.xyz, w = dist
+  float4* sql;      // [parity][sample][path]: li.xyz (single lights: final contribution), w = valid
   uint32_t* smask;      // [sample][path]: volumes that pass the bounding-sphere pre-test for the shadow ray (k_wf_shadow_mask)
   float4* ps[3];        // prepared walks [queue position]: 0 = tmax.xyz, t; 1 = tdelta.xyz, P' bits; 2 = E.xyz, flags (k_wf_prepare)
   uint32_t* q[2];       // active-path queues (ping-pong)
   uint32_t* qs[2];      // shadow-request queues (bounce parity)
   uint32_t* counts;     // [iter][4]: 0 = active count entering iter, 1 = shadow count of iter, 2 = extend cursor, 3 = shadow cursor
-  // persistent pipeline (vp_persistent.cuh): append-only queues 0 extend / 1 shade / 2 shadow + control block
-  uint32_t* pq[3];
-  uint32_t* pctl;
 };
 
 struct WfParams {
@@ -89,7 +88,10 @@ struct WfParams {
   int iter;              // bounce iteration of this launch
   int refill;            // lanes still walking below which idle lanes refill from the queue
   int bulk;              // with at most this many lanes walking, lanes in empty 8^3/16^3 blocks bulk-advance
-  int persistent;        // 1: generate feeds the persistent kernel's extend queue
+  // compact path ids: only the 4-row tile rows a pass can own get ids, so a row band or one rank's share of the frame
+  // sizes (and scans) a quarter / an eighth of the path state.  cmode 0: tile row = j; 1: j + ctrow0 (row range);
+  // 2: interleaved row tiles of ck tile rows each: tile row = ((j / ck) * row_tile_stride + row_tile_phase) * ck + j % ck
+  int cmode, ctrow0, ck;
   int prepared;          // 1: k_wf_prepare has set up the first walk of every ray of the bounce
   int write_rgb8;
   float4* accum;
@@ -119,13 +121,17 @@ __device__ __forceinline__ bool wf_row_selected(const WfParams& p, int y)
   if (wf_row_owned(p, y)) return true;
   return p.halo && ((y > 0 && wf_row_owned(p, y - 1)) || (y + 1 < p.H && wf_row_owned(p, y + 1)));
 }
-// path id <-> pixel: 8x4 tiles in row-major tile order, lane = position inside the tile
+// path id <-> pixel: 8x4 tiles in row-major tile order over the tile rows the pass can own (WfParams.cmode), lane =
+// position inside the tile
 __device__ __forceinline__ bool wf_pixel_of(const WfParams& p, uint32_t path, int& x, int& y)
 {
   const uint32_t tiles_x = (uint32_t)(p.W + 7) / 8u;
   const uint32_t tile = path >> 5, lane = path & 31u;
+  uint32_t trow = tile / tiles_x;
+  if (p.cmode == 1) trow += (uint32_t)p.ctrow0;
+  else if (p.cmode == 2) { const uint32_t k = (uint32_t)p.ck; trow = ((trow / k) * (uint32_t)p.row_tile_stride + (uint32_t)p.row_tile_phase) * k + trow % k; }
   x = (int)((tile % tiles_x) * 8u + (lane & 7u));
-  y = (int)((tile / tiles_x) * 4u + (lane >> 3));
+  y = (int)(trow * 4u + (lane >> 3));
   return x < p.W && y < p.H && wf_row_selected(p, y);
 }
 __device__ __forceinline__ Staged wf_stage_scene(const DScene& sc, unsigned char* smem)
@@ -199,17 +205,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant_
       active = p.max_bounces >= 0;  // Trace(depth < 0) returns before FindNearest, renderer.cpp:1080
       if (active) launched++;
     }
-    if (p.persistent) {
-      // extend queue of the persistent kernel (slot 0 = tail word of the control block); every path is pending work
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, active);
-      if (m) {
-        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-        uint32_t base = 0;
-        if (lane == leader) { atomicAdd(p.st.pctl + 192, (uint32_t)__popc(m)); base = atomicAdd(p.st.pctl + 0, (uint32_t)__popc(m)); }
-        base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        if (active) p.st.pq[0][base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = path;
-      }
-    } else wf_push(p.st.q[0], p.st.counts + 0, active, path);
+    wf_push(p.st.q[0], p.st.counts + 0, active, path);
   }
   wf_add_counter(p.counters + 4, launched);
 }
@@ -413,7 +409,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
 // Illumination() would run, a shadow request (the RNG draws of the light sample happen here, in
 // the reference's order; only the occlusion tests are deferred to K4).
 template <bool CS>
-__device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t path, int level, const Ray& ray, uint32_t& seed,
+__device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t path, int level, int type, const Ray& ray, uint32_t& seed,
                                                  bool& queued, f3& A_now)
 {
   const DScene& sc = p.sc;
@@ -426,9 +422,11 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
   queued = false;
   A_now = muls(v3s(0), (float)lightCount);
   const uint32_t cap = p.st.cap;
-  float4* const sq0 = p.st.sq0 + (size_t)level * cap;
-  float4* const sqd = p.st.sqd + (size_t)level * p.st.nsamp * cap;
-  float4* const sql = p.st.sql + (size_t)level * p.st.nsamp * cap;
+  const size_t slot = (size_t)(level & 1);  // in the staged pipeline the level of a request is the bounce index
+  float4* const sq0 = p.st.sq0 + slot * cap;
+  float4* const sqd = p.st.sqd + slot * p.st.nsamp * cap;
+  float4* const sql = p.st.sql + slot * p.st.nsamp * cap;
+  const uint32_t tag = ((uint32_t)level << 8) | ((uint32_t)type << 13) | ((uint32_t)(ray.mat & 255) << 24);
   if (idx >= (uint32_t)sc.npl && idx < (uint32_t)(sc.nal + sc.npl)) {
     const VpAreaLight L = sc.al[idx - sc.npl];
     const f3 center = ld3(L.position);
@@ -455,8 +453,7 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
       sql[(size_t)i * cap + path] = make_float4(li.x, li.y, li.z, valid ? 1.0f : 0.0f);
     }
     if (nvalid > 0) {
-      sq0[path] = make_float4(point.x, point.y, point.z,
-                                   __uint_as_float((uint32_t)sc.area_samples | ((uint32_t)level << 8) | (1u << 16) | ((uint32_t)(ray.mat & 255) << 24)));
+      sq0[path] = make_float4(point.x, point.y, point.z, __uint_as_float((uint32_t)sc.area_samples | (1u << 16) | tag));
       queued = true;
     } else {
       // inc = (0 / n) * k * lightCount, as the reference computes it
@@ -495,7 +492,7 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
     }
     if (lit) {
       const f3 org = offset_ray(ip, n);
-      sq0[path] = make_float4(org.x, org.y, org.z, __uint_as_float(1u | ((uint32_t)level << 8) | ((uint32_t)(ray.mat & 255) << 24)));
+      sq0[path] = make_float4(org.x, org.y, org.z, __uint_as_float(1u | tag));
       sqd[path] = make_float4(dirn.x, dirn.y, dirn.z, tshadow);
       sql[path] = make_float4(contrib.x, contrib.y, contrib.z, 1.0f);
       queued = true;
@@ -636,9 +633,11 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
       L.type = 2; L.mx = al.x; L.my = al.y; L.mz = al.z;
     }
     f3 A = v3s(0);
-    if (illum) { wf_light_request<CS>(p, path, top, ray, seed, want_shadow, A); level = top; }
-    __stcg(p.st.lm + (size_t)top * cap + path, make_float4(L.mx, L.my, L.mz, __int_as_float(L.type)));
-    __stcg(p.st.la + (size_t)top * cap + path, make_float4(A.x, A.y, A.z, 0));
+    if (illum) { wf_light_request<CS>(p, path, top, L.type, ray, seed, want_shadow, A); level = top; }
+    // one record per level: the multiplier itself for type 0, else the light term (the shadow stage overwrites it when the
+    // sample was queued) - M is then the material's albedo, which the resolve stage looks up again
+    const f3 rec = L.type == 0 ? v3(L.mx, L.my, L.mz) : A;
+    __stcg(p.st.lv + (size_t)top * cap + path, make_float4(rec.x, rec.y, rec.z, __uint_as_float((uint32_t)L.type | ((uint32_t)(m & 255) << 8))));
     top++; depth--;
     cont = depth >= 0 && top < VP_MAX_LEVELS;  // Trace(depth < 0) returns 0: term stays 0
     if (cont) {
@@ -694,9 +693,9 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow_mask(const __grid_consta
   const uint32_t cap = p.st.cap;
   const int nvol = p.sc.nvol;
   const uint32_t* queue = p.st.qs[p.iter & 1];
-  const float4* const sq0 = p.st.sq0 + (size_t)p.iter * cap;
-  const float4* const sqd = p.st.sqd + (size_t)p.iter * p.st.nsamp * cap;
-  const float4* const sql = p.st.sql + (size_t)p.iter * p.st.nsamp * cap;
+  const float4* const sq0 = p.st.sq0 + (size_t)(p.iter & 1) * cap;
+  const float4* const sqd = p.st.sqd + (size_t)(p.iter & 1) * p.st.nsamp * cap;
+  const float4* const sql = p.st.sql + (size_t)(p.iter & 1) * p.st.nsamp * cap;
   for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
     const uint32_t path = queue[qi];
     const float4 q0 = sq0[path];
@@ -730,9 +729,9 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow(const __grid_const
   const int nvol = sc.nvol;
   const float lightCount = (float)(uint32_t)(sc.npl + sc.nsl + sc.nal + 1);
   const int par = p.iter & 1;
-  const float4* const sq0 = p.st.sq0 + (size_t)p.iter * cap;  // staged pipeline: the request level is the bounce index
-  const float4* const sqd = p.st.sqd + (size_t)p.iter * p.st.nsamp * cap;
-  const float4* const sql = p.st.sql + (size_t)p.iter * p.st.nsamp * cap;
+  const float4* const sq0 = p.st.sq0 + (size_t)par * cap;  // the request slot of this bounce (its level is the bounce index)
+  const float4* const sqd = p.st.sqd + (size_t)par * p.st.nsamp * cap;
+  const float4* const sql = p.st.sql + (size_t)par * p.st.nsamp * cap;
   const bool use_mask = BWK && p.prepared && nvol > 1 && nvol <= 32;  // k_wf_shadow_mask ran for this bounce
   uint32_t cand = 0;
   bool has_req = false, has_ray = false, in_dda = false, exhausted = false;
@@ -821,8 +820,8 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow(const __grid_const
             t = mul(t, albedo_of(sc, (int)(bits >> 24)));
             A = muls(t, lightCount);
           } else A = muls(inc, lightCount);
-          const uint32_t level = (bits >> 8) & 255u;
-          p.st.la[(size_t)level * cap + path] = make_float4(A.x, A.y, A.z, 0);
+          const uint32_t level = (bits >> 8) & 31u;
+          p.st.lv[(size_t)level * cap + path] = make_float4(A.x, A.y, A.z, __uint_as_float(((bits >> 13) & 7u) | ((bits >> 24) << 8)));
           has_req = false;
           break;
         }
@@ -878,7 +877,6 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow(const __grid_const
 __global__ void __launch_bounds__(kWfBlock) k_wf_resolve(const __grid_constant__ WfParams p)
 {
   const uint32_t cap = p.st.cap;
-  if (p.persistent && blockIdx.x == 0 && threadIdx.x < 3) p.st.pctl[256 + threadIdx.x] = p.st.pctl[64 * threadIdx.x];  // tails -> kPrevTails
   for (uint32_t path = blockIdx.x * blockDim.x + threadIdx.x; path < cap; path += gridDim.x * blockDim.x) {
     int x, y;
     if (!wf_pixel_of(p, path, x, y)) continue;
@@ -887,25 +885,28 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_resolve(const __grid_constant__
     const float4 t4 = p.st.term[path];
     f3 R = v3(t4.x, t4.y, t4.z);
     for (int l = top - 1; l >= (p.reproject ? 1 : 0); l--) {
-      const float4 m4 = p.st.lm[(size_t)l * cap + path];
-      const float4 a4 = p.st.la[(size_t)l * cap + path];
-      const int type = __float_as_int(m4.w);
-      const f3 M = v3(m4.x, m4.y, m4.z), A = v3(a4.x, a4.y, a4.z);
-      if (type == 0) R = mul(R, M);
-      else if (type == 1) R = add(add(v3s(0), A), mul(R, M));
-      else if (type == 2) R = mul(add(R, A), M);
-      else if (type == 4) R = mul(add(add(v3s(0), A), R), M);  // TraceNonMetal: albedo * ((0 + incLight) + child)
+      const float4 v4 = __ldcs(p.st.lv + (size_t)l * cap + path);
+      const uint32_t w = __float_as_uint(v4.w);
+      const int type = (int)(w & 7u);
+      const f3 V = v3(v4.x, v4.y, v4.z);  // M for type 0, A otherwise
+      if (type == 0) R = mul(R, V);
+      else if (type != 3) {
+        const f3 M = albedo_of(p.sc, (int)((w >> 8) & 255u));
+        if (type == 1) R = add(add(v3s(0), V), mul(R, M));
+        else if (type == 2) R = mul(add(R, V), M);
+        else R = mul(add(add(v3s(0), V), R), M);  // type 4, TraceNonMetal: albedo * ((0 + incLight) + child)
+      }
     }
     if (p.reproject) {
       // the first hit keeps albedo and illumination apart (AlbedoIlluminationData of the primary ray, renderer.cpp:2013-2018)
       f3 alb = R, ill = v3s(1.0f);  // miss / emissive: {colour, 1}
       if (top > 0) {
-        const float4 m4 = p.st.lm[path];
-        const float4 a4 = p.st.la[path];
-        const int type = __float_as_int(m4.w);
-        const f3 A = v3(a4.x, a4.y, a4.z);
-        alb = v3(m4.x, m4.y, m4.z);
-        ill = type == 0 ? R : (type == 4 ? add(add(v3s(0), A), R) : add(R, A));
+        const float4 v4 = p.st.lv[path];
+        const uint32_t w = __float_as_uint(v4.w);
+        const int type = (int)(w & 7u);
+        const f3 V = v3(v4.x, v4.y, v4.z);
+        alb = type == 0 ? V : (type == 3 ? v3s(1.0f) : albedo_of(p.sc, (int)((w >> 8) & 255u)));
+        ill = type == 0 ? R : (type == 4 ? add(add(v3s(0), V), R) : add(R, V));
       }
       p.rp_alb[3 * (size_t)px] = alb.x; p.rp_alb[3 * (size_t)px + 1] = alb.y; p.rp_alb[3 * (size_t)px + 2] = alb.z;
       p.rp_ill[3 * (size_t)px] = ill.x; p.rp_ill[3 * (size_t)px + 1] = ill.y; p.rp_ill[3 * (size_t)px + 2] = ill.z;

@@ -69,9 +69,14 @@ def frame_params(width, height, max_bounces=14, spp=1, frame_index=0, seed=0x123
 class Session:
     """One renderer context on one library (the analogue of one reference `Renderer`)."""
 
-    def __init__(self, lib: abi.Lib, device: int = -1):
+    def __init__(self, lib: abi.Lib, device=-1):
+        """device: a CUDA device index, or a list of indices for a multi-device context (vp_create_multi)."""
         self.lib = lib
-        self.ctx = lib.c_create(device)
+        if isinstance(device, (list, tuple)):
+            arr = (C.c_int * len(device))(*[int(d) for d in device])
+            self.ctx = lib.c_create_multi(arr, len(device))
+        else:
+            self.ctx = lib.c_create(device)
         if not self.ctx:
             msg = lib.c_last_error().decode() if lib.has("last_error") else ""
             raise abi.VpError(f"{lib.prefix}create failed: {msg}")
@@ -142,6 +147,24 @@ class Session:
         self.lib.check(self.lib.c_render(self.ctx, C.byref(cc), C.byref(fp), accum.ctypes.data,
                                          rgb8.ctypes.data if want_rgb8 else None, C.byref(st)), "render")
         return accum, rgb8, st
+
+    def render_async(self, cam: Camera, fp, accum_in, accum_out, rgb8_out):
+        """vp_render_async: returns the ticket; the arrays must stay alive and untouched until wait(ticket)."""
+        t = C.c_uint64()
+        cc = cam.to_c()
+        self.lib.check(self.lib.c_render_async(self.ctx, C.byref(cc), C.byref(fp), accum_in.ctypes.data if accum_in is not None else None,
+                                               accum_out.ctypes.data, rgb8_out.ctypes.data if rgb8_out is not None else None, C.byref(t)),
+                       "render_async")
+        return t.value
+
+    def wait(self, ticket):
+        self.lib.check(self.lib.c_render_wait(self.ctx, ticket), "render_wait")
+
+    def info(self):
+        import json
+        buf = C.create_string_buffer(4096)
+        self.lib.check(self.lib.c_info(self.ctx, buf, 4096), "info")
+        return json.loads(buf.value.decode())
 
     def render_reproject(self, cam: Camera, prev, fp, history=None, want_buffers=True):
         """One frame of the reprojection mode (Renderer::Tick static-camera branch).  prev: abi.VpPrevCamera;

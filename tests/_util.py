@@ -146,3 +146,40 @@ def side_channels(lib, width=96, height=54):
         out["focus"] = np.array([s.focus_distance(cam, width, height, sd) for sd in (1, 0x12345678, 0xDEADBEEF, 77)], np.float32)
         out["accum"] = acc
     return out
+
+
+# ---- round-2 parity scenes (tools/make_golden_r2.py writes their reference-build digests) ---------------------------
+def prims_scene(glass=False, width=160, height=90):
+    """cfg 4 (city, area + point lights) with analytic primitives through the whole render path (reference
+    renderer.cpp:994-1016, src/BVH/Shapes.h): three spheres and two triangles; with `glass`, two GLASS spheres in front of
+    them - rays refracted into a sphere carry isInsideGlass = 1 until a primitive hit overwrites it (renderer.cpp:1012)."""
+    sc, cam, fpd = small_config(4, width, height, spp=2, max_bounces=6)
+    sc.spheres = [((0.2, 0.6, -0.5), 0.3, 5), ((1.0, 0.4, 0.2), 0.25, 1), ((-0.8, 0.5, 0.1), 0.2, 20)]
+    sc.triangles = [((-0.5, 0, 0), (0, 0.6, 0), (0.5, 0, 0), (0.4, 0.1, -0.9), 7), ((-1, 0, 0), (0, 1, 0), (1, 0, 0), (0.0, 0.2, 3.5), 30)]
+    if glass:
+        sc.spheres = sc.spheres + [((0.3, 0.75, -1.3), 0.22, 8), ((0.75, 0.5, -1.0), 0.2, 8)]
+    return sc, cam, fpd
+
+
+def light_scene(kind, width=160, height=90):
+    """Light evaluation variants no BASELINE config reaches: 'dir' = only the directional light, coloured
+    (DirectionalLightEvaluate, reference renderer.cpp:315-338); 'area1' / 'area5' = cfg 4's area lights with
+    numCheckShadowsAreaLight 1 / 5 (AreaLightEvaluation, :163-207) next to the coloured directional light."""
+    sc, cam, fpd = small_config(4, width, height, spp=2, max_bounces=6)
+    sc.dir_light = (tuple(float(x) for x in host.normalize((-0.3, -0.8, 0.5))), (2.0, 1.8, 1.5))
+    if kind == "dir":
+        sc.point_lights, sc.area_lights, sc.spot_lights = [], [], []
+    else:
+        sc.area_shadow_samples = {"area1": 1, "area5": 5}[kind]
+    return sc, cam, fpd
+
+
+def frame_digest(acc, rgb8, st):
+    import hashlib
+    return dict(accum_sha256=hashlib.sha256(np.ascontiguousarray(acc).tobytes()).hexdigest(),
+                rgb8_sha256=hashlib.sha256(np.ascontiguousarray(rgb8).tobytes()).hexdigest(),
+                stats=[int(st.primary_rays), int(st.secondary_rays), int(st.shadow_rays), int(st.exit_rays)])
+
+
+R2_SMALL = {"prims": lambda: prims_scene(False), "prims_glass": lambda: prims_scene(True), "dir": lambda: light_scene("dir"),
+            "area1": lambda: light_scene("area1"), "area5": lambda: light_scene("area5")}

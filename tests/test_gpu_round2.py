@@ -1,0 +1,348 @@
+"""Round-2 GPU parity: what the round-1 tests did not discriminate, and the new entry points.
+
+* analytic primitives through the WAVEFRONT stages (k_wf_extend -> hn -> wf_shade_one's voxIndex == -1 branch ->
+  k_wf_shadow's prims_any), incl. rays that carry isInsideGlass into a primitive hit (reference renderer.cpp:994-1016);
+* a directional light that carries colour, area lights with 1 and 5 shadow samples (renderer.cpp:315-338,163-207);
+* equal-spp accumulation at BASELINE.json's sample counts (cfg 3: 16 spp at full size, cfg 5: 64 spp at 960x540);
+* CUDA against the reference build directly when oracle/_ref/libvpref.so travelled to the box;
+* vp_render_async / vp_render_wait, compact path ids (row ranges, ragged interleaved tiles), multi-device contexts,
+  images shared between processes, HBM footprint and graph-replay cost reported by vp_info.
+All comparisons are bit for bit (the north_star tolerances are 1e-3 abs / 1e-4 rel-L2; the fold keeps the reference's
+operation order, so nothing less than identity is accepted here)."""
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+from _util import GOLDEN, R2_SMALL, abi, bits, frame_digest, params, ref_lib, scenes, small_config, vp
+
+pytestmark = pytest.mark.gpu
+
+WANT = json.load(open(os.path.join(GOLDEN, "r2_digests.json")))
+COUNTERS = ("primary_rays", "secondary_rays", "shadow_rays", "exit_rays", "dda_steps", "sky_samples")
+
+
+def same_frame(a, b, what):
+    assert np.count_nonzero(bits(a[0]) != bits(b[0])) == 0, f"{what}: accumulator differs"
+    assert np.count_nonzero(a[1] != b[1]) == 0, f"{what}: rgb8 differs"
+
+
+@pytest.mark.parametrize("pipeline", ["staged_counting", "staged_graph", "megakernel"])
+@pytest.mark.parametrize("name", sorted(R2_SMALL))
+def test_r2_scenes(product, oracle, name, pipeline):
+    """The three formulations against the oracle (arrays + counters) and against the reference build's digests."""
+    sc, cam, fpd = R2_SMALL[name]()
+    flags = {"staged_counting": abi.VP_FLAG_COUNT_STEPS, "staged_graph": 0, "megakernel": abi.VP_FLAG_MEGAKERNEL | abi.VP_FLAG_COUNT_STEPS}[pipeline]
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        want = s.render(cam, params(fpd, flags=abi.VP_FLAG_COUNT_STEPS))
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        got = s.render(cam, params(fpd, flags=flags))  # spp = 2: the staged_graph variant runs prepared, graph-replayed passes
+    same_frame(got, want, f"{name}/{pipeline}")
+    for k in COUNTERS:
+        if k == "dda_steps" and not (flags & abi.VP_FLAG_COUNT_STEPS):
+            continue
+        assert getattr(got[2], k) == getattr(want[2], k), (name, pipeline, k)
+    d = frame_digest(*got)
+    for k in d:
+        assert d[k] == WANT[name][k], (name, pipeline, k, "reference-build digest")
+    if name.startswith("prims"):
+        assert got[2].shadow_rays > 0 and got[2].secondary_rays > 0
+
+
+@pytest.mark.parametrize("name,idx,size,spp", [("cfg3_16spp", 3, None, 16), ("cfg5_64spp_960x540", 5, (960, 540), 64)])
+def test_equal_spp_accumulation(product, name, idx, size, spp):
+    """Running-average weight chain 1 / (frame + 1) and lane rotation over many samples, against the reference build."""
+    sc, cam, fpd = scenes.config(idx) if size is None else small_config(idx, *size)
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        got = s.render(cam, params(fpd, spp=spp))
+        first = frame_digest(*got)
+        # the same samples as `spp` single-sample calls on a carried accumulator (what Update() per frame does)
+        acc = np.zeros_like(got[0])
+        if spp <= 16:
+            for f in range(spp):
+                acc, rgb8, _ = s.render(cam, params(fpd, spp=1, frame_index=f), accum=acc)
+            assert np.count_nonzero(bits(acc) != bits(got[0])) == 0 and np.count_nonzero(rgb8 != got[1]) == 0
+    for k in first:
+        assert first[k] == WANT[name][k], (name, k)
+
+
+def test_cuda_vs_reference_build_directly(product):
+    """No port in between: the CUDA library against the reference's own renderer.cpp / scene.cpp built headless
+    (oracle/_ref/libvpref.so), when that file is present on this box."""
+    ref = ref_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libvpref.so did not travel to this box")
+    from _util import assert_hits_equal, prims_scene
+    for what, (sc, cam, fpd) in (("cfg2", small_config(2, 192, 108, spp=2)), ("cfg3", small_config(3, 128, 72, spp=3)),
+                                 ("cfg4+prims", prims_scene(True)), ("cfg5", small_config(5, 128, 72, spp=1))):
+        res = []
+        for lib in (ref, product):
+            with vp.Session(lib) as s:
+                s.set_scene(sc)
+                res.append((s.trace_primary(cam, params(fpd)), s.render(cam, params(fpd))))
+        assert_hits_equal(res[0][0], res[1][0], what)
+        same_frame(res[1][1], res[0][1], what)
+        a, b = res[0][1][2], res[1][1][2]
+        assert (a.primary_rays, a.secondary_rays, a.shadow_rays, a.exit_rays) == (b.primary_rays, b.secondary_rays, b.shadow_rays, b.exit_rays)
+
+
+def test_bad_row_ranges_are_rejected(product):
+    sc, cam, fpd = small_config(1, 32, 18)
+    cc = cam.to_c()
+    acc = np.zeros((18, 32, 4), np.float32)
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        for rb, re in ((-1, 5), (5, 4), (0, 19), (18, 40)):
+            fp = params(fpd, row_begin=rb, row_end=re)
+            assert product.c_render(s.ctx, C.byref(cc), C.byref(fp), acc.ctypes.data, None, None) == abi.VP_EINVAL, (rb, re)
+            assert b"row range" in product.c_last_error()
+        fp = params(fpd, row_begin=18, row_end=18)  # empty but valid
+        product.check(product.c_render(s.ctx, C.byref(cc), C.byref(fp), acc.ctypes.data, None, None), "empty range")
+        assert not acc.any()
+
+
+@pytest.mark.parametrize("w,h,stride", [(160, 90, 3), (67, 41, 2), (96, 54, 8)])
+def test_compact_path_ids(product, oracle, w, h, stride):
+    """Row bands and interleaved row tiles get path ids of their own rows only.  Frame heights that are no multiple of the
+    8-row tile (ragged last tile), widths off the 8-pixel tile, row ranges off the 4-row path tile: shards rendered one
+    after the other into ONE host buffer (each call moves its own rows only) equal the whole frame."""
+    sc, cam, fpd = small_config(2, w, h, spp=2, max_bounces=5)
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        want = s.render(cam, params(fpd))
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        acc, rgb = np.zeros((h, w, 4), np.float32), np.zeros((h, w), np.uint32)
+        rays = 0
+        for ph in range(stride):
+            fp = params(fpd, row_tile=8, row_tile_stride=stride, row_tile_phase=ph)
+            st = abi.VpStats()
+            cc = cam.to_c()
+            product.check(product.c_render(s.ctx, C.byref(cc), C.byref(fp), acc.ctypes.data, rgb.ctypes.data, C.byref(st)), "render")
+            rays += st.rays
+        same_frame((acc, rgb), want, f"tiles x{stride}")
+        assert rays == want[2].rays
+        acc2, rgb2 = np.zeros((h, w, 4), np.float32), np.zeros((h, w), np.uint32)
+        edges = [0, 3, 10, h // 2 + 1, h]
+        for a, b in zip(edges[:-1], edges[1:]):
+            fp = params(fpd, row_begin=a, row_end=b)
+            cc = cam.to_c()
+            product.check(product.c_render(s.ctx, C.byref(cc), C.byref(fp), acc2.ctypes.data, rgb2.ctypes.data, None), "render")
+        same_frame((acc2, rgb2), want, "row ranges")
+        # tiles combined with a row range
+        acc3, rgb3 = np.zeros((h, w, 4), np.float32), np.zeros((h, w), np.uint32)
+        for a, b in ((0, 13), (13, h)):
+            for ph in range(2):
+                fp = params(fpd, row_begin=a, row_end=b, row_tile=8, row_tile_stride=2, row_tile_phase=ph)
+                cc = cam.to_c()
+                product.check(product.c_render(s.ctx, C.byref(cc), C.byref(fp), acc3.ctypes.data, rgb3.ctypes.data, None), "render")
+        same_frame((acc3, rgb3), want, "tiles x row ranges")
+
+
+def test_render_async(product, oracle):
+    """vp_render_async / vp_render_wait: frames enqueued back to back (same accumulator handed on, then two accumulators
+    alternated, page-locked through vp_host_register) equal the synchronous frames bit for bit; tickets, the ring limit
+    and the argument checks."""
+    sc, cam, fpd = small_config(3, 160, 90, max_bounces=6)
+    W, H, N = fpd["width"], fpd["height"], 20  # more frames than tickets in the ring
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        want = s.render(cam, params(fpd, spp=N))
+        want3 = s.render(cam, params(fpd, spp=3))
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        acc, rgb = np.zeros((H, W, 4), np.float32), np.zeros((H, W), np.uint32)
+        product.check(product.c_host_register(s.ctx, acc.ctypes.data, acc.nbytes), "host_register")
+        tickets = [s.render_async(cam, params(fpd, spp=1, frame_index=f), acc, acc, rgb) for f in range(N)]
+        assert tickets == list(range(1, N + 1))
+        s.wait(tickets[-1])
+        s.wait(tickets[0])  # long done
+        same_frame((acc, rgb), want, "async, one accumulator")
+        product.check(product.c_host_unregister(s.ctx, acc.ctypes.data), "host_unregister")
+        assert product.c_render_wait(s.ctx, N + 5) == abi.VP_EINVAL
+        # two accumulators alternated; the first frame starts from zeros, frame 3 continues from the device copy (accum_in = NULL)
+        A, B = np.zeros((H, W, 4), np.float32), np.full((H, W, 4), 7.0, np.float32)
+        ra, rb = np.zeros((H, W), np.uint32), np.zeros((H, W), np.uint32)
+        t0 = s.render_async(cam, params(fpd, spp=1, frame_index=0), A, B, rb)
+        t1 = s.render_async(cam, params(fpd, spp=1, frame_index=1), B, A, ra)
+        s.wait(t0)
+        first = B.copy()  # readable while frame 1 is in flight
+        t2 = s.render_async(cam, params(fpd, spp=1, frame_index=2), None, B, rb)
+        s.wait(t2)
+        same_frame((B, rb), want3, "async, alternating accumulators")
+        with vp.Session(oracle) as so:
+            so.set_scene(sc)
+            w1 = so.render(cam, params(fpd, spp=1))
+        assert np.count_nonzero(bits(first) != bits(w1[0])) == 0
+        # a synchronous call afterwards sees a quiet context
+        got = s.render(cam, params(fpd, spp=3))
+        same_frame(got, want3, "sync after async")
+
+
+def test_multi_device_context(product, oracle, monkeypatch):
+    """vp_create_multi: the library shards the frame itself.  On a one-GPU box the contexts of the group share the device
+    (VP_ALLOW_DUPLICATE_DEVICES test hook), which exercises the sharding, the per-device copies into one host buffer and
+    the peer-pointer path of vp_render_device; on a box with more GPUs the real devices are used."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    devices = list(range(min(ngpu, 4))) if ngpu >= 2 else [0, 0, 0]
+    if ngpu < 2:
+        monkeypatch.setenv("VP_ALLOW_DUPLICATE_DEVICES", "1")
+    for idx, (w, h) in ((2, (160, 90)), (4, (128, 72))):
+        sc, cam, fpd = small_config(idx, w, h, max_bounces=6)
+        with vp.Session(oracle) as s:
+            s.set_scene(sc)
+            want = s.render(cam, params(fpd, spp=3))
+            want_hits = s.trace_primary(cam, params(fpd))
+        with vp.Session(product, devices) as s:
+            assert product.c_device_count(s.ctx) == len(devices)
+            s.set_scene(sc)
+            got = s.render(cam, params(fpd, spp=3))
+            same_frame(got, want, f"group vp_render cfg{idx}")
+            assert got[2].rays == want[2].rays and got[2].kernel_launches > 0
+            # asynchronous frames on the group, accumulator handed on
+            acc, rgb = np.zeros((h, w, 4), np.float32), np.zeros((h, w), np.uint32)
+            ts = [s.render_async(cam, params(fpd, spp=1, frame_index=f), acc, acc, rgb) for f in range(3)]
+            s.wait(ts[-1])
+            same_frame((acc, rgb), want, f"group async cfg{idx}")
+            # device buffers on the first GPU: the other contexts store into them through peer pointers
+            dev = torch.device("cuda", devices[0])
+            dacc = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
+            drgb = torch.zeros((h, w), dtype=torch.int32, device=dev)
+            stream = torch.cuda.current_stream(dev)
+            cc = cam.to_c()
+            for f in range(3):
+                fp = params(fpd, spp=1, frame_index=f, flags=abi.VP_FLAG_DEFER)
+                product.check(product.c_render_device(s.ctx, C.byref(cc), C.byref(fp), dacc.data_ptr(), drgb.data_ptr(), stream.cuda_stream, None), "render_device")
+            product.check(product.c_render_fence(s.ctx, stream.cuda_stream, 0), "fence")
+            torch.cuda.synchronize(dev)
+            same_frame((dacc.cpu().numpy(), drgb.cpu().numpy().view(np.uint32)), want, f"group vp_render_device cfg{idx}")
+            # resident accumulator + download, seams on the first device, scene edits on all
+            product.check(product.c_accum_reset(s.ctx, w, h), "accum_reset")
+            fp = params(fpd, spp=3)
+            st = abi.VpStats()
+            product.check(product.c_render_resident(s.ctx, C.byref(cc), C.byref(fp), C.byref(st)), "render_resident")
+            racc, rrgb = np.zeros((h, w, 4), np.float32), np.zeros((h, w), np.uint32)
+            product.check(product.c_accum_download(s.ctx, racc.ctypes.data, rrgb.ctypes.data), "accum_download")
+            same_frame((racc, rrgb), want, f"group resident cfg{idx}")
+            assert st.rays == want[2].rays
+            from _util import assert_hits_equal
+            assert_hits_equal(s.trace_primary(cam, params(fpd)), want_hits, "group trace_primary")
+            info = s.info()
+            assert info["devices"] == len(devices)
+            bad = params(fpd, row_tile=8, row_tile_stride=2, row_tile_phase=0)
+            assert product.c_render(s.ctx, C.byref(cc), C.byref(bad), racc.ctypes.data, None, None) == abi.VP_EINVAL
+
+
+class _DevArray:
+    """A raw device pointer as a CUDA-array-interface object (so torch can read the shared image)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def _share_peer(info_bytes, cfg, w, h, frames, q):
+    """Second process of test_shared_image: maps the image, renders the odd row tiles into it, signals."""
+    try:
+        from _util import abi, params, small_config, vp
+        import torch
+        lib = vp.load_product()
+        info = abi.VpShareInfo.from_buffer_copy(info_bytes)
+        sc, cam, fpd = small_config(cfg, w, h, max_bounces=5)
+        with vp.Session(lib, 0) as s:
+            s.set_scene(sc)
+            sh = lib.c_share_open(s.ctx, C.byref(info))
+            assert sh, lib.c_last_error()
+            img = lib.c_share_ptr(sh)
+            dev = torch.device("cuda", 0)
+            acc = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
+            stream = torch.cuda.current_stream(dev)
+            cc = cam.to_c()
+            for f in range(frames):
+                fp = params(fpd, spp=1, frame_index=f, row_tile=8, row_tile_stride=2, row_tile_phase=1, flags=abi.VP_FLAG_DEFER)
+                lib.check(lib.c_render_device(s.ctx, C.byref(cc), C.byref(fp), acc.data_ptr(), img, stream.cuda_stream, None), "render_device")
+                lib.check(lib.c_render_fence(s.ctx, stream.cuda_stream, 0), "fence")
+                lib.check(lib.c_share_signal(sh, stream.cuda_stream, 1, f + 1), "signal")
+            torch.cuda.synchronize(dev)
+            lib.check(lib.c_share_close(sh), "close")
+        q.put("ok")
+    except Exception as e:  # pragma: no cover - reported to the parent
+        q.put(repr(e))
+
+
+def test_shared_image_between_processes(product, oracle):
+    """vp_share_*: two processes (here on one GPU; one per GPU in bench.py) render interleaved row tiles of the same
+    frames, the second one storing its RGB8 pixels straight into the image the first one owns (CUDA IPC mapping), ordered
+    by the system-scope arrival flags; the assembled image equals the whole frame.  Also: a wait whose peer never arrives
+    gives up instead of hanging the GPU."""
+    import torch
+    cfg, w, h, frames = 2, 160, 96, 3
+    sc, cam, fpd = small_config(cfg, w, h, max_bounces=5)
+    with vp.Session(oracle) as s:
+        s.set_scene(sc)
+        want = s.render(cam, params(fpd, spp=frames))
+    dev = torch.device("cuda", 0)
+    with vp.Session(product, 0) as s:
+        s.set_scene(sc)
+        info = abi.VpShareInfo()
+        sh = product.c_share_create(s.ctx, w * h * 4, C.byref(info))
+        assert sh, product.c_last_error()
+        img = product.c_share_ptr(sh)
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        peer = ctx.Process(target=_share_peer, args=(bytes(info), cfg, w, h, frames, q))
+        peer.start()
+        acc = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev)
+        cc = cam.to_c()
+        for f in range(frames):
+            fp = params(fpd, spp=1, frame_index=f, row_tile=8, row_tile_stride=2, row_tile_phase=0, flags=abi.VP_FLAG_DEFER)
+            product.check(product.c_render_device(s.ctx, C.byref(cc), C.byref(fp), acc.data_ptr(), img, stream.cuda_stream, None), "render_device")
+        product.check(product.c_render_fence(s.ctx, stream.cuda_stream, 0), "fence")
+        product.check(product.c_share_signal(sh, stream.cuda_stream, 0, frames), "signal")
+        product.check(product.c_share_wait(sh, stream.cuda_stream, 0, 2, frames, 60.0), "wait")  # both ranks have stored their last frame
+        out = torch.as_tensor(_DevArray(img, (h, w), "<i4"), device=dev).clone()  # on the stream that waited for the flags
+        torch.cuda.synchronize(dev)
+        msg = q.get(timeout=120)
+        peer.join(timeout=60)
+        assert msg == "ok", msg
+        err = C.c_uint32()
+        product.check(product.c_share_error(sh, C.byref(err)), "share_error")
+        assert err.value == 0
+        assert np.count_nonzero(out.cpu().numpy().view(np.uint32) != want[1]) == 0, "assembled image differs from the whole frame"
+        # a peer that never signals: the wait gives up after its timeout and reports the slot
+        product.check(product.c_share_wait(sh, stream.cuda_stream, 5, 1, 1, 0.2), "wait")
+        torch.cuda.synchronize(dev)
+        product.check(product.c_share_error(sh, C.byref(err)), "share_error")
+        assert err.value == 1 + 5
+        product.check(product.c_share_close(sh), "close")
+
+
+def test_footprint_and_graph_replay_cost(product):
+    """cfg 2 at full size with four frames in flight: the path state (one float4 per fold level, two request slots per
+    path, optional parts only when a scene needs them) stays below 6 GB, and a replayed frame rewrites the arguments of
+    the generate node only."""
+    import torch
+    sc, cam, fpd = scenes.config(2)
+    W, H = fpd["width"], fpd["height"]
+    dev = torch.device("cuda", 0)
+    acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    rgb = torch.zeros((H, W), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    cc = cam.to_c()
+    with vp.Session(product) as s:
+        s.set_scene(sc)
+        for f in range(24):
+            fp = params(fpd, spp=1, frame_index=f, flags=abi.VP_FLAG_DEFER)
+            product.check(product.c_render_device(s.ctx, C.byref(cc), C.byref(fp), acc.data_ptr(), rgb.data_ptr(), stream.cuda_stream, None), "render_device")
+        product.check(product.c_render_fence(s.ctx, stream.cuda_stream, 0), "fence")
+        torch.cuda.synchronize(dev)
+        info = s.info()
+    print({k: info[k] for k in ("hbm_scene_bytes", "hbm_lane_bytes", "hbm_frame_bytes", "hbm_in_use", "lanes", "lanes_allocated", "graph_replays", "graph_node_updates")})
+    assert info["lanes_allocated"] == 4 and info["hbm_in_use"] <= 6 * 2 ** 30
+    assert info["graph_replays"] >= 16 and info["graph_node_updates"] <= 2 * info["graph_replays"]

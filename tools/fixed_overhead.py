@@ -9,7 +9,7 @@ W, H = fpd["width"], fpd["height"]
 s = vp.Session(lib, 0); s.set_scene(sc); cc = cam.to_c()
 acc = torch.zeros((H, W, 4), device="cuda"); rgb = torch.zeros((H, W), dtype=torch.int32, device="cuda")
 st = torch.cuda.current_stream()
-for name, flags in (("persistent", abi.VP_FLAG_PERSISTENT), ("staged", 0)):
+for name, flags in (("staged", 0),):
     ts = []
     for i in range(13):
         fp = vp.frame_params(W, H, max_bounces=fpd["max_bounces"], spp=1, frame_index=i, seed=scenes.SEED, aa_strength=1.0,
