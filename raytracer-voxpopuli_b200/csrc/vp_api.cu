@@ -274,7 +274,7 @@ int check_frame(const vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp)
     return fail(VP_EINVAL, "bad row range [%d,%d) for a frame of %d rows", fp->row_begin, fp->row_end, fp->height);
   if (fp->row_tile > 0 && (fp->row_tile_stride <= 0 || fp->row_tile_phase < 0 || fp->row_tile_phase >= fp->row_tile_stride))
     return fail(VP_EINVAL, "bad row tile interleave %d/%d/%d", fp->row_tile, fp->row_tile_stride, fp->row_tile_phase);
-  if (!c->have_volumes) return fail(VP_ESTATE, "vp_set_volumes has not been called");
+  if (!(c->group ? (!c->kids.empty() && c->kids[0]->have_volumes) : c->have_volumes)) return fail(VP_ESTATE, "vp_set_volumes has not been called");
   return 0;
 }
 
