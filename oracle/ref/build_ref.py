@@ -41,6 +41,14 @@ own alternative code path; none of them introduces new arithmetic:
       The hit cell index and pre-matrix face are also recorded (Scene::FindNearest hit block,
       Ray::GetNormalVoxel) for the bit-exact primary-hit dumps.
   P11 the stdout print inside Trace's smoke branch (renderer.cpp:1238) is silenced.
+
+Two libraries are built from the same sources:
+  libvpref.so       all patches - the parity checker (DDA-step counters, hit cell / face records);
+  libvpref_fast.so  without P10e / P10f / P10g, i.e. nothing added inside the DDA loops (the per-step
+                    `++g_vp_cnt.steps` is a thread-local read-modify-write in the reference's hottest loop) -
+                    the build bench.py TIMES (--impl reference, cpu_baseline).  Its dda_steps counter reads 0
+                    and vpref_trace_primary reports no cell / face; the per-ray counters (one increment per
+                    Renderer::FindNearest / IsOccluded call) stay, they define the metric.
 """
 import os
 import re
@@ -75,7 +83,7 @@ def sub(text, pattern, repl, name, count=0, flags=0, expect=None):
     return new
 
 
-def patch(rel, text):
+def patch(rel, text, timing=False):
     text = text.lstrip("﻿")
     if rel.endswith(".cpp"):
         text = re.sub(r'#include "precomp.h"', "", text)                                  # P1
@@ -111,6 +119,8 @@ def patch(rel, text):
         text = sub(text, r"(bool Scene::FindMaterialExit\(Ray& ray, MaterialType::MatType matType\) const\s*\{)",
                    r"\1 ++g_vp_cnt.exitray;", "P10c", expect=1)
         text = sub(text, r"(bool Scene::FindSmokeExit\(Ray& ray\) const\s*\{)", r"\1 ++g_vp_cnt.exitray;", "P10d", expect=1)
+        if timing:
+            return text
         # one DDA step == one grid load (scene.cpp:765,829,889,954,1017)
         text = sub(text, r"(const (?:MaterialType::MatType|auto) cell = grid\[GetVoxel\(s\.X, s\.Y, s\.Z\)\];)",
                    r"\1 ++g_vp_cnt.steps;", "P10e", expect=5)
@@ -122,10 +132,7 @@ def patch(rel, text):
     return text
 
 
-def main():
-    if not os.path.isdir(REF):
-        print(f"build_ref: {REF} not present - keeping any prebuilt oracle/_ref/libvpref.so")
-        return 0
+def build_one(so_name, timing):
     shutil.rmtree(BUILD, ignore_errors=True)
     os.makedirs(BUILD, exist_ok=True)
     for rel in FILES:
@@ -134,8 +141,8 @@ def main():
         dst = os.path.join(BUILD, rel)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         with open(dst, "w", encoding="utf-8", errors="surrogateescape") as f:
-            f.write(patch(rel, text))
-    so = os.path.join(OUT, "libvpref.so")
+            f.write(patch(rel, text, timing))
+    so = os.path.join(OUT, so_name)
     cmd = [
         "g++", "-std=c++17", "-O2", "-g0", "-fPIC", "-shared", "-fopenmp",
         "-mavx2", "-mfma", "-mbmi2", "-ffp-contract=off", "-fno-fast-math",
@@ -151,6 +158,23 @@ def main():
     if r.returncode == 0 and not os.environ.get("VP_KEEP_BUILD"):
         shutil.rmtree(BUILD, ignore_errors=True)
     return r.returncode
+
+
+def main():
+    if not os.path.isdir(REF):
+        print(f"build_ref: {REF} not present - keeping any prebuilt oracle/_ref/libvpref*.so")
+        return 0
+    os.makedirs(OUT, exist_ok=True)
+    jobs = [("libvpref.so", False), ("libvpref_fast.so", True)]
+    if "--timing" in sys.argv:
+        jobs = jobs[1:]
+    if "--parity" in sys.argv:
+        jobs = jobs[:1]
+    for so_name, timing in jobs:
+        rc = build_one(so_name, timing)
+        if rc:
+            return rc
+    return 0
 
 
 if __name__ == "__main__":

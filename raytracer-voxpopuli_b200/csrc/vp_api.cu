@@ -79,7 +79,7 @@ struct PassGraph {
   // kind 0 = other, 1 = extend grid, 2 = shadow grid, 3 = generate (the only graphed stage that reads per-frame fields)
   struct Node { cudaGraphNode_t node; cudaKernelNodeParams kp; int iter; int kind; WfParams last; unsigned grid; };
   std::vector<Node> nodes;
-  unsigned long long updates = 0, replays = 0;  // node parameter updates issued / graph launches (vp_info)
+  unsigned long long updates = 0, replays = 0, captures = 0;  // node parameter updates issued / graph launches / captures (vp_info)
 };
 
 struct WfLane {
@@ -452,6 +452,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
     }
     G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared; G.smem = sm; G.counts = (const void*)p.st.counts;
     G.nvol = p.sc.nvol; G.stagger = c->tune_band_stagger;
+    G.captures++;
   } else {
     for (PassGraph::Node& x : G.nodes) {
       WfParams q;
@@ -1463,8 +1464,8 @@ int vp_info(vp_ctx* c, char* buf, int cap)
   size_t scene = c->d_regions.cap * 8 + c->d_sky.cap * 4 + 256 * sizeof(VpMaterial), lanes = 0, frames = 0;
   for (const HostVolume& v : c->vols) scene += (size_t)v.n * v.n * v.n + ((size_t)64 << (3 * v.jr)) * 8;
   int lanes_held = 0;
-  unsigned long long updates = 0, replays = 0;
-  for (const WfLane& L : c->lane) { lanes += L.d_wf.p ? L.d_wf.cap : 0; lanes_held += L.d_wf.p ? 1 : 0; updates += L.pg.updates; replays += L.pg.replays; }
+  unsigned long long updates = 0, replays = 0, captures = 0;
+  for (const WfLane& L : c->lane) { lanes += L.d_wf.p ? L.d_wf.cap : 0; lanes_held += L.d_wf.p ? 1 : 0; updates += L.pg.updates; replays += L.pg.replays; captures += L.pg.captures; }
   frames = c->d_accum.cap * sizeof(float4) + c->d_rgb8.cap * 4 + (c->d_rp_alb.cap + c->d_rp_ill.cap + c->d_rp_hist_in.cap + c->d_rp_hist_out.cap) * 4 +
            c->d_rp_ray.cap * sizeof(float4);
   snprintf(buf, (size_t)cap,
@@ -1473,10 +1474,10 @@ int vp_info(vp_ctx* c, char* buf, int cap)
            "\"k_wf_shade_regs\": %d, \"k_wf_shade_local_bytes\": %zu, \"wf_blocks_extend\": %d, \"wf_blocks_shadow\": %d, \"volumes\": %d, \"max_levels\": %d, "
            "\"region_words_staged\": %d, \"dbg_extend_steps_in_empty_region\": %llu, \"dbg_extend_steps_in_empty_brick\": %llu, \"extend_steps\": %llu, "
            "\"hbm_scene_bytes\": %zu, \"hbm_lane_bytes\": %zu, \"hbm_frame_bytes\": %zu, \"hbm_in_use\": %zu, \"lanes\": %d, \"lanes_allocated\": %d, "
-           "\"graph_replays\": %llu, \"graph_node_updates\": %llu}",
+           "\"graph_replays\": %llu, \"graph_node_updates\": %llu, \"graph_captures\": %llu, \"graph_enabled\": %d}",
            c->device, ndev, peer ? "true" : "false", prop.name, prop.major, prop.minor, c->sm_count, c->blocks_per_sm, kBlock, fa.numRegs, fa.localSizeBytes,
            fe.numRegs, fs.numRegs, fh.numRegs, fh.localSizeBytes, c->wf_blocks_extend, c->wf_blocks_shadow, c->sc.nvol, VP_MAX_LEVELS,
-           c->sc.region_words, dbg[9], dbg[10], dbg[11], scene, lanes, frames, scene + lanes + frames, c->nlanes, lanes_held, replays, updates);
+           c->sc.region_words, dbg[9], dbg[10], dbg[11], scene, lanes, frames, scene + lanes + frames, c->nlanes, lanes_held, replays, updates, captures, c->tune_graph);
   return 0;
 }
 

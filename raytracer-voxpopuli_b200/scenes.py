@@ -6,6 +6,7 @@ Scene::LoadModel, see tools/make_scene_fixtures.py); transforms, materials, ligh
 cameras are built here with the host-side restatement of the reference's authoring code
 (host.py -> libvoxpop_host.so).  Nothing here touches /root/reference or oracle/.
 """
+import json
 import os
 
 import numpy as np
@@ -46,7 +47,7 @@ def _volume(name, position, rotation=(0.0, 0.0, 0.0), scale=(1.0, 1.0, 1.0), rem
         for a, b in remap.items():
             grid[grid == a] = b
     M, iM, bmin, bmax = host.make_transform(position, rotation, scale)
-    return Volume(grid, n, bmin, bmax, M, iM), mats
+    return Volume(grid, n, bmin, bmax, M, iM, (name, tuple(sorted((remap or {}).items())))), mats
 
 
 def _merge_materials(tables):
@@ -60,7 +61,14 @@ def _merge_materials(tables):
 
 
 def config(idx, width=None, height=None):
-    """Returns (SceneDesc, Camera, dict(width, height, max_bounces, spp, aa_strength)) for configs 1..5."""
+    """Returns (SceneDesc, Camera, dict(width, height, max_bounces, spp, aa_strength)) for configs 1..5; 6 is config 2 with
+    room.vox's native material mapping (palette 8 = GLASS for 99 % of its voxels, reference template/scene.cpp:508-522):
+    the "room.vox ... with glass" wording of the north_star target."""
+    if idx == 6:
+        sc, cam, fpd = config(2, width, height)
+        vol, mats = _volume("room", (0, 0, 0))
+        sc.volumes, sc.materials = [vol], _merge_materials([mats])
+        return sc, cam, fpd
     if idx == 1:
         # teapot.vox single volume, 1280x720, primary rays + 1 point light shadow, 1 spp
         vol, mats = _volume("teapot", (0, 0, 0), remap={8: 249})  # all-glass -> diffuse palette id so a shadow ray exists
@@ -148,4 +156,49 @@ WORKLOAD_NAMES = {
     3: "cfg3 roomGlass.vox 128^3 1920x1080 16spp maxBounces=8 glass + synthetic HDR sky, 2 point + 2 spot lights",
     4: "cfg4 city 6x64^3+16^3 2560x1440 1spp maxBounces=14 4 area + 2 point lights",
     5: "cfg5 city x3 (21 volumes) 3840x2160 64spp maxBounces=14 64 lights",
+    6: "cfg2g room.vox 128^3 1920x1080 1spp maxBounces=14 2 point + 2 spot lights, native materials (palette 8 = GLASS)",
 }
+
+BENCH_DIR = os.path.join(os.path.dirname(DATA_DIR), "bench")
+
+
+def save_inputs(idx, path):
+    """Everything config(idx) computes with the host mirror (transforms, material table, lights, camera), as plain arrays:
+    bench.py's reference arm reads this file instead, so that no library of this repository is mapped into that process
+    (tools/make_bench_inputs.py writes it, tests/test_bench_inputs.py keeps it in step with config())."""
+    sc, cam, fpd = config(idx)
+    f = lambda rows, k: np.array([np.concatenate([np.ravel(np.asarray(x, np.float32)) for x in r]) for r in rows], np.float32).reshape(len(rows), k)
+    np.savez_compressed(
+        path, names=np.array([v.source[0] for v in sc.volumes]), remap=np.array([json.dumps(v.source[1]) for v in sc.volumes]),
+        n=np.array([v.n for v in sc.volumes], np.int32), cube_min=np.array([v.cube_min for v in sc.volumes], np.float32),
+        cube_max=np.array([v.cube_max for v in sc.volumes], np.float32), matrix=np.array([v.matrix for v in sc.volumes], np.float32),
+        inv_matrix=np.array([v.inv_matrix for v in sc.volumes], np.float32), materials=np.asarray(sc.materials, np.float32),
+        point=f(sc.point_lights, 6), area=f(sc.area_lights, 8), spot=f(sc.spot_lights, 10),
+        dir=np.concatenate([np.asarray(sc.dir_light[0], np.float32), np.asarray(sc.dir_light[1], np.float32)]),
+        area_samples=np.int32(sc.area_shadow_samples), sky=np.int32(1 if sc.sky is not None else 0), sky_contribution=np.float32(sc.sky_contribution),
+        sky_active=np.int32(sc.sky_active),
+        camera=np.concatenate([np.asarray(getattr(cam, k), np.float32) for k in ("cam_pos", "top_left", "top_right", "bottom_left", "right", "up")] +
+                              [np.array([cam.focal_distance, cam.defocus_jitter], np.float32)]),
+        frame=np.array([fpd["width"], fpd["height"], fpd["max_bounces"], fpd["spp"]], np.int32), aa=np.float32(fpd["aa_strength"]))
+
+
+def load_inputs(path):
+    """(SceneDesc, Camera, frame dict) from a save_inputs file; numpy only."""
+    from .session import Camera
+    d = np.load(path)
+    vols = []
+    for i, nm in enumerate(d["names"]):
+        grid, n, _ = load_grid(str(nm))
+        for a, b in json.loads(str(d["remap"][i])):
+            grid[grid == a] = b
+        assert n == int(d["n"][i])
+        vols.append(Volume(grid, n, d["cube_min"][i], d["cube_max"][i], d["matrix"][i], d["inv_matrix"][i], (str(nm), ())))
+    sc = SceneDesc(volumes=vols, materials=d["materials"],
+                   point_lights=[(r[:3], r[3:6]) for r in d["point"]], area_lights=[(r[:3], r[3:6], float(r[6]), float(r[7])) for r in d["area"]],
+                   spot_lights=[(r[:3], r[3:6], r[6:9], float(r[9])) for r in d["spot"]], dir_light=(tuple(d["dir"][:3]), tuple(d["dir"][3:])),
+                   area_shadow_samples=int(d["area_samples"]), sky=synthetic_sky() if int(d["sky"]) else None,
+                   sky_contribution=float(d["sky_contribution"]), sky_active=bool(int(d["sky_active"])))
+    c = d["camera"]
+    cam = Camera(c[0:3], c[3:6], c[6:9], c[9:12], c[12:15], c[15:18], float(c[18]), float(c[19]))
+    fr = d["frame"]
+    return sc, cam, dict(width=int(fr[0]), height=int(fr[1]), max_bounces=int(fr[2]), spp=int(fr[3]), aa_strength=float(d["aa"]))

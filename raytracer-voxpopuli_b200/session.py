@@ -21,6 +21,7 @@ class Volume:
     cube_max: np.ndarray
     matrix: np.ndarray        # float32[16], row-major mat4 cells
     inv_matrix: np.ndarray
+    source: tuple = None      # (fixture name, ((from, to), ...) palette remap) when the grid comes from data/scenes/
 
 
 @dataclass
