@@ -248,8 +248,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # barriers around phases in which only rank 0 works wait on the HOST (gloo): an NCCL barrier is a kernel that spins
+        # on every waiting rank's GPU, and a GPU shared by two processes is time-sliced between them
+        host_group = dist.new_group(backend="gloo")
     dev = torch.device("cuda", local)
 
     lib = vp.load_product()
@@ -342,7 +346,10 @@ def main():
             stream.wait_stream(comm)
         fence(stream)
 
-    STAGE_EVERY = 20
+    # The first timed step runs alone (pipeline empty after the warm-up, not deferred) with CUDA events around its
+    # extend-stage launches: the roofline's kernel duration is measured inside the timed region, without other frames'
+    # kernels sharing the SMs.  (Round 1 ran every 20th step alone; draining the pipeline that often costs a 1/8-frame
+    # shard 12 % of its step time.)
     sampler = ClockSampler(local, period_s=float(os.environ.get("VP_BENCH_CLOCK_PERIOD", "0.02")))
     if os.environ.get("VP_BENCH_NO_SAMPLER") != "1":
         sampler.start()
@@ -368,14 +375,7 @@ def main():
     torch.cuda.synchronize(dev)
     t_begin.record(stream)
     for i in range(args.steps):
-        if i % STAGE_EVERY == 0:
-            # every 20th step runs alone (pipeline drained, not deferred) with CUDA events around its extend-stage
-            # launches: the roofline's kernel duration is measured inside the timed region, without other frames'
-            # kernels sharing the SMs
-            drain()
-            step(args.warmup + i, flags=abi.VP_FLAG_TIME_STAGES)
-        else:
-            step(args.warmup + i)
+        step(args.warmup + i, flags=abi.VP_FLAG_TIME_STAGES if i == 0 else abi.VP_FLAG_DEFER)
     drain()
     t_end.record(stream)
     torch.cuda.synchronize(dev)
@@ -421,7 +421,7 @@ def main():
             lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp), acc1.data_ptr(), one.data_ptr(), stream.cuda_stream, None), "render_device(check)")
             torch.cuda.synchronize(dev)
             exchange_check = {"pixels_differing_from_single_gpu_image": int((got != one).sum().item()), "frames": last + 1}
-        dist.barrier()
+        dist.barrier(group=host_group)
 
     # ---- e2e: the reference-facing C-ABI calls with host buffers, copies inside the timed region ----
     e2e_steps = max(3, min(args.steps, 20))
@@ -456,7 +456,7 @@ def main():
                       "row tiles over its own PCIe link into ONE page-locked host accumulator / image, 3 frames in flight",
                "steps": e2e_steps, "timer": "host wall clock around the steps, last ticket waited for", "peer_access": ginfo.get("peer_access")}
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=host_group)
 
     if rank != 0:
         if share is not None:
@@ -485,7 +485,7 @@ def main():
     own_rows = sum(min(ROW_TILE, H - k * ROW_TILE) for k in range(rank, (H + ROW_TILE - 1) // ROW_TILE, world))
     px_rank = own_rows * W if world > 1 else W * H
     ext_rays = inst.primary_rays + inst.secondary_rays
-    timed_steps = len(range(0, args.steps, STAGE_EVERY))
+    timed_steps = 1
     ext_launches_per_frame = max(1, ext_n.value // max(1, timed_steps))
     ext_bytes_frame = meta["extend_steps"] * 1 + ext_rays * nvol * 128
     frame_bytes = inst.dda_steps * 1 + (inst.rays + inst.exit_rays) * nvol * 128 + px_rank * 32 + px_rank * 4 + inst.sky_samples * 12
@@ -593,7 +593,7 @@ def main():
                        "l2": "not flushed: every step streams its own path state through HBM (~1.3 GB per 1080p frame, >> 126 MB L2); the "
                              "2.3 MB scene is L2-resident by design (DESIGN.md section 3)",
                        "frames_in_flight": 4, "traversal": "brick walk (one exact merge step per empty 4x4x4 brick), prepare stage",
-                       "timed_region": "one CUDA-event pair around all steps; every 20th step runs alone with stage events (VP_FLAG_TIME_STAGES)",
+                       "timed_region": "one CUDA-event pair around all steps; the first step runs alone with stage events (VP_FLAG_TIME_STAGES)",
                        "hbm_in_use": meta.get("hbm_in_use"), "graph_node_updates_per_replay": (meta["graph_node_updates"] / meta["graph_replays"]) if meta.get("graph_replays") else None,
                        "also": also},
             "ms_per_frame": total_ms / args.steps,

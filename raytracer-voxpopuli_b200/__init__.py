@@ -12,7 +12,7 @@ from .session import Camera, SceneDesc, Session, Volume, frame_params, make_rays
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
-PRODUCT_SO = os.path.join(PKG_DIR, "libvoxpop_b200.so")
+PRODUCT_SO = os.environ.get("VP_PRODUCT_SO") or os.path.join(PKG_DIR, "libvoxpop_b200.so")  # the override selects an experiment build (build.build_variant)
 HOST_SO = os.path.join(PKG_DIR, "libvoxpop_host.so")
 
 

@@ -28,6 +28,13 @@ def _run(cmd):
     subprocess.check_call(cmd)
 
 
+def build_variant(name, defines):
+    """Experiment builds: libvoxpop_b200_<name>.so with extra -D macros (select with VP_PRODUCT_SO=<path>)."""
+    so = os.path.join(PKG, f"libvoxpop_b200_{name}.so")
+    _run(["nvcc"] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", so, os.path.join(PKG, "csrc", "vp_api.cu")])
+    return so
+
+
 def build(force=False, verbose_ptxas=False):
     csrc = os.path.join(PKG, "csrc")
     hdr = os.path.join(os.path.dirname(PKG), "include", "voxpop.h")

@@ -76,7 +76,7 @@ struct PassGraph {
   int max_bounces = -2, brickwalk = -1, nvol = -1, stagger = -99;
   size_t smem = 0;
   const void* counts = nullptr;  // the lane's buffers were (re)allocated: the memset node and every pointer changed
-  // kind 0 = other, 1 = extend grid, 2 = shadow grid, 3 = generate (the only graphed stage that reads per-frame fields)
+  // kind 0 = other, 1 = extend grid, 2 = shadow grid, 4 = shade grid, 3 = generate (the only graphed stage that reads per-frame fields)
   struct Node { cudaGraphNode_t node; cudaKernelNodeParams kp; int iter; int kind; WfParams last; unsigned grid; };
   std::vector<Node> nodes;
   unsigned long long updates = 0, replays = 0, captures = 0;  // node parameter updates issued / graph launches / captures (vp_info)
@@ -158,7 +158,9 @@ struct vp_ctx {
   int tune_refill = kRefill;  // VP_REFILL
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
   int tune_brickwalk = 1;     // VP_BRICKWALK: 0 = cell walk only (A/B)
-  int wf_grid_shade = 0;      // blocks of the shade stage: what is resident at once (VP_BLOCKS_SHADE per SM)
+  int wf_grid_shade = 0;      // blocks of the shade stage of the current call (small shards: fewer blocks, each stages the scene once)
+  int wf_blocks_shade = 0;    // ... at full load: what is resident at once (VP_BLOCKS_SHADE per SM fixes it)
+  bool wf_shade_fixed = false;
   int tune_graph = 1;         // VP_GRAPH: 0 = launch every kernel of a pass from the host, 2 = graph + prepare stage for lone passes too
   int tune_prepare = 1;       // VP_PREPARE: 0 = the extend stage sets up every walk itself
   bool graph_now = false;     // this call's passes go through the lane graphs
@@ -169,7 +171,7 @@ struct vp_ctx {
   int tune_bands = 4;         // VP_BANDS: row bands a vp_render call is cut into (1 = off)
   long long tune_band_min_pixels = 1 << 18;  // VP_BAND_MIN_PIXELS: smaller calls are not cut
   int tune_paths_per_thread = 8;  // VP_PATHS_PER_THREAD: paths of a call per thread of the persistent traversal grids (small shards: fewer, longer-lived warps)
-  int tune_min_blocks = 3;        // VP_MIN_BLOCKS: ... but at least this many blocks per SM
+  int tune_min_blocks = 2;        // VP_MIN_BLOCKS: ... but at least this many blocks per SM (1/8 frame shares: 0.636 ms with 1-2, 0.654 with 3, 0.669 with 4)
   // VP_FLAG_TIME_STAGES: CUDA-event pairs around every k_wf_extend launch, summed by vp_stage_times
   std::vector<cudaEvent_t> tev;
   size_t tev_used = 0;
@@ -447,7 +449,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
                 x.kp.func == (void*)k_wf_extend<false, true, kWfMinBlocksMulti>) ? 1
              : (x.kp.func == (void*)k_wf_shadow<false, true> || x.kp.func == (void*)k_wf_shadow<false, false> ||
                 x.kp.func == (void*)k_wf_shadow<false, true, kWfMinBlocksMulti>) ? 2
-             : (x.kp.func == (void*)k_wf_generate) ? 3 : 0;
+             : (x.kp.func == (void*)k_wf_generate) ? 3 : (x.kp.func == (void*)k_wf_shade<false>) ? 4 : 0;
       G.nodes.push_back(x);
     }
     G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared; G.smem = sm; G.counts = (const void*)p.st.counts;
@@ -466,7 +468,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
         q.cmode = x.last.cmode; q.ctrow0 = x.last.ctrow0; q.ck = x.last.ck;
         q.accum = x.last.accum; q.rgb8 = x.last.rgb8; q.write_rgb8 = x.last.write_rgb8;
       }
-      const unsigned grid = x.kind == 1 ? (unsigned)c->wf_grid_extend : (x.kind == 2 ? (unsigned)c->wf_grid_shadow : x.grid);
+      const unsigned grid = x.kind == 1 ? (unsigned)c->wf_grid_extend : x.kind == 2 ? (unsigned)c->wf_grid_shadow : x.kind == 4 ? (unsigned)c->wf_grid_shade : x.grid;
       if (grid == x.grid && memcmp(&q, &x.last, sizeof(q)) == 0) continue;
       void* args[1] = {&q};
       cudaKernelNodeParams kp = x.kp;
@@ -645,6 +647,8 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
     const bool full = c->wf_blocks_fixed || !(overlap || fp->spp > 1);  // a lone pass wants the lowest latency: full grid
     c->wf_grid_extend = full ? be : (int)we;
     c->wf_grid_shadow = full ? bs : (int)ws;
+    const long long wh = want * c->sm_count < c->wf_blocks_shade ? want * c->sm_count : c->wf_blocks_shade;
+    c->wf_grid_shade = (full || c->wf_shade_fixed) ? c->wf_blocks_shade : (int)wh;
   }
   const bool cs = (fp->flags & VP_FLAG_COUNT_STEPS) != 0;
   CU(cudaEventRecord(c->ev_in, stream));
@@ -843,8 +847,8 @@ vp_ctx* vp_create(int device)
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shadow<false, true, kWfMinBlocksMulti>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
   c->wf_blocks_shadow_mv = occ * c->sm_count;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shade<false>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 6;
-  c->wf_grid_shade = occ * c->sm_count;
-  if (const char* e = getenv("VP_BLOCKS_SHADE")) c->wf_grid_shade = atoi(e) * c->sm_count;
+  c->wf_blocks_shade = c->wf_grid_shade = occ * c->sm_count;
+  if (const char* e = getenv("VP_BLOCKS_SHADE")) { c->wf_blocks_shade = c->wf_grid_shade = atoi(e) * c->sm_count; c->wf_shade_fixed = true; }
   // tuning knobs for experiments (defaults are the shipped values)
   if (const char* e = getenv("VP_PATHS_PER_THREAD")) c->tune_paths_per_thread = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("VP_MIN_BLOCKS")) c->tune_min_blocks = atoi(e) < 1 ? 1 : atoi(e);

@@ -29,6 +29,9 @@ constexpr int kWfBlock = 128;
 #ifndef VP_WF_MINBLOCKS
 #define VP_WF_MINBLOCKS 7
 #endif
+#ifndef VP_HOIST_PS
+#define VP_HOIST_PS 1
+#endif
 #ifndef VP_BW_UNROLL
 #define VP_BW_UNROLL 2
 #endif
@@ -297,16 +300,25 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
           vi = 0; has_ray = true; in_dda = false;
           nrays++;
           if (BWK && p.prepared) {
-            // the walk through the first volume the ray enters was set up by k_wf_prepare
+            // the walk through the first volume the ray enters was set up by k_wf_prepare.  The three records are taken
+            // unconditionally (a ray that enters no volume has zeros there): loads that only feed the branch below would
+            // be issued inside it, one memory round trip after the flags word arrived
             const float4 w0 = __ldcs(p.st.ps[0] + qi), w1 = __ldcs(p.st.ps[1] + qi), w2 = __ldcs(p.st.ps[2] + qi);
             const uint32_t fl = __float_as_uint(w2.w);
             vi = (fl & 63u) ? (int)(fl & 63u) : nvol;
             cand = fl >> 10;
+#if VP_HOIST_PS
+            s.tx = w0.x; s.ty = w0.y; s.tz = w0.z; s.t = w0.w;
+            s.dx = w1.x; s.dy = w1.y; s.dz = w1.z; s.P = __float_as_uint(w1.w);
+            bw.ex = w2.x; bw.ey = w2.y; bw.ez = w2.z;
+#endif
             if (fl & 63u) {
               const DVolume& v = svol[vi - 1];
+#if !VP_HOIST_PS
               s.tx = w0.x; s.ty = w0.y; s.tz = w0.z; s.t = w0.w;
               s.dx = w1.x; s.dy = w1.y; s.dz = w1.z; s.P = __float_as_uint(w1.w);
               bw.ex = w2.x; bw.ey = w2.y; bw.ez = w2.z;
+#endif
               bw.F = axis_field(v.jr, 0);
               bw.flip = ((fl >> 7) & 1u ? bw.F : 0u) | ((fl >> 8) & 1u ? bw.F << 1 : 0u) | ((fl >> 9) & 1u ? bw.F << 2 : 0u);
               bw.plain = (fl >> 6) & 1u; bw.ac = 0u; bw.tc = __uint_as_float(0xFF800000u);
