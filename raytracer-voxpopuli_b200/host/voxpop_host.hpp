@@ -147,6 +147,8 @@ class Camera {  // template/camera.h
 class Renderer {
  public:
   Renderer(int scrwidth, int scrheight, int device = -1);
+  // the same renderer over several GPUs of the box (vp_create_multi): the library shards the rows of every frame
+  Renderer(int scrwidth, int scrheight, const std::vector<int>& devices);
   ~Renderer();
   Renderer(const Renderer&) = delete;
   Renderer& operator=(const Renderer&) = delete;
@@ -156,7 +158,15 @@ class Renderer {
   void ResetAccumulator();      // renderer.cpp:343-346
   // push voxelVolumes / materials / lights / prims / sky to the device ("dirty" call, between frames)
   void UploadScene();
-  void Update();                                  // one accumulated frame, renderer.cpp:1646-1891
+  // One accumulated frame, renderer.cpp:1646-1891.  The frame is ENQUEUED (vp_render_async): like the reference's Tick,
+  // which only needs the pixels when it blits them (renderer.cpp:1972-2217), the host goes on - game logic, the next
+  // Update() - while the GPU traces; Pixels() / Accumulator() / Finish() wait for the frames enqueued so far.  Read
+  // screenPixels / accumulator directly only after one of them.
+  void Update();
+  void UpdateBlocking();                          // vp_render: returns with the frame and fills lastStats
+  void Finish();
+  const uint32_t* Pixels() { Finish(); return screenPixels.data(); }
+  const float* Accumulator() { Finish(); return accumulator.data(); }
   // the static-camera branch of Tick (renderer.cpp:1997-2101): one reprojected frame into screenPixels; keeps
   // illuminationHistoryBuffer, and CopyToPrevCamera() (renderer.cpp:1893-1902) is the caller's move, as in the reference
   void UpdateReproject();
@@ -192,7 +202,9 @@ class Renderer {
   VpStats lastStats{};
 
  private:
+  void Init();
   vp_ctx* ctx_ = nullptr;
+  uint64_t ticket_ = 0;  // last frame enqueued by Update()
 };
 
 }  // namespace voxpop

@@ -16,12 +16,30 @@ Renderer::Renderer(int w, int h, int device) : width(w), height(h), camera(w, h)
 {
   ctx_ = vp_create(device);
   if (!ctx_) throw std::runtime_error(std::string("vp_create failed: ") + vp_last_error());
-  accumulator.assign((size_t)w * h * 4, 0.0f);  // Init(): MALLOC64 + memset, renderer.cpp:699-702
-  screenPixels.assign((size_t)w * h, 0u);
+  Init();
+}
+Renderer::Renderer(int w, int h, const std::vector<int>& devices) : width(w), height(h), camera(w, h)
+{
+  ctx_ = vp_create_multi(devices.data(), (int)devices.size());
+  if (!ctx_) throw std::runtime_error(std::string("vp_create_multi failed: ") + vp_last_error());
+  Init();
+}
+void Renderer::Init()
+{
+  accumulator.assign((size_t)width * height * 4, 0.0f);  // Init(): MALLOC64 + memset, renderer.cpp:699-702
+  screenPixels.assign((size_t)width * height, 0u);
+  // page-locked, so that the copies of Update() run asynchronously (failure is not fatal: the copies then block)
+  vp_host_register(ctx_, accumulator.data(), accumulator.size() * sizeof(float));
+  vp_host_register(ctx_, screenPixels.data(), screenPixels.size() * sizeof(uint32_t));
   MaterialSetUp();
   CalculateLightCount();
 }
-Renderer::~Renderer() { vp_destroy(ctx_); }
+Renderer::~Renderer()
+{
+  vp_host_unregister(ctx_, accumulator.data());
+  vp_host_unregister(ctx_, screenPixels.data());
+  vp_destroy(ctx_);
+}
 const char* Renderer::LastError() const { return vp_last_error(); }
 
 void Renderer::MaterialSetUp() { default_materials(materials); }
@@ -33,6 +51,11 @@ void Renderer::CalculateLightCount()
   lightCount = pointCount + spotCount + areaCount + 1;  // directional light is always counted
 }
 void Renderer::ResetAccumulator() { numRenderedFrames = 0; }
+void Renderer::Finish()
+{
+  if (ticket_ && vp_render_wait(ctx_, ticket_)) throw std::runtime_error(vp_last_error());
+  ticket_ = 0;
+}
 
 void Renderer::UploadScene()
 {
@@ -96,12 +119,25 @@ void Renderer::Update()  // renderer.cpp:1646-1891
 {
   const VpCamera cam = camera.Pack();
   const VpFrameParams fp = frame_params(*this, 1);
+  // the first frame after ResetAccumulator() ignores the accumulator (weight 1): nothing to upload; later frames
+  // continue from the library's device copy of the previous frame's result
+  const float* in = numRenderedFrames == 0 ? accumulator.data() : nullptr;
+  if (vp_render_async(ctx_, &cam, &fp, in, accumulator.data(), screenPixels.data(), &ticket_)) throw std::runtime_error(vp_last_error());
+  numRenderedFrames++;
+}
+
+void Renderer::UpdateBlocking()
+{
+  Finish();
+  const VpCamera cam = camera.Pack();
+  const VpFrameParams fp = frame_params(*this, 1);
   if (vp_render(ctx_, &cam, &fp, accumulator.data(), screenPixels.data(), &lastStats)) throw std::runtime_error(vp_last_error());
   numRenderedFrames++;
 }
 
 void Renderer::UpdateReproject()  // renderer.cpp:1997-2101
 {
+  Finish();
   const size_t n = (size_t)width * height * 3;
   if (illuminationHistoryBuffer.size() != n) illuminationHistoryBuffer.assign(n, 0.0f);
   tempIlluminationBuffer.resize(n);
@@ -176,9 +212,16 @@ extern "C" int vphr_demo_render(const char* vox_path, const uint8_t* grid, uint3
     r.UploadScene();
     unsigned long long rays = 0;
     for (int f = 0; f < frames; f++) {
-      r.Update();
+      r.UpdateBlocking();
       rays += r.lastStats.primary_rays + r.lastStats.secondary_rays + r.lastStats.shadow_rays;
     }
+    // the same frames again through the asynchronous Update(): enqueue all of them, then read
+    std::vector<float> first(r.accumulator);
+    std::vector<uint32_t> first_rgb(r.screenPixels);
+    r.ResetAccumulator();
+    for (int f = 0; f < frames; f++) r.Update();
+    if (memcmp(first.data(), r.Accumulator(), first.size() * sizeof(float)) != 0) return -3;
+    if (memcmp(first_rgb.data(), r.Pixels(), first_rgb.size() * sizeof(uint32_t)) != 0) return -4;
     memcpy(accum_out, r.accumulator.data(), r.accumulator.size() * sizeof(float));
     memcpy(rgb8_out, r.screenPixels.data(), r.screenPixels.size() * sizeof(uint32_t));
     *rays_out = rays;
