@@ -281,6 +281,16 @@ int vp_stats_end(vp_ctx* ctx, VpStats* stats);
  * the previous call, and their number; synchronises the device. */
 int vp_stage_times(vp_ctx* ctx, double* extend_ms, uint64_t* extend_launches);
 
+/* ---- display interop ------------------------------------------------------------------------------
+ * The template blits screen->pixels through an RGBA8 texture it re-uploads every frame (reference
+ * template/opengl.cpp:144-150 GLTexture::CopyFrom with GL_BGRA, template/template.cpp:305-309).  vp_render_to_gl writes the
+ * library's RGB8 image of the most recent vp_render / vp_render_async / vp_render_resident frame straight into that
+ * texture (CUDA-GL interop: the texture is registered once, mapped per call, filled by a kernel through a surface, channel
+ * order R, G, B, A = 255) - no device-to-host copy, no glTexImage2D.  gl_texture: the name of a GL_TEXTURE_2D with
+ * internal format GL_RGBA8 and the frame's size; the OpenGL context that owns it must be current on the calling thread.
+ * Headless build boxes have no GL: the call then fails with VP_ECUDA and a message (unmeasured on the B200 pool). */
+int vp_render_to_gl(vp_ctx* ctx, uint32_t gl_texture);
+
 /* ---- one image shared by several PROCESSES (one rank per GPU) ----------------------------------------
  * The display rank allocates the image in its GPU's HBM (vp_share_create) and hands the 128-byte VpShareInfo to the other
  * ranks by any transport; they map it (vp_share_open: CUDA IPC + peer access over NVLink) and pass vp_share_ptr() as the

@@ -100,7 +100,7 @@ ABI_SYMBOLS = [
     "accum_download", "render_device", "trace_primary", "find_nearest", "is_occluded", "trace", "info", "stats_begin", "stats_end", "stage_times",
     "render_fence", "render_reproject", "render_reproject_device", "in_light", "find_nearest_player", "focus_distance",
     "create_multi", "device_count", "render_async", "render_wait", "host_register", "host_unregister",
-    "share_create", "share_open", "share_ptr", "share_signal", "share_wait", "share_error", "share_close",
+    "render_to_gl", "share_create", "share_open", "share_ptr", "share_signal", "share_wait", "share_error", "share_close",
 ]
 
 
@@ -166,6 +166,7 @@ class Lib:
         f("render_wait", C.c_int, [C.c_void_p, C.c_uint64], optional=True)
         f("host_register", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64], optional=True)
         f("host_unregister", C.c_int, [C.c_void_p, C.c_void_p], optional=True)
+        f("render_to_gl", C.c_int, [C.c_void_p, C.c_uint32], optional=True)
         f("share_create", C.c_void_p, [C.c_void_p, C.c_uint64, C.POINTER(VpShareInfo)], optional=True)
         f("share_open", C.c_void_p, [C.c_void_p, C.POINTER(VpShareInfo)], optional=True)
         f("share_ptr", C.c_void_p, [C.c_void_p], optional=True)

@@ -111,6 +111,9 @@ struct vp_ctx {
   // ---- asynchronous host-buffer frames (vp_render_async / vp_render_wait) ----
   cudaEvent_t ev_ticket[kTickets] = {};
   unsigned long long nticket = 0;
+  // ---- display interop (vp_render_to_gl): the registered GL texture ----
+  cudaGraphicsResource* gl_res = nullptr;
+  unsigned int gl_tex = 0;
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
@@ -264,6 +267,11 @@ int upload_array(vp_ctx* c, DevBuf<T>& buf, const T* src, int n)
 }
 
 size_t smem_bytes(const vp_ctx* c) { return (size_t)c->sc.nvol * sizeof(DVolume) + 16 + (size_t)c->sc.region_words * 8; }
+// the shade stage also stages the light lists behind that, when they fit the 64 KB the kernels opt into
+size_t light_bytes(const vp_ctx* c) { return (size_t)c->sc.npl * sizeof(VpPointLight) + (size_t)c->sc.nal * sizeof(VpAreaLight) + (size_t)c->sc.nsl * sizeof(VpSpotLight); }
+size_t light_offset(const vp_ctx* c) { return (smem_bytes(c) + 15) & ~(size_t)15; }
+bool lights_staged(const vp_ctx* c) { return light_bytes(c) > 0 && light_offset(c) + light_bytes(c) <= 64 * 1024 - 64; }
+size_t smem_bytes_shade(const vp_ctx* c) { return lights_staged(c) ? light_offset(c) + light_bytes(c) : smem_bytes(c); }
 
 int check_frame(const vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp)
 {
@@ -387,7 +395,7 @@ int enqueue_trace(vp_ctx* c, WfLane& L, WfParams& p, bool timing, bool capturing
     else k_wf_extend<CS, false><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
     if (e1) CU(cudaEventRecord(e1, stream));
     if (it >= 2) CU(cudaStreamWaitEvent(stream, L.ev_shadow[it - 2], 0));  // shade(k) reuses the id queue of shadow(k-2)
-    k_wf_shade<CS><<<c->wf_grid_shade, kWfBlock, sm, stream>>>(p);  // one resident wave: the stage is a grid-stride loop
+    k_wf_shade<CS><<<c->wf_grid_shade, kWfBlock, smem_bytes_shade(c), stream>>>(p);  // one resident wave: the stage is a grid-stride loop
     CU(cudaEventRecord(L.ev_shade[it], stream));
     if (it == c->tune_band_stagger || (it == p.max_bounces && p.max_bounces < c->tune_band_stagger))
       CU(cudaEventRecordWithFlags(L.ev_mid, stream, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));  // a node of its own when the pass is a graph
@@ -421,7 +429,7 @@ void drop_graph(PassGraph& G)
 int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
 {
   PassGraph& G = L.pg;
-  const size_t sm = smem_bytes(c);
+  const size_t sm = smem_bytes(c) + (smem_bytes_shade(c) << 20);
   const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared && G.smem == sm &&
                        G.counts == (const void*)p.st.counts && G.nvol == p.sc.nvol && G.stagger == c->tune_band_stagger);
   if (fresh) {
@@ -610,6 +618,8 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   p.accum = accum; p.rgb8 = rgb8; p.counters = c->d_counters.p; p.iter = 0;
   p.refill = c->tune_refill;
   p.bulk = c->tune_bulk;
+  p.light_smem = lights_staged(c) ? 1 : 0;
+  p.light_smem_off = (int)light_offset(c);
   p.reproject = rp ? 1 : 0;
   p.halo = rp ? 1 : 0;  // no effect on whole frames
   p.rp_alb = c->d_rp_alb.p; p.rp_ill = c->d_rp_ill.p; p.rp_ray = c->d_rp_ray.p;
@@ -900,6 +910,7 @@ void vp_destroy(vp_ctx* c)
     if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_ticket)
     if (e) cudaEventDestroy(e);
+  if (c->gl_res) cudaGraphicsUnregisterResource(c->gl_res);
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_direct) cudaEventDestroy(c->ev_direct);
   if (c->copy) cudaStreamDestroy(c->copy);

@@ -243,7 +243,24 @@ __global__ void k_share_wait(const unsigned int* flags, int first, int n, unsign
   }
 }
 
+// ---- display interop -------------------------------------------------------------------------------
+// The template uploads screen->pixels into an RGBA8 texture with format GL_BGRA (reference template/opengl.cpp:144-150,
+// template/template.cpp:305-309): byte order B, G, R, x of every 0x00RRGGBB pixel.  Here the library's RGB8 image is
+// written into the texture's CUDA array by a kernel (surface store, channels reordered to R, G, B, A = 255): the frame
+// never leaves the GPU.
+__global__ void k_to_gl(cudaSurfaceObject_t surf, const uint32_t* __restrict__ rgb8, int W, int H)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const uint32_t v = rgb8[(size_t)y * W + x];
+  surf2Dwrite(make_uchar4((unsigned char)(v >> 16), (unsigned char)(v >> 8), (unsigned char)v, 255), surf, x * 4, y);
+}
+
 }  // namespace
+
+// cuda_gl_interop.h needs <GL/gl.h>, which a headless build box does not have; the two entry points only take GL names
+// (GLuint image, GLenum target) and are part of the CUDA runtime
+extern "C" cudaError_t cudaGraphicsGLRegisterImage(struct cudaGraphicsResource** resource, unsigned int image, unsigned int target, unsigned int flags);
 
 struct vp_share {
   vp_ctx* ctx = nullptr;
@@ -327,6 +344,51 @@ int vp_host_unregister(vp_ctx* c, void* ptr)
       if (bind(k) || quiesce(k)) return VP_ECUDA;
   } else if (quiesce(c)) return VP_ECUDA;
   CU(cudaHostUnregister(ptr));
+  return 0;
+}
+
+int vp_render_to_gl(vp_ctx* c, uint32_t gl_texture)
+{
+  if (!c) return fail(VP_EINVAL, "null context");
+  vp_ctx* k = c->group ? c->kids[0] : c;
+  if (k->acc_w <= 0 || !k->d_rgb8.p) return fail(VP_ESTATE, "no image yet: render a frame with vp_render / vp_render_async / vp_render_resident first");
+  if (c->group) {
+    for (vp_ctx* q : c->kids)
+      if (bind(q) || quiesce(q)) return VP_ECUDA;
+  }
+  if (bind(k) || quiesce(k)) return VP_ECUDA;
+  if (k->gl_res && k->gl_tex != gl_texture) { cudaGraphicsUnregisterResource(k->gl_res); k->gl_res = nullptr; }
+  if (!k->gl_res) {
+    const unsigned int kGlTexture2D = 0x0DE1;  // GL_TEXTURE_2D
+    const cudaError_t e = cudaGraphicsGLRegisterImage(&k->gl_res, gl_texture, kGlTexture2D, cudaGraphicsRegisterFlagsSurfaceLoadStore | cudaGraphicsRegisterFlagsWriteDiscard);
+    if (e != cudaSuccess) {
+      k->gl_res = nullptr;
+      cudaGetLastError();
+      return fail(VP_ECUDA, "cudaGraphicsGLRegisterImage(texture %u) failed: %s (an OpenGL context that owns the texture must be current on this thread)",
+                  gl_texture, cudaGetErrorString(e));
+    }
+    k->gl_tex = gl_texture;
+  }
+  CU(cudaGraphicsMapResources(1, &k->gl_res, k->stream));
+  cudaArray_t arr = nullptr;
+  cudaError_t e = cudaGraphicsSubResourceGetMappedArray(&arr, k->gl_res, 0, 0);
+  cudaSurfaceObject_t surf = 0;
+  if (e == cudaSuccess) {
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    e = cudaCreateSurfaceObject(&surf, &rd);
+  }
+  if (e == cudaSuccess) {
+    const dim3 blk(32, 8), grd((unsigned)(k->acc_w + 31) / 32, (unsigned)(k->acc_h + 7) / 8);
+    k_to_gl<<<grd, blk, 0, k->stream>>>(surf, k->d_rgb8.p, k->acc_w, k->acc_h);
+    e = cudaGetLastError();
+  }
+  cudaGraphicsUnmapResources(1, &k->gl_res, k->stream);
+  const cudaError_t es = cudaStreamSynchronize(k->stream);
+  if (surf) cudaDestroySurfaceObject(surf);
+  if (e != cudaSuccess || es != cudaSuccess) return fail(VP_ECUDA, "vp_render_to_gl: %s", cudaGetErrorString(e != cudaSuccess ? e : es));
   return 0;
 }
 

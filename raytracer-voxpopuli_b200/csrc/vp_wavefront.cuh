@@ -96,6 +96,7 @@ struct WfParams {
   // 2: interleaved row tiles of ck tile rows each: tile row = ((j / ck) * row_tile_stride + row_tile_phase) * ck + j % ck
   int cmode, ctrow0, ck;
   int prepared;          // 1: k_wf_prepare has set up the first walk of every ray of the bounce
+  int light_smem, light_smem_off;  // shade stage: the light lists are staged in shared memory at this byte offset
   int write_rgb8;
   float4* accum;
   uint32_t* rgb8;
@@ -152,6 +153,28 @@ __device__ __forceinline__ Staged wf_stage_scene(const DScene& sc, unsigned char
   }
   __syncthreads();
   return st;
+}
+// The light lists of the scene, staged behind the volume table / region masks by the shade stage (WfParams.light_smem:
+// 24 / 32 / 40 B per point / area / spot light; every lane of a warp may pick a different light, so these are the
+// stage's scattered small reads).  Falls back to the global arrays when they do not fit.
+struct Lights { const VpPointLight* pl; const VpAreaLight* al; const VpSpotLight* sl; };
+__device__ __forceinline__ Lights wf_stage_lights(const DScene& sc, unsigned char* smem, int offset, int enabled)
+{
+  Lights L; L.pl = sc.pl; L.al = sc.al; L.sl = sc.sl;
+  if (!enabled) return L;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(smem + offset);
+  const int wp = sc.npl * (int)(sizeof(VpPointLight) / 4), wa = sc.nal * (int)(sizeof(VpAreaLight) / 4), ws = sc.nsl * (int)(sizeof(VpSpotLight) / 4);
+  const uint32_t* sp = reinterpret_cast<const uint32_t*>(sc.pl);
+  const uint32_t* sa = reinterpret_cast<const uint32_t*>(sc.al);
+  const uint32_t* ss = reinterpret_cast<const uint32_t*>(sc.sl);
+  for (int i = threadIdx.x; i < wp; i += blockDim.x) dst[i] = __ldg(sp + i);
+  for (int i = threadIdx.x; i < wa; i += blockDim.x) dst[wp + i] = __ldg(sa + i);
+  for (int i = threadIdx.x; i < ws; i += blockDim.x) dst[wp + wa + i] = __ldg(ss + i);
+  __syncthreads();
+  L.pl = reinterpret_cast<const VpPointLight*>(dst);
+  L.al = reinterpret_cast<const VpAreaLight*>(dst + wp);
+  L.sl = reinterpret_cast<const VpSpotLight*>(dst + wp + wa);
+  return L;
 }
 // Blocks that get scheduled after the stage queue ran dry (small shards, late bounces) leave before staging the scene
 // into shared memory; `taken` is the queue's ticket counter, n its length.
@@ -421,8 +444,8 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
 // Illumination() would run, a shadow request (the RNG draws of the light sample happen here, in
 // the reference's order; only the occlusion tests are deferred to K4).
 template <bool CS>
-__device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t path, int level, int type, const Ray& ray, uint32_t& seed,
-                                                 bool& queued, f3& A_now)
+__device__ __forceinline__ void wf_light_request(const WfParams& p, const Lights& lights, uint32_t path, int level, int type, const Ray& ray,
+                                                 uint32_t& seed, bool& queued, f3& A_now)
 {
   const DScene& sc = p.sc;
   const uint32_t lightCount = (uint32_t)(sc.npl + sc.nsl + sc.nal + 1);
@@ -440,7 +463,7 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
   float4* const sql = p.st.sql + slot * p.st.nsamp * cap;
   const uint32_t tag = ((uint32_t)level << 8) | ((uint32_t)type << 13) | ((uint32_t)(ray.mat & 255) << 24);
   if (idx >= (uint32_t)sc.npl && idx < (uint32_t)(sc.nal + sc.npl)) {
-    const VpAreaLight L = sc.al[idx - sc.npl];
+    const VpAreaLight L = lights.al[idx - sc.npl];
     const f3 center = ld3(L.position);
     const float radius = L.radius;
     const f3 point = offset_ray(ip, n);
@@ -476,7 +499,7 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
   } else {
     f3 dirn, contrib; float tshadow; bool lit;
     if (idx < (uint32_t)sc.npl) {
-      const VpPointLight L = sc.pl[idx];
+      const VpPointLight L = lights.pl[idx];
       const f3 dir = sub(ld3(L.position), ip);
       const float dst = sqrtf(dot3(dir, dir));
       dirn = muls(dir, 1.0f / dst);
@@ -485,7 +508,7 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
       contrib = mul(muls(muls(ld3(L.color), stdmax(0.0f, ct)), 1.0f / (dst * dst)), k);
       tshadow = dst;
     } else if (idx < (uint32_t)(sc.nal + sc.nsl + sc.npl)) {
-      const VpSpotLight L = sc.sl[idx - sc.nal - sc.npl];
+      const VpSpotLight L = lights.sl[idx - sc.nal - sc.npl];
       const f3 dir = sub(ld3(L.position), ip);
       const float dst = sqrtf(dot3(dir, dir));
       dirn = divs(dir, dst);
@@ -516,7 +539,7 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, uint32_t pat
 // cont = the path continues with the ray now stored in r0/r1; want_shadow = a light sample was
 // written to the request slot [level][path] and needs its occlusion test.
 template <bool CS>
-__device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& stg, uint32_t path, Counters& cn, int& in_light,
+__device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& stg, const Lights& lights, uint32_t path, Counters& cn, int& in_light,
                                              bool& cont, bool& want_shadow, int& level)
 {
   const DVolume* svol = stg.vol;
@@ -645,7 +668,7 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
       L.type = 2; L.mx = al.x; L.my = al.y; L.mz = al.z;
     }
     f3 A = v3s(0);
-    if (illum) { wf_light_request<CS>(p, path, top, L.type, ray, seed, want_shadow, A); level = top; }
+    if (illum) { wf_light_request<CS>(p, lights, path, top, L.type, ray, seed, want_shadow, A); level = top; }
     // one record per level: the multiplier itself for type 0, else the light term (the shadow stage overwrites it when the
     // sample was queued) - M is then the material's albedo, which the resolve stage looks up again
     const f3 rec = L.type == 0 ? v3(L.mx, L.my, L.mz) : A;
@@ -668,13 +691,11 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocksShade) k_wf_shade(const 
   extern __shared__ __align__(16) unsigned char smem[];
   if (blockIdx.x * blockDim.x >= p.st.counts[4 * p.iter]) return;  // grid-stride loop below would be empty
   const Staged stg = wf_stage_scene(p.sc, smem);
-  const DVolume* svol = stg.vol;
-  const DScene& sc = p.sc;
+  const Lights lights = wf_stage_lights(p.sc, smem, p.light_smem_off, p.light_smem);
   const uint32_t* queue = p.st.q[p.iter & 1];
   uint32_t* qnext = p.st.q[(p.iter + 1) & 1];
   uint32_t* cnt = p.st.counts + 4 * p.iter;
   const uint32_t n = cnt[0];
-  const uint32_t cap = p.st.cap;
   Counters cn; cn.nearest = cn.shadow = cn.exitray = cn.sky = 0; cn.steps = 0;
   int in_light = 0;
   const uint32_t nround = (n + 31u) & ~31u;  // whole warps so the aggregated pushes stay convergent
@@ -684,7 +705,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocksShade) k_wf_shade(const 
     if (qi < n) {
       path = queue[qi];
       int level;
-      wf_shade_one<CS>(p, stg, path, cn, in_light, cont, want_shadow, level);
+      wf_shade_one<CS>(p, stg, lights, path, cn, in_light, cont, want_shadow, level);
     }
     wf_push(qnext, cnt + 4, cont, path);          // counts[iter+1][0]
     wf_push(p.st.qs[p.iter & 1], cnt + 1, want_shadow, path);  // counts[iter][1]; the request's level == iter

@@ -346,3 +346,31 @@ def test_footprint_and_graph_replay_cost(product):
     print({k: info[k] for k in ("hbm_scene_bytes", "hbm_lane_bytes", "hbm_frame_bytes", "hbm_in_use", "lanes", "lanes_allocated", "graph_replays", "graph_node_updates")})
     assert info["lanes_allocated"] == 4 and info["hbm_in_use"] <= 6 * 2 ** 30
     assert info["graph_replays"] >= 16 and info["graph_node_updates"] <= 2 * info["graph_replays"]
+
+
+def test_render_to_gl_fails_cleanly_without_a_gl_context(product):
+    """vp_render_to_gl (display interop) needs an OpenGL context that owns the texture; the B200 pool is
+    headless, so what can be checked here is the contract around it: VP_ESTATE before any frame, and a clean VP_ECUDA with
+    a message - not a crash - when no GL context is current.  Run in a child process so that a misbehaving GL stack cannot
+    take the test session down."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os
+sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+from _util import abi, params, small_config, vp
+lib = vp.load_product()
+sc, cam, fpd = small_config(1, 64, 36)
+with vp.Session(lib, 0) as s:
+    s.set_scene(sc)
+    assert lib.c_render_to_gl(s.ctx, 1) == abi.VP_ESTATE, "before any frame"
+    s.render(cam, params(fpd))
+    rc = lib.c_render_to_gl(s.ctx, 1)
+    msg = lib.c_last_error().decode()
+    assert rc == abi.VP_ECUDA and "OpenGL" in msg, (rc, msg)
+    s.render(cam, params(fpd))  # the context is still usable
+print("GL-OK")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert "GL-OK" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-1500:])
