@@ -584,34 +584,27 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
     const f3 t = muls(albedo_of(sc, m), sc.mat[m].emissive);
     __stcg(p.st.term + path, make_float4(t.x, t.y, t.z, 0));
   } else {
-    Level L; L.pad = 0; L.ax = L.ay = L.az = 0;
-    Ray nr;
+    // Every material class ends in "spawn the next ray from the hit along rdir" (normalising Ray ctor) and a fold level;
+    // the classes only differ in how rdir, the side of the surface (rn), the medium flag and the level are made.  The
+    // parts they share are executed once, with the lanes of all classes together.
+    int type = 0;
+    f3 M = v3s(1.0f);  // multiplier of a type-0 level
+    f3 rn = ray.N, rdir = v3s(0);
+    int ins = 0;
     bool illum = false;
-    if (m >= 5 && m <= 7) {
-      const f3 refl = reflect3(ray.D, ray.N);
-      const float rough = sc.mat[m].roughness;
-      nr = spawn(offset_ray(isect(ray), ray.N), add(refl, muls(random_sphere_sample(seed), rough)), 0);
-      const f3 al = albedo_of(sc, m);
-      L.type = 0; L.mx = al.x; L.my = al.y; L.mz = al.z;
-    } else if (m <= 4 && p.reproject) {  // TraceNonMetal, renderer.cpp:1342-1358: no Fresnel draw, always the Lambert branch
-      const f3 rdir = add(ray.N, random_sphere_sample(seed));
-      illum = true;
-      nr = spawn(offset_ray(isect(ray), ray.N), rdir, 0);
-      const f3 al = albedo_of(sc, m);
-      L.type = 4; L.mx = al.x; L.my = al.y; L.mz = al.z;
-    } else if (m <= 4) {
-      if (rnd(seed) > schlick_nonmetal(dot3(neg(ray.D), ray.N))) {
-        const f3 rdir = add(ray.N, random_sphere_sample(seed));
-        illum = true;
-        nr = spawn(offset_ray(isect(ray), ray.N), rdir, 0);
-        const f3 al = albedo_of(sc, m);
-        L.type = 1; L.mx = al.x; L.my = al.y; L.mz = al.z;
-      } else {
-        const f3 refl = reflect3(ray.D, ray.N);
-        const float rough = sc.mat[m].roughness;
-        nr = spawn(offset_ray(isect(ray), ray.N), add(refl, muls(random_sphere_sample(seed), rough)), 0);
-        L.type = 3; L.mx = L.my = L.mz = 1.0f;
+    if (m <= 7) {
+      // METAL_* (renderer.cpp:1103-1114) and NON_METAL_* (:1117-1144; TraceNonMetal :1342-1358 in the reprojection mode,
+      // which draws no Fresnel number and always takes the Lambert branch): ONE sphere sample for the lanes of these
+      // classes, after the Fresnel draw of the non-metals - the draw order of each class is unchanged
+      bool mirror = m >= 5;
+      if (m <= 4) {
+        if (p.reproject) type = 4;
+        else { mirror = !(rnd(seed) > schlick_nonmetal(dot3(neg(ray.D), ray.N))); type = mirror ? 3 : 1; }
       }
+      const f3 rs = random_sphere_sample(seed);
+      if (mirror) rdir = add(reflect3(ray.D, ray.N), muls(rs, sc.mat[m].roughness));
+      else { rdir = add(ray.N, rs); illum = true; }
+      if (type == 0) M = albedo_of(sc, m);
     } else if (m == 8) {
       f3 color = v3s(1.0f);
       int inGlass = ray.inside;
@@ -626,11 +619,10 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
       const float ct = stdmin(dot3(neg(ray.D), ray.N), 1.0f);
       const float st = sqrtf(1.0f - ct * ct);
       const bool cannot = ratio * st > 1.0f;
-      f3 rdir, rn;
       if (cannot || schlick(ct, ratio) > rnd(seed)) { rdir = reflect3(ray.D, ray.N); rn = ray.N; }
       else { rdir = refract3(ray.D, ray.N, ratio); inGlass = !inGlass; rn = neg(ray.N); }
-      nr = spawn(offset_ray(isect(ray), rn), rdir, inGlass);
-      L.type = 0; L.mx = color.x; L.my = color.y; L.mz = color.z;
+      ins = inGlass;
+      M = color;
     } else if (m >= 9 && m <= 14) {
       f3 color = v3s(1.0f);
       int inGlass = ray.inside;
@@ -656,30 +648,29 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
       }
       color = absorption(color, intensity, dist);
       if (!insideVolume) { ray.O = add(ray.O, muls(ray.D, ray.t)); ray.t = 0; }
-      const f3 rdir = refract3(ray.D, ray.N, 1.0f);
-      inGlass = !inGlass;
-      nr = spawn(offset_ray(isect(ray), neg(ray.N)), rdir, inGlass);
-      L.type = 0; L.mx = color.x; L.my = color.y; L.mz = color.z;
+      rdir = refract3(ray.D, ray.N, 1.0f);
+      rn = neg(ray.N);
+      ins = !inGlass;
+      M = color;
     } else {
-      const f3 rdir = diffuse_reflection(seed, ray.N);
+      rdir = diffuse_reflection(seed, ray.N);
       illum = true;
-      nr = spawn(offset_ray(isect(ray), ray.N), rdir, 0);
-      const f3 al = albedo_of(sc, m);
-      L.type = 2; L.mx = al.x; L.my = al.y; L.mz = al.z;
+      type = 2;
     }
     f3 A = v3s(0);
-    if (illum) { wf_light_request<CS>(p, lights, path, top, L.type, ray, seed, want_shadow, A); level = top; }
+    if (illum) { wf_light_request<CS>(p, lights, path, top, type, ray, seed, want_shadow, A); level = top; }
     // one record per level: the multiplier itself for type 0, else the light term (the shadow stage overwrites it when the
     // sample was queued) - M is then the material's albedo, which the resolve stage looks up again
-    const f3 rec = L.type == 0 ? v3(L.mx, L.my, L.mz) : A;
-    __stcg(p.st.lv + (size_t)top * cap + path, make_float4(rec.x, rec.y, rec.z, __uint_as_float((uint32_t)L.type | ((uint32_t)(m & 255) << 8))));
+    const f3 rec = type == 0 ? M : A;
+    __stcg(p.st.lv + (size_t)top * cap + path, make_float4(rec.x, rec.y, rec.z, __uint_as_float((uint32_t)type | ((uint32_t)(m & 255) << 8))));
     top++; depth--;
     cont = depth >= 0 && top < VP_MAX_LEVELS;  // Trace(depth < 0) returns 0: term stays 0
     if (cont) {
-      __stcg(p.st.r0 + path, make_float4(nr.O.x, nr.O.y, nr.O.z, __uint_as_float(pack_r0w(nr.inside, depth, top))));
+      const Ray nr = spawn(offset_ray(isect(ray), rn), rdir, ins);
+      __stcg(p.st.r0 + path, make_float4(nr.O.x, nr.O.y, nr.O.z, __uint_as_float(pack_r0w(ins, depth, top))));
       __stcg(p.st.r1 + path, make_float4(nr.D.x, nr.D.y, nr.D.z, __uint_as_float(seed)));
     } else {
-      __stcg(&p.st.r0[path].w, __uint_as_float(pack_r0w(nr.inside, depth, top)));
+      __stcg(&p.st.r0[path].w, __uint_as_float(pack_r0w(ins, depth, top)));
     }
   }
 
