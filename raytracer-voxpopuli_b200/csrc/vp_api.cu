@@ -93,7 +93,7 @@ struct WfLane {
   DevBuf<unsigned char> d_wf;
   uint32_t cap = 0;
   int levels = 0, samples = 0;
-  bool prims = false, prepared = false, masks = false;  // optional parts laid out
+  bool prims = false, prepared = false, masks = false, area = false;  // optional parts laid out
   size_t bytes = 0;
 };
 constexpr int kLanes = 6;       // most frames in flight (c->nlanes are used: 4 unless VP_LANES says otherwise)
@@ -314,24 +314,25 @@ int grid_blocks(const vp_ctx* c, long long work_warps)
 // path state of one lane (HBM-resident, sized for the largest pass / depth seen).  Optional parts are only laid out when
 // a scene needs them: primitive normals (spheres / triangles), prepared walks (passes that overlap), candidate masks
 // (multi-volume scenes).
-struct WfNeed { uint32_t cap; int levels, samples; bool prims, prepared, masks; };
+struct WfNeed { uint32_t cap; int levels, samples; bool prims, prepared, masks, area; };
 int wf_reserve(WfLane& L, const WfNeed& nd, size_t* bytes_only = nullptr)
 {
   if (bytes_only) *bytes_only = 0;
   if (nd.cap <= L.cap && nd.levels <= L.levels && nd.samples <= L.samples && (!nd.prims || L.prims) && (!nd.prepared || L.prepared) &&
-      (!nd.masks || L.masks) && L.d_wf.p)
+      (!nd.masks || L.masks) && (!nd.area || L.area) && L.d_wf.p)
     return 0;
   const uint32_t cap = nd.cap > L.cap ? nd.cap : L.cap;
   const int levels = nd.levels > L.levels ? nd.levels : L.levels;
   const int samples = nd.samples > L.samples ? nd.samples : L.samples;
-  const bool prims = nd.prims || L.prims, prepared = nd.prepared || L.prepared, masks = nd.masks || L.masks;
+  const bool prims = nd.prims || L.prims, prepared = nd.prepared || L.prepared, masks = nd.masks || L.masks, area = nd.area || L.area;
   const size_t f4 = sizeof(float4);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_r0 = take(cap * f4), o_r1 = take(cap * f4), o_h0 = take(cap * 8), o_h1 = take(cap * 4), o_hn = take(prims ? cap * f4 : 0), o_term = take(cap * f4);
   const size_t o_lv = take((size_t)levels * cap * f4);
-  const size_t o_sq0 = take((size_t)2 * cap * f4), o_sqd = take((size_t)2 * samples * cap * f4), o_sql = take((size_t)2 * samples * cap * f4);
-  const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_qs = take(2 * cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
+  const size_t o_rq0 = take((size_t)2 * cap * f4), o_rq1 = take((size_t)2 * cap * f4), o_rq2 = take((size_t)2 * cap * f4);
+  const size_t o_sqd = take(area ? (size_t)2 * samples * cap * f4 : 0), o_sql = take(area ? (size_t)2 * samples * cap * f4 : 0);
+  const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
   const size_t o_ps = take(prepared ? 3 * cap * f4 : 0);  // prepared walks of the bounce being extended, by queue position
   const size_t o_sm = take(masks ? (size_t)samples * cap * 4 : 0);  // bounding-sphere candidates of the bounce's shadow rays
   if (bytes_only) { *bytes_only = off; return 0; }  // what growing this lane would take
@@ -342,12 +343,12 @@ int wf_reserve(WfLane& L, const WfNeed& nd, size_t* bytes_only = nullptr)
   w.cap = cap;
   w.r0 = (float4*)(b + o_r0); w.r1 = (float4*)(b + o_r1); w.h0 = (float2*)(b + o_h0); w.h1 = (uint32_t*)(b + o_h1); w.hn = (float4*)(b + o_hn);
   w.term = (float4*)(b + o_term); w.lv = (float4*)(b + o_lv);
-  w.sq0 = (float4*)(b + o_sq0); w.sqd = (float4*)(b + o_sqd); w.sql = (float4*)(b + o_sql); w.nsamp = (uint32_t)samples;
-  for (int k = 0; k < 2; k++) w.qs[k] = (uint32_t*)(b + o_qs) + (size_t)k * cap;
+  w.rq0 = (float4*)(b + o_rq0); w.rq1 = (float4*)(b + o_rq1); w.rq2 = (float4*)(b + o_rq2);
+  w.sqd = (float4*)(b + o_sqd); w.sql = (float4*)(b + o_sql); w.nsamp = (uint32_t)samples;
   w.q[0] = (uint32_t*)(b + o_q0); w.q[1] = (uint32_t*)(b + o_q1); w.counts = (uint32_t*)(b + o_cnt);
   for (int k = 0; k < 3; k++) w.ps[k] = (float4*)(b + o_ps) + (size_t)k * cap;
   w.smask = (uint32_t*)(b + o_sm);
-  L.cap = cap; L.levels = levels; L.samples = samples; L.prims = prims; L.prepared = prepared; L.masks = masks;
+  L.cap = cap; L.levels = levels; L.samples = samples; L.prims = prims; L.prepared = prepared; L.masks = masks; L.area = area;
   L.bytes = off;
   return 0;
 }
@@ -638,7 +639,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   p.prepared = c->tune_prepare && piped && c->tune_brickwalk && !(fp->flags & VP_FLAG_COUNT_STEPS) && c->sc.nvol <= 60;
   WfNeed need;
   need.cap = cap; need.levels = levels; need.samples = samples;
-  need.prims = c->sc.nsph + c->sc.ntri > 0; need.prepared = p.prepared != 0; need.masks = c->sc.nvol > 1 && c->sc.nvol <= 32;
+  need.prims = c->sc.nsph + c->sc.ntri > 0; need.prepared = p.prepared != 0; need.masks = c->sc.nvol > 1 && c->sc.nvol <= 32; need.area = c->sc.nal > 0;
   // Persistent grids follow the number of paths this call can have: a warp that gets only ~1 ray per lane never refills
   // and ends at the SIMD efficiency of its longest ray, so small shards run fewer, longer-lived warps (>= 3 blocks per SM
   // to keep latency hidden; measured on 1/8 frame shares, profiles/README.md).

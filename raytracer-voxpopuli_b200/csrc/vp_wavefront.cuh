@@ -65,17 +65,22 @@ struct WfState {
   // multiplier is a computed colour), else A (the light term; M is then the material's albedo, looked up by the resolve
   // stage) - half the bytes of separate M / A arrays
   float4* lv;
-  // shadow requests, one slot per (bounce parity, path): shadow(k) runs on the lane's side stream while the path is
-  // extended and shaded again; shade(k + 2) waits for it before it reuses the slot
+  // Shadow requests of a bounce, indexed by POSITION in the bounce's request queue (bounce parity: shadow(k) runs on the
+  // lane's side stream while the path is extended and shaded again; shade(k + 2) waits for it before it reuses the slots).
+  // The shade stage gets the position from its aggregated append and writes the records there, so the shadow stage finds
+  // everything a single-light request needs with ONE trip to memory after its ticket instead of four dependent ones
+  // (queue entry -> request head -> light term -> direction: 22 % of its warp time, profiles/r2a):
+  float4* rq0;      // [parity][pos]: origin.xyz, w = bits nsamp(8) | level(5) << 8 | type(3) << 13 | area(1) << 16 | mat(8) << 24
+  float4* rq1;      // [parity][pos]: single-light requests: dir.xyz, w = dist
+  float4* rq2;      // [parity][pos]: li.xyz (single lights: the final contribution), w = path id
+  // area-light requests keep their samples by path (laid out only when the scene has area lights)
   uint32_t nsamp;   // samples allocated per request (>= area_samples)
-  float4* sq0;      // [parity][path]: origin.xyz, w = bits nsamp(8) | level(5) << 8 | type(3) << 13 | area(1) << 16 | mat(8) << 24
   float4* sqd;      // [parity][sample][path]: dir.xyz, w = dist
-  float4* sql;      // [parity][sample][path]: li.xyz (single lights: final contribution), w = valid
+  float4* sql;      // [parity][sample][path]: li.xyz, w = valid
   uint32_t* smask;      // [sample][path]: volumes that pass the bounding-sphere pre-test for the shadow ray (k_wf_shadow_mask)
   float4* ps[3];        // prepared walks [queue position]: 0 = tmax.xyz, t; 1 = tdelta.xyz, P' bits; 2 = E.xyz, flags (k_wf_prepare)
   uint32_t* q[2];       // active-path queues (ping-pong)
-  uint32_t* qs[2];      // shadow-request queues (bounce parity)
-  uint32_t* counts;     // [iter][4]: 0 = active count entering iter, 1 = shadow count of iter, 2 = extend cursor, 3 = shadow cursor
+  uint32_t* counts;     // [iter][4]: 0 = active count entering iter, 1 = shadow requests of iter, 2 = extend cursor, 3 = shadow cursor
 };
 
 struct WfParams {
@@ -443,6 +448,18 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
 // One lane per path of the iteration's queue.  Emits the next ray, the fold level and, where
 // Illumination() would run, a shadow request (the RNG draws of the light sample happen here, in
 // the reference's order; only the occlusion tests are deferred to K4).
+// Appends the lanes that call it with want == true (a subset of the lanes executing this code together) to the shadow-request
+// queue of the bounce: one aggregated atomicAdd per converged group; returns the lane's position.
+__device__ __forceinline__ uint32_t wf_request_slot(uint32_t* counter)
+{
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
 template <bool CS>
 __device__ __forceinline__ void wf_light_request(const WfParams& p, const Lights& lights, uint32_t path, int level, int type, const Ray& ray,
                                                  uint32_t& seed, bool& queued, f3& A_now)
@@ -457,12 +474,15 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, const Lights
   queued = false;
   A_now = muls(v3s(0), (float)lightCount);
   const uint32_t cap = p.st.cap;
-  const size_t slot = (size_t)(level & 1);  // in the staged pipeline the level of a request is the bounce index
-  float4* const sq0 = p.st.sq0 + slot * cap;
-  float4* const sqd = p.st.sqd + slot * p.st.nsamp * cap;
-  float4* const sql = p.st.sql + slot * p.st.nsamp * cap;
+  const size_t par = (size_t)(level & 1);  // in the staged pipeline the level of a request is the bounce index
+  float4* const rq0 = p.st.rq0 + par * cap;
+  float4* const rq1 = p.st.rq1 + par * cap;
+  float4* const rq2 = p.st.rq2 + par * cap;
+  uint32_t* const counter = p.st.counts + 4 * level + 1;
   const uint32_t tag = ((uint32_t)level << 8) | ((uint32_t)type << 13) | ((uint32_t)(ray.mat & 255) << 24);
   if (idx >= (uint32_t)sc.npl && idx < (uint32_t)(sc.nal + sc.npl)) {
+    float4* const sqd = p.st.sqd + par * p.st.nsamp * cap;
+    float4* const sql = p.st.sql + par * p.st.nsamp * cap;
     const VpAreaLight L = lights.al[idx - sc.npl];
     const f3 center = ld3(L.position);
     const float radius = L.radius;
@@ -488,7 +508,9 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, const Lights
       sql[(size_t)i * cap + path] = make_float4(li.x, li.y, li.z, valid ? 1.0f : 0.0f);
     }
     if (nvalid > 0) {
-      sq0[path] = make_float4(point.x, point.y, point.z, __uint_as_float((uint32_t)sc.area_samples | (1u << 16) | tag));
+      const uint32_t pos = wf_request_slot(counter);
+      rq0[pos] = make_float4(point.x, point.y, point.z, __uint_as_float((uint32_t)sc.area_samples | (1u << 16) | tag));
+      rq2[pos] = make_float4(0, 0, 0, __uint_as_float(path));
       queued = true;
     } else {
       // inc = (0 / n) * k * lightCount, as the reference computes it
@@ -527,9 +549,10 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, const Lights
     }
     if (lit) {
       const f3 org = offset_ray(ip, n);
-      sq0[path] = make_float4(org.x, org.y, org.z, __uint_as_float(1u | tag));
-      sqd[path] = make_float4(dirn.x, dirn.y, dirn.z, tshadow);
-      sql[path] = make_float4(contrib.x, contrib.y, contrib.z, 1.0f);
+      const uint32_t pos = wf_request_slot(counter);
+      rq0[pos] = make_float4(org.x, org.y, org.z, __uint_as_float(1u | tag));
+      rq1[pos] = make_float4(dirn.x, dirn.y, dirn.z, tshadow);
+      rq2[pos] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(path));
       queued = true;
     }
   }
@@ -699,7 +722,6 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocksShade) k_wf_shade(const 
       wf_shade_one<CS>(p, stg, lights, path, cn, in_light, cont, want_shadow, level);
     }
     wf_push(qnext, cnt + 4, cont, path);          // counts[iter+1][0]
-    wf_push(p.st.qs[p.iter & 1], cnt + 1, want_shadow, path);  // counts[iter][1]; the request's level == iter
   }
   wf_add_counter(p.counters + 6, cn.sky);
   wf_add_counter(p.counters + 2, cn.exitray);
@@ -716,23 +738,27 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow_mask(const __grid_consta
   const uint32_t n = p.st.counts[4 * p.iter + 1];
   const uint32_t cap = p.st.cap;
   const int nvol = p.sc.nvol;
-  const uint32_t* queue = p.st.qs[p.iter & 1];
-  const float4* const sq0 = p.st.sq0 + (size_t)(p.iter & 1) * cap;
-  const float4* const sqd = p.st.sqd + (size_t)(p.iter & 1) * p.st.nsamp * cap;
-  const float4* const sql = p.st.sql + (size_t)(p.iter & 1) * p.st.nsamp * cap;
+  const size_t par = (size_t)(p.iter & 1);
+  const float4* const rq0 = p.st.rq0 + par * cap;
+  const float4* const rq1 = p.st.rq1 + par * cap;
+  const float4* const rq2 = p.st.rq2 + par * cap;
+  const float4* const sqd = p.st.sqd + par * p.st.nsamp * cap;
+  const float4* const sql = p.st.sql + par * p.st.nsamp * cap;
   for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
-    const uint32_t path = queue[qi];
-    const float4 q0 = sq0[path];
+    const float4 q0 = rq0[qi];
     const f3 org = v3(q0.x, q0.y, q0.z);
-    const int nsamp = (int)(__float_as_uint(q0.w) & 255u);
+    const uint32_t bits = __float_as_uint(q0.w);
+    const int nsamp = (int)(bits & 255u);
+    const bool area = (bits >> 16) & 1u;
+    const uint32_t path = __float_as_uint(rq2[qi].w);
     for (int sample = 0; sample < nsamp; sample++) {
-      if (sql[(size_t)sample * cap + path].w == 0.0f) continue;
-      const float4 d4 = sqd[(size_t)sample * cap + path];
+      if (area && sql[(size_t)sample * cap + path].w == 0.0f) continue;
+      const float4 d4 = area ? sqd[(size_t)sample * cap + path] : rq1[qi];
       const f3 D = normalize3(v3(d4.x, d4.y, d4.z));  // as the shadow stage builds the ray
       uint32_t m = 0;
       for (int vi = 0; vi < nvol; vi++)
         if (volume_may_hit(p.sc.vol[vi], org, D)) m |= 1u << vi;
-      p.st.smask[(size_t)sample * cap + path] = m;
+      p.st.smask[(size_t)sample * cap + qi] = m;  // by queue position
     }
   }
 }
@@ -753,13 +779,15 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow(const __grid_const
   const int nvol = sc.nvol;
   const float lightCount = (float)(uint32_t)(sc.npl + sc.nsl + sc.nal + 1);
   const int par = p.iter & 1;
-  const float4* const sq0 = p.st.sq0 + (size_t)par * cap;  // the request slot of this bounce (its level is the bounce index)
-  const float4* const sqd = p.st.sqd + (size_t)par * p.st.nsamp * cap;
+  const float4* const rq0 = p.st.rq0 + (size_t)par * cap;  // the requests of this bounce, by queue position
+  const float4* const rq1 = p.st.rq1 + (size_t)par * cap;
+  const float4* const rq2 = p.st.rq2 + (size_t)par * cap;
+  const float4* const sqd = p.st.sqd + (size_t)par * p.st.nsamp * cap;  // area-light samples, by path
   const float4* const sql = p.st.sql + (size_t)par * p.st.nsamp * cap;
   const bool use_mask = BWK && p.prepared && nvol > 1 && nvol <= 32;  // k_wf_shadow_mask ran for this bounce
   uint32_t cand = 0;
   bool has_req = false, has_ray = false, in_dda = false, exhausted = false;
-  uint32_t path = 0, bits = 0;
+  uint32_t path = 0, bits = 0, pos = 0;
   int nsamp = 0, sample = 0, vi = 0;
   f3 org = v3s(0), D = v3s(0), inc = v3s(0), li = v3s(0);
   float tmaxray = 0;
@@ -781,13 +809,23 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow(const __grid_const
       if (need) {
         const uint32_t qi = base + (uint32_t)__popc(nm & ((1u << lane) - 1u));
         if (qi < n) {
-          path = p.st.qs[par][qi];
-          const float4 q0 = sq0[path];
+          // one trip to memory: head, ray and light term of the request sit at its queue position
+          const float4 q0 = __ldcs(rq0 + qi), q1 = __ldcs(rq1 + qi), q2 = __ldcs(rq2 + qi);
           org = v3(q0.x, q0.y, q0.z);
           bits = __float_as_uint(q0.w);
+          path = __float_as_uint(q2.w);
+          pos = qi;
           nsamp = (int)(bits & 255u);
           sample = 0; inc = v3s(0);
           has_req = true; has_ray = false; in_dda = false;
+          if (!(bits & (1u << 16))) {  // single light: this is the ray
+            D = normalize3(v3(q1.x, q1.y, q1.z));  // normalising Ray ctor of the shadow ray
+            tmaxray = q1.w;
+            li = v3(q2.x, q2.y, q2.z);
+            if (use_mask) cand = p.st.smask[qi];
+            vi = 0; has_ray = true;
+            nrays++;
+          }
         } else exhausted = true;
       }
     }
@@ -829,7 +867,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow(const __grid_const
             D = normalize3(v3(d4.x, d4.y, d4.z));  // normalising Ray ctor of the shadow ray
             tmaxray = d4.w;
             li = v3(l4.x, l4.y, l4.z);
-            if (use_mask) cand = p.st.smask[(size_t)sample * cap + path];
+            if (use_mask) cand = p.st.smask[(size_t)sample * cap + pos];
             vi = 0; has_ray = true; found = true;
             nrays++;
             break;
