@@ -120,6 +120,7 @@ struct vp_ctx {
   WfLane lane[kLanes];
   int next_lane = 0;
   int nlanes = 4;      // frames in flight (VP_LANES); lowered only when a lane's path state cannot be allocated
+  bool lanes_fixed = false;
   cudaEvent_t ev_in = nullptr;      // recorded on the caller's stream when a render call enters
   cudaEvent_t ev_direct = nullptr;  // recorded after a launch made directly on the caller's stream (single-kernel formulations)
   bool direct_recorded = false;
@@ -665,11 +666,13 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   CU(cudaEventRecord(c->ev_in, stream));
   bool entered[kLanes] = {};
   const bool rotate = overlap || fp->spp > 1;  // lanes rotate only when passes can overlap (several samples in this call, or a deferred call)
+  // small shards (a rank's share of a multi-GPU frame) are latency-bound: two more passes in flight, their state is small
+  const int lanes = (!c->lanes_fixed && cap <= (1u << 19) && c->nlanes + 2 <= kLanes) ? c->nlanes + 2 : c->nlanes;
   const int passes = rp ? 1 : fp->spp;
   for (int s = 0; s < passes; s++) {
     p.frame = fp->frame_index + (uint32_t)s;
     p.write_rgb8 = (s == passes - 1);
-    int li = rotate ? (c->next_lane++ % c->nlanes) : 0;
+    int li = rotate ? (c->next_lane++ % lanes) : 0;
     if (int rc = wf_reserve(c->lane[li], need)) {  // grows the lane when this call needs more (synchronises the device then)
       if (li == 0) return rc;
       cudaGetLastError();  // out of memory for another lane: keep the frames in flight that fit
@@ -863,7 +866,7 @@ vp_ctx* vp_create(int device)
   // tuning knobs for experiments (defaults are the shipped values)
   if (const char* e = getenv("VP_PATHS_PER_THREAD")) c->tune_paths_per_thread = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("VP_MIN_BLOCKS")) c->tune_min_blocks = atoi(e) < 1 ? 1 : atoi(e);
-  if (const char* e = getenv("VP_LANES")) { const int n = atoi(e); c->nlanes = n < 1 ? 1 : (n > kLanes ? kLanes : n); }
+  if (const char* e = getenv("VP_LANES")) { const int n = atoi(e); c->nlanes = n < 1 ? 1 : (n > kLanes ? kLanes : n); c->lanes_fixed = true; }
   if (const char* e = getenv("VP_BULK_LANES")) c->tune_bulk = atoi(e);
   if (const char* e = getenv("VP_REFILL")) c->tune_refill = atoi(e);
   if (const char* e = getenv("VP_BRICKWALK")) c->tune_brickwalk = atoi(e);
