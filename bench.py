@@ -211,12 +211,13 @@ def async_e2e(lib, sess, cc, fpd, steps, W, H, torch, in_flight=3):
         if len(tickets) > in_flight:
             lib.check(lib.c_render_wait(sess.ctx, tickets[-1 - in_flight]), "render_wait")
 
-    for i in range(3):
+    WARM = 8  # every lane of every device has allocated its path state and captured its graph (up to six lanes for small shards)
+    for i in range(WARM):
         issue(i)
     lib.check(lib.c_render_wait(sess.ctx, tickets[-1]), "render_wait")
     lib.check(lib.c_stats_begin(sess.ctx), "stats_begin")
     t0 = time.perf_counter()
-    for i in range(3, 3 + steps):
+    for i in range(WARM, WARM + steps):
         issue(i)
     lib.check(lib.c_render_wait(sess.ctx, tickets[-1]), "render_wait")
     dt = time.perf_counter() - t0
@@ -353,10 +354,10 @@ def main():
     sampler = ClockSampler(local, period_s=float(os.environ.get("VP_BENCH_CLOCK_PERIOD", "0.02")))
     if os.environ.get("VP_BENCH_NO_SAMPLER") != "1":
         sampler.start()
-    # set-up, not warm-up: the first frame on each of the library's four lanes allocates that lane's path state and
+    # set-up, not warm-up: the first frame on each of the library's lanes (four, six for small shards) allocates that lane's path state and
     # captures its CUDA graph (into a scratch accumulator; frame indices of the measured frames are untouched)
     scratch = torch.zeros_like(accum)
-    for k in range(4):
+    for k in range(6):
         fp0 = frame_params(fpd, frame_index=0, flags=abi.VP_FLAG_DEFER, **shard)
         lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp0), scratch.data_ptr(), None, stream.cuda_stream, None), "render_device(set-up)")
     fence(stream)
