@@ -7,7 +7,11 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "vp_kernels.cuh"
@@ -100,12 +104,24 @@ constexpr int kLanes = 6;       // most frames in flight (c->nlanes are used: 4 
 constexpr int kCallRing = 8;    // completion events kept for vp_render_fence
 
 constexpr int kTickets = 16;     // vp_render_async calls whose completion events are kept
+// One host thread per device of a multi-device context: a frame is ~25 runtime calls per device (copies, graph launch,
+// events); issued from one thread they add up to more than a 1/8 frame takes on the GPUs.
+struct KidWorker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has_job = false, done = true, quit = false;
+  int rc = 0;
+  std::string err;
+};
 struct vp_ctx {
   // ---- multi-device context (vp_create_multi): owns one single-device context per GPU, the scene replicated on each;
   // render calls shard the frame as interleaved 8-row tiles (tile k -> kids[k mod n]) ----
   bool group = false;
   bool peer_ok = false;            // every device can store into kids[0]'s memory (NVLink / PCIe peer access)
   std::vector<vp_ctx*> kids;
+  std::vector<KidWorker*> workers;  // one per kid (VP_GROUP_THREADS=0: issue from the calling thread)
   cudaEvent_t gev_in = nullptr;    // recorded on the caller's stream (device of kids[0]) when a device-buffer call enters
   unsigned long long gtickets[kTickets][16] = {};
   // ---- asynchronous host-buffer frames (vp_render_async / vp_render_wait) ----
@@ -885,6 +901,12 @@ void vp_destroy(vp_ctx* c)
 {
   if (!c) return;
   if (c->group) {
+    for (KidWorker* w : c->workers) {
+      { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; }
+      w->cv.notify_all();
+      if (w->th.joinable()) w->th.join();
+      delete w;
+    }
     for (vp_ctx* k : c->kids) vp_destroy(k);
     if (c->gev_in) { cudaSetDevice(c->device); cudaEventDestroy(c->gev_in); }
     delete c;

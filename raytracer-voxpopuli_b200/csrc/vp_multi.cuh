@@ -77,15 +77,66 @@ int g_shard(const vp_ctx* g, const VpFrameParams* fp, int d, VpFrameParams& f)
   return 0;
 }
 
+void worker_main(KidWorker* w)
+{
+  for (;;) {
+    std::function<int()> job;
+    {
+      std::unique_lock<std::mutex> lk(w->mu);
+      w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+      if (w->quit) return;
+      job = std::move(w->job);
+      w->has_job = false;
+    }
+    const int rc = job();
+    {
+      std::lock_guard<std::mutex> lk(w->mu);
+      w->rc = rc;
+      w->err = rc ? g_err : std::string();  // the message lives in the worker's thread-local slot: hand it over
+      w->done = true;
+    }
+    w->cv.notify_all();
+  }
+}
+
+// run one job per device (on the device's worker thread when the group has them) and wait for all of them
+int g_parallel(vp_ctx* g, const std::function<int(size_t)>& per_kid)
+{
+  if (g->workers.empty()) {
+    for (size_t d = 0; d < g->kids.size(); d++)
+      if (int rc = per_kid(d)) return rc;
+    return 0;
+  }
+  for (size_t d = 0; d < g->kids.size(); d++) {
+    KidWorker* w = g->workers[d];
+    {
+      std::lock_guard<std::mutex> lk(w->mu);
+      w->job = [&per_kid, d] { return per_kid(d); };
+      w->has_job = true; w->done = false;
+    }
+    w->cv.notify_all();
+  }
+  int rc = 0;
+  for (KidWorker* w : g->workers) {
+    std::unique_lock<std::mutex> lk(w->mu);
+    w->cv.wait(lk, [&] { return w->done; });
+    if (w->rc && !rc) { rc = w->rc; g_err = w->err; }
+  }
+  return rc;
+}
+
 int g_render_async(vp_ctx* g, const VpCamera* cam, const VpFrameParams* fp, const float* accum_in, float* accum_out, uint32_t* rgb8_out,
                    unsigned long long* ticket)
 {
   const int slot = (int)(g->nticket % kTickets);
-  for (size_t d = 0; d < g->kids.size(); d++) {
+  VpFrameParams probe;
+  if (int rc = g_shard(g, fp, 0, probe)) return rc;
+  const int rc = g_parallel(g, [&](size_t d) -> int {
     VpFrameParams f;
-    if (int rc = g_shard(g, fp, (int)d, f)) return rc;
-    if (int rc = single_render_async(g->kids[d], cam, &f, accum_in, accum_out, rgb8_out, &g->gtickets[slot][d])) return rc;
-  }
+    if (int r = g_shard(g, fp, (int)d, f)) return r;
+    return single_render_async(g->kids[d], cam, &f, accum_in, accum_out, rgb8_out, &g->gtickets[slot][d]);
+  });
+  if (rc) return rc;
   *ticket = ++g->nticket;
   return 0;
 }
@@ -170,16 +221,19 @@ int g_render_device(vp_ctx* g, const VpCamera* cam, const VpFrameParams* fp, voi
   CU(cudaEventRecord(g->gev_in, stream));
   const bool defer = !stats && (fp->flags & VP_FLAG_DEFER) != 0;
   cudaEvent_t done[16];
-  for (size_t d = 0; d < g->kids.size(); d++) {
-    vp_ctx* k = g->kids[d];
-    VpFrameParams f;
-    if (int rc = g_shard(g, fp, (int)d, f)) return rc;
-    f.flags |= VP_FLAG_DEFER;
-    if (bind(k)) return VP_ECUDA;
-    CU(cudaStreamWaitEvent(k->stream, g->gev_in, 0));  // the device's passes start after what the caller's stream held
-    done[d] = k->ev_call[k->ncalls % kCallRing];
-    if (int rc = launch_render(k, cam, &f, (float4*)accum_dev, (uint32_t*)rgb8_dev, k->stream, nullptr, true)) return rc;
-  }
+  VpFrameParams probe;
+  if (int rc = g_shard(g, fp, 0, probe)) return rc;
+  if (int rc = g_parallel(g, [&](size_t d) -> int {
+        vp_ctx* k = g->kids[d];
+        VpFrameParams f;
+        if (int r = g_shard(g, fp, (int)d, f)) return r;
+        f.flags |= VP_FLAG_DEFER;
+        if (bind(k)) return VP_ECUDA;
+        CU(cudaStreamWaitEvent(k->stream, g->gev_in, 0));  // the device's passes start after what the caller's stream held
+        done[d] = k->ev_call[k->ncalls % kCallRing];
+        return launch_render(k, cam, &f, (float4*)accum_dev, (uint32_t*)rgb8_dev, k->stream, nullptr, true);
+      }))
+    return rc;
   if (bind(k0)) return VP_ECUDA;
   if (!defer)
     for (size_t d = 0; d < g->kids.size(); d++) CU(cudaStreamWaitEvent(stream, done[d], 0));
@@ -298,6 +352,13 @@ vp_ctx* vp_create_multi(const int* devices, int ndev)
     const cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
     if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) g->peer_ok = false;
     cudaGetLastError();
+  }
+  if (!(getenv("VP_GROUP_THREADS") && atoi(getenv("VP_GROUP_THREADS")) == 0)) {
+    for (int i = 0; i < ndev; i++) {
+      KidWorker* w = new KidWorker;
+      w->th = std::thread(worker_main, w);
+      g->workers.push_back(w);
+    }
   }
   cudaSetDevice(devices[0]);
   if (cudaEventCreateWithFlags(&g->gev_in, cudaEventDisableTiming) != cudaSuccess) {
