@@ -345,7 +345,7 @@ int wf_reserve(WfLane& L, const WfNeed& nd, size_t* bytes_only = nullptr)
   const size_t f4 = sizeof(float4);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  const size_t o_r0 = take(cap * f4), o_r1 = take(cap * f4), o_h0 = take(cap * 8), o_h1 = take(cap * 4), o_hn = take(prims ? cap * f4 : 0), o_term = take(cap * f4);
+  const size_t o_r0 = take(2 * cap * f4), o_r1 = take(2 * cap * f4), o_h0 = take(cap * 8), o_h1 = take(cap * 4), o_hn = take(prims ? cap * f4 : 0), o_term = take(cap * f4);
   const size_t o_lv = take((size_t)levels * cap * f4);
   const size_t o_rq0 = take((size_t)2 * cap * f4), o_rq1 = take((size_t)2 * cap * f4), o_rq2 = take((size_t)2 * cap * f4);
   const size_t o_sqd = take(area ? (size_t)2 * samples * cap * f4 : 0), o_sql = take(area ? (size_t)2 * samples * cap * f4 : 0);
@@ -358,7 +358,8 @@ int wf_reserve(WfLane& L, const WfNeed& nd, size_t* bytes_only = nullptr)
   unsigned char* b = L.d_wf.p;
   WfState& w = L.wf;
   w.cap = cap;
-  w.r0 = (float4*)(b + o_r0); w.r1 = (float4*)(b + o_r1); w.h0 = (float2*)(b + o_h0); w.h1 = (uint32_t*)(b + o_h1); w.hn = (float4*)(b + o_hn);
+  for (int k = 0; k < 2; k++) { w.r0[k] = (float4*)(b + o_r0) + (size_t)k * cap; w.r1[k] = (float4*)(b + o_r1) + (size_t)k * cap; }
+  w.h0 = (float2*)(b + o_h0); w.h1 = (uint32_t*)(b + o_h1); w.hn = (float4*)(b + o_hn);
   w.term = (float4*)(b + o_term); w.lv = (float4*)(b + o_lv);
   w.rq0 = (float4*)(b + o_rq0); w.rq1 = (float4*)(b + o_rq1); w.rq2 = (float4*)(b + o_rq2);
   w.sqd = (float4*)(b + o_sqd); w.sql = (float4*)(b + o_sql); w.nsamp = (uint32_t)samples;

@@ -55,12 +55,15 @@ constexpr int kMaxAreaSamples = 8;    // numCheckShadowsAreaLight supported by t
 // Per-path state, structure of arrays over `cap` paths.
 struct WfState {
   uint32_t cap;
-  float4* r0;    // O.xyz, w = bits: inside(1) | depth+1 (8 bits << 8) | top (8 bits << 16)
-  float4* r1;    // D.xyz (normalised), w = RNG state bits
-  float2* h0;    // hit: t, P bits (cell of the hit inside volume `vol`, brick-major)
-  uint32_t* h1;  // hit: (vol + 2) << 8; primitive hits: mat (8) | 1 << 8 | inside << 30 | 1 << 31
-  float4* hn;    // primitive hits only: normal
-  float4* term;  // terminal radiance (sky / emissive / 0)
+  // The ray of a path lives at its POSITION in the bounce's queue (bounce parity): the shade stage writes the next ray where
+  // its append put the path, so prepare / extend / shade read rays, hits and path ids of a bounce coalesced and without
+  // waiting for the queue entry first (the path id is only needed for what outlives the bounce: levels, term, requests).
+  float4* r0[2]; // [parity][pos]: O.xyz, w = bits: inside(1) | depth+1 (8 bits << 8) | top (8 bits << 16)
+  float4* r1[2]; // [parity][pos]: D.xyz (normalised), w = RNG state bits
+  float2* h0;    // [pos] hit: t, P bits (cell of the hit inside volume `vol`, brick-major)
+  uint32_t* h1;  // [pos] hit: (vol + 2) << 8; primitive hits: mat (8) | 1 << 8 | inside << 30 | 1 << 31
+  float4* hn;    // [pos] primitive hits only: normal
+  float4* term;  // [path] terminal radiance (sky / emissive / 0), w = number of fold levels of the path
   // fold levels, ONE record per (level, path): w = type (bits 0..2) | material (bits 8..15); xyz = M for type 0 (the
   // multiplier is a computed colour), else A (the light term; M is then the material's albedo, looked up by the resolve
   // stage) - half the bytes of separate M / A arrays
@@ -191,16 +194,19 @@ __device__ __forceinline__ bool wf_block_has_work(const uint32_t* taken, uint32_
   return go != 0;
 }
 // warp-aggregated append of one id per participating lane
-__device__ __forceinline__ void wf_push(uint32_t* queue, uint32_t* counter, bool want, uint32_t id)
+// returns the queue position of the lane's id (only meaningful where `want`)
+__device__ __forceinline__ uint32_t wf_push(uint32_t* queue, uint32_t* counter, bool want, uint32_t id)
 {
   const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
-  if (!m) return;
+  if (!m) return 0;
   const int lane = threadIdx.x & 31;
   const int leader = __ffs(m) - 1;
   uint32_t base = 0;
   if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
   base = __shfl_sync(0xFFFFFFFFu, base, leader);
-  if (want) queue[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = id;
+  const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+  if (want) queue[slot] = id;
+  return slot;
 }
 __device__ __forceinline__ void wf_add_counter(unsigned long long* slot, unsigned long long v)
 {
@@ -219,6 +225,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant_
     int x, y;
     const bool on = wf_pixel_of(p, path, x, y);
     bool active = false;
+    float4 a0 = make_float4(0, 0, 0, 0), a1 = a0;
     if (on) {
       const uint32_t px = (uint32_t)y * (uint32_t)p.W + (uint32_t)x;
       uint32_t seed = pixel_seed(px, p.frame, npix, p.seed);
@@ -230,13 +237,14 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant_
         const float ry = rnd(seed) * p.aa;
         pr = primary_ray(p.cam, (float)x + rx, (float)y + ry, p.W, p.H, seed);
       }
-      p.st.r0[path] = make_float4(pr.O.x, pr.O.y, pr.O.z, __uint_as_float(pack_r0w(0, p.max_bounces, 0)));
-      p.st.r1[path] = make_float4(pr.D.x, pr.D.y, pr.D.z, __uint_as_float(seed));
+      a0 = make_float4(pr.O.x, pr.O.y, pr.O.z, __uint_as_float(pack_r0w(0, p.max_bounces, 0)));
+      a1 = make_float4(pr.D.x, pr.D.y, pr.D.z, __uint_as_float(seed));
       p.st.term[path] = make_float4(0, 0, 0, 0);
       active = p.max_bounces >= 0;  // Trace(depth < 0) returns before FindNearest, renderer.cpp:1080
       if (active) launched++;
     }
-    wf_push(p.st.q[0], p.st.counts + 0, active, path);
+    const uint32_t slot = wf_push(p.st.q[0], p.st.counts + 0, active, path);
+    if (active) { p.st.r0[0][slot] = a0; p.st.r1[0][slot] = a1; }
   }
   wf_add_counter(p.counters + 4, launched);
 }
@@ -251,12 +259,10 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(const __grid_constant_
 // candidate instead of repeating the test on a few lanes).
 __global__ void __launch_bounds__(kWfBlock) k_wf_prepare(const __grid_constant__ WfParams p)
 {
-  const uint32_t* queue = p.st.q[p.iter & 1];
   const uint32_t n = p.st.counts[4 * p.iter];
   const int nvol = p.sc.nvol;
   for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
-    const uint32_t path = queue[qi];
-    const float4 a = p.st.r0[path], b = p.st.r1[path];
+    const float4 a = p.st.r0[p.iter & 1][qi], b = p.st.r1[p.iter & 1][qi];
     const f3 O = v3(a.x, a.y, a.z), D = v3(b.x, b.y, b.z);
     DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = 0;
     BW bw; bw.ex = bw.ey = bw.ez = 0; bw.plain = 0; bw.flip = 0; bw.F = 0;
@@ -292,7 +298,6 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
   const Staged stg = wf_stage_scene(p.sc, smem);
   const DVolume* svol = stg.vol;
   const int lane = threadIdx.x & 31;
-  const uint32_t* queue = p.st.q[p.iter & 1];
   uint32_t* cnt = p.st.counts + 4 * p.iter;
   const uint32_t n = cnt[0];
   const int nvol = p.sc.nvol;
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
   const bool use_mask = BWK && p.prepared && nvol > 1 && nvol <= kMaskVolumes;
   uint32_t cand = 0;
   bool has_ray = false, in_dda = false, exhausted = false;
-  uint32_t path = 0;
+  uint32_t pos = 0;  // the ray's position in the bounce's queue: where its ray is read and its hit is written
   f3 O = v3s(0), D = v3s(0);
   float tbest = 0; uint32_t pbest = 0; int volbest = -2;
   int vi = 0;
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
       if (need) {
         const uint32_t qi = base + (uint32_t)__popc(nm & ((1u << lane) - 1u));
         if (qi < n) {
-          path = queue[qi];
+          pos = qi;
           tbest = 1e34f; pbest = 0; volbest = -2;
           vi = 0; has_ray = true; in_dda = false;
           nrays++;
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
             }
           }
           if (!(BWK && p.prepared) || need_world) {
-            const float4 a = p.st.r0[path], b = p.st.r1[path];
+            const float4 a = p.st.r0[p.iter & 1][qi], b = p.st.r1[p.iter & 1][qi];
             O = v3(a.x, a.y, a.z); D = v3(b.x, b.y, b.z);
           }
         } else exhausted = true;
@@ -389,11 +394,11 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
           if (tbest > h.t) {
             tbest = h.t;
             hb = (uint32_t)(h.mat & 255) | (1u << 8) | ((uint32_t)(h.inside & 1) << 30) | (1u << 31);  // vol = -1, bit 31: inside flag valid
-            p.st.hn[path] = make_float4(h.N.x, h.N.y, h.N.z, 0);
+            p.st.hn[pos] = make_float4(h.N.x, h.N.y, h.N.z, 0);
           }
         }
-        p.st.h0[path] = make_float2(tbest, __uint_as_float(pbest));
-        p.st.h1[path] = hb;
+        p.st.h0[pos] = make_float2(tbest, __uint_as_float(pbest));
+        p.st.h1[pos] = hb;
         has_ray = false;
       }
     }
@@ -562,16 +567,18 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, const Lights
 // cont = the path continues with the ray now stored in r0/r1; want_shadow = a light sample was
 // written to the request slot [level][path] and needs its occlusion test.
 template <bool CS>
-__device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& stg, const Lights& lights, uint32_t path, Counters& cn, int& in_light,
-                                             bool& cont, bool& want_shadow, int& level)
+__device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& stg, const Lights& lights, uint32_t qi, uint32_t& path, Counters& cn,
+                                             int& in_light, bool& cont, bool& want_shadow, int& level, float4& next0, float4& next1)
 {
   const DVolume* svol = stg.vol;
   const DScene& sc = p.sc;
   const uint32_t cap = p.st.cap;
   cont = false; want_shadow = false; level = 0;
-  const float4 a = __ldcg(p.st.r0 + path), b = __ldcg(p.st.r1 + path);
-  const float2 h = __ldcg(p.st.h0 + path);
-  const uint32_t hb = __ldcg(p.st.h1 + path), rb = __float_as_uint(a.w);
+  // everything the bounce knows about the path sits at its queue position: one trip to memory
+  const float4 a = __ldcs(p.st.r0[p.iter & 1] + qi), b = __ldcs(p.st.r1[p.iter & 1] + qi);
+  const float2 h = __ldcs(p.st.h0 + qi);
+  const uint32_t hb = __ldcs(p.st.h1 + qi), rb = __float_as_uint(a.w);
+  path = p.st.q[p.iter & 1][qi];
   Ray ray;
   ray.O = v3(a.x, a.y, a.z); ray.D = v3(b.x, b.y, b.z);
   ray.t = h.x; ray.N = v3s(0); ray.mat = VP_MAT_NONE;
@@ -584,7 +591,7 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
     ray.mat = __ldg(v.grid + cell_of(v, __float_as_uint(h.y)));
     ray.N = normal_voxel(v, oO, oD, neg_bits(oD), ray.t, nullptr);
   } else if (voxIndex == -1) {
-    const float4 nn = __ldcg(p.st.hn + path);
+    const float4 nn = __ldcs(p.st.hn + qi);
     ray.N = v3(nn.x, nn.y, nn.z);
     ray.mat = (int)(hb & 255u);
     ray.inside = (int)((hb >> 30) & 1u);  // FindNearest overwrites isInsideGlass on a sphere/triangle hit (renderer.cpp:1012)
@@ -602,10 +609,10 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
   if (m == VP_MAT_NONE) {
     cn.sky++;
     const f3 t = sample_sky(sc, ray.D);
-    __stcg(p.st.term + path, make_float4(t.x, t.y, t.z, 0));
+    __stcg(p.st.term + path, make_float4(t.x, t.y, t.z, __uint_as_float((uint32_t)top)));
   } else if (m == 15) {
     const f3 t = muls(albedo_of(sc, m), sc.mat[m].emissive);
-    __stcg(p.st.term + path, make_float4(t.x, t.y, t.z, 0));
+    __stcg(p.st.term + path, make_float4(t.x, t.y, t.z, __uint_as_float((uint32_t)top)));
   } else {
     // Every material class ends in "spawn the next ray from the hit along rdir" (normalising Ray ctor) and a fold level;
     // the classes only differ in how rdir, the side of the surface (rn), the medium flag and the level are made.  The
@@ -690,10 +697,10 @@ __device__ __forceinline__ void wf_shade_one(const WfParams& p, const Staged& st
     cont = depth >= 0 && top < VP_MAX_LEVELS;  // Trace(depth < 0) returns 0: term stays 0
     if (cont) {
       const Ray nr = spawn(offset_ray(isect(ray), rn), rdir, ins);
-      __stcg(p.st.r0 + path, make_float4(nr.O.x, nr.O.y, nr.O.z, __uint_as_float(pack_r0w(ins, depth, top))));
-      __stcg(p.st.r1 + path, make_float4(nr.D.x, nr.D.y, nr.D.z, __uint_as_float(seed)));
+      next0 = make_float4(nr.O.x, nr.O.y, nr.O.z, __uint_as_float(pack_r0w(ins, depth, top)));  // stored where the append puts the path
+      next1 = make_float4(nr.D.x, nr.D.y, nr.D.z, __uint_as_float(seed));
     } else {
-      __stcg(&p.st.r0[path].w, __uint_as_float(pack_r0w(ins, depth, top)));
+      __stcg(p.st.term + path, make_float4(0, 0, 0, __uint_as_float((uint32_t)top)));  // the path ends here: Trace(depth < 0) returns 0
     }
   }
 
@@ -716,12 +723,13 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocksShade) k_wf_shade(const 
   for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < nround; qi += gridDim.x * blockDim.x) {
     bool cont = false, want_shadow = false;
     uint32_t path = 0;
+    float4 next0 = make_float4(0, 0, 0, 0), next1 = next0;
     if (qi < n) {
-      path = queue[qi];
       int level;
-      wf_shade_one<CS>(p, stg, lights, path, cn, in_light, cont, want_shadow, level);
+      wf_shade_one<CS>(p, stg, lights, qi, path, cn, in_light, cont, want_shadow, level, next0, next1);
     }
-    wf_push(qnext, cnt + 4, cont, path);          // counts[iter+1][0]
+    const uint32_t slot = wf_push(qnext, cnt + 4, cont, path);          // counts[iter+1][0]
+    if (cont) { __stcg(p.st.r0[(p.iter + 1) & 1] + slot, next0); __stcg(p.st.r1[(p.iter + 1) & 1] + slot, next1); }
   }
   wf_add_counter(p.counters + 6, cn.sky);
   wf_add_counter(p.counters + 2, cn.exitray);
@@ -943,8 +951,8 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_resolve(const __grid_constant__
     int x, y;
     if (!wf_pixel_of(p, path, x, y)) continue;
     const uint32_t px = (uint32_t)y * (uint32_t)p.W + (uint32_t)x;
-    const int top = (int)((__float_as_uint(p.st.r0[path].w) >> 16) & 0xFFu);
     const float4 t4 = p.st.term[path];
+    const int top = (int)(__float_as_uint(t4.w) & 0xFFu);
     f3 R = v3(t4.x, t4.y, t4.z);
     for (int l = top - 1; l >= (p.reproject ? 1 : 0); l--) {
       const float4 v4 = __ldcs(p.st.lv + (size_t)l * cap + path);
