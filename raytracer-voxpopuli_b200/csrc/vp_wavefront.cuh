@@ -43,7 +43,7 @@ constexpr int kWfMinBlocksShadow = VP_WF_MINBLOCKS_SHADOW;
 constexpr int kWfMinBlocks = VP_WF_MINBLOCKS;  // resident blocks per SM the traversal kernels are compiled for: 72 registers at 7 (no spills in
                                                // the brick-walk kernels); single-volume scenes: 8 blocks / 64 registers is 2.4 % slower, 6 / 80 slower again
 #ifndef VP_WF_MINBLOCKS_SHADE
-#define VP_WF_MINBLOCKS_SHADE 6
+#define VP_WF_MINBLOCKS_SHADE 5
 #endif
 constexpr int kWfMinBlocksShade = VP_WF_MINBLOCKS_SHADE;
 constexpr int kWfMinBlocksMulti = 8;           // multi-volume scenes (more time between volumes, more latency to hide) prefer the extra warps
