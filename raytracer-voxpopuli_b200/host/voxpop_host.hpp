@@ -7,7 +7,7 @@
 // Update()/Trace()/FindNearest()/IsOccluded()/ResetAccumulator() forward to
 // libvoxpop_b200.so.  The authoring arithmetic (SetTransform, LoadModel, MaterialSetUp,
 // camera frame) is restated here operation by operation so the uploaded bytes equal the
-// reference's; tests/test_host.py pins that against the reference build.
+// reference's; tests/test_golden.py::test_host_authoring_matches_reference pins that against the reference build.
 #pragma once
 #include <cstdint>
 #include <memory>
