@@ -175,6 +175,9 @@ struct vp_ctx {
   bool wf_blocks_fixed = false;                    // VP_BLOCKS_* given: no per-call sizing
   unsigned long long host_launches = 0;
   unsigned long long in_light_seen = 0;  // value of the device's inLight counter at the previous vp_in_light
+  int tune_spare = 1;         // VP_SPARE: single-volume scenes: every lane of the extend stage holds a spare ray (k_wf_extend_spare)
+  int tune_refill_spare = 24; // VP_REFILL_SPARE (8: 3.83 ms, 16: 3.73, 20: 3.69, 24: 3.67, 28: 3.68 per cfg-2 frame)
+  int wf_blocks_extend_spare = 0;
   int tune_refill = kRefill;  // VP_REFILL
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
   int tune_brickwalk = 1;     // VP_BRICKWALK: 0 = cell walk only (A/B)
@@ -409,7 +412,9 @@ int enqueue_trace(vp_ctx* c, WfLane& L, WfParams& p, bool timing, bool capturing
       c->host_launches++;
     }
     if (e0) CU(cudaEventRecord(e0, stream));
-    if (!CS && c->tune_brickwalk && p.sc.nvol > 1) k_wf_extend<false, true, kWfMinBlocksMulti><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
+    const bool spare = !CS && c->tune_brickwalk && c->tune_spare && p.prepared && p.sc.nvol == 1 && p.sc.nsph + p.sc.ntri == 0;
+    if (spare) k_wf_extend_spare<kWfMinBlocksSpare><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
+    else if (!CS && c->tune_brickwalk && p.sc.nvol > 1) k_wf_extend<false, true, kWfMinBlocksMulti><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
     else if (!CS && c->tune_brickwalk) k_wf_extend<false, true><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
     else k_wf_extend<CS, false><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
     if (e1) CU(cudaEventRecord(e1, stream));
@@ -449,7 +454,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
 {
   PassGraph& G = L.pg;
   const size_t sm = smem_bytes(c) + (smem_bytes_shade(c) << 20);
-  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared && G.smem == sm &&
+  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 && G.smem == sm &&
                        G.counts == (const void*)p.st.counts && G.nvol == p.sc.nvol && G.stagger == c->tune_band_stagger);
   if (fresh) {
     if (G.exec) CU(cudaStreamSynchronize(L.main));  // the old graph may still be running on this lane
@@ -473,13 +478,13 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
       x.iter = x.last.iter;
       x.grid = x.kp.gridDim.x;
       x.kind = (x.kp.func == (void*)k_wf_extend<false, true> || x.kp.func == (void*)k_wf_extend<false, false> ||
-                x.kp.func == (void*)k_wf_extend<false, true, kWfMinBlocksMulti>) ? 1
+                x.kp.func == (void*)k_wf_extend<false, true, kWfMinBlocksMulti> || x.kp.func == (void*)k_wf_extend_spare<kWfMinBlocksSpare>) ? 1
              : (x.kp.func == (void*)k_wf_shadow<false, true> || x.kp.func == (void*)k_wf_shadow<false, false> ||
                 x.kp.func == (void*)k_wf_shadow<false, true, kWfMinBlocksMulti>) ? 2
              : (x.kp.func == (void*)k_wf_generate) ? 3 : (x.kp.func == (void*)k_wf_shade<false>) ? 4 : 0;
       G.nodes.push_back(x);
     }
-    G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared; G.smem = sm; G.counts = (const void*)p.st.counts;
+    G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4; G.smem = sm; G.counts = (const void*)p.st.counts;
     G.nvol = p.sc.nvol; G.stagger = c->tune_band_stagger;
     G.captures++;
   } else {
@@ -636,6 +641,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   p.row_tile = fp->row_tile; p.row_tile_stride = fp->row_tile_stride; p.row_tile_phase = fp->row_tile_phase;
   p.accum = accum; p.rgb8 = rgb8; p.counters = c->d_counters.p; p.iter = 0;
   p.refill = c->tune_refill;
+  p.refill_spare = c->tune_refill_spare;
   p.bulk = c->tune_bulk;
   p.light_smem = lights_staged(c) ? 1 : 0;
   p.light_smem_off = (int)light_offset(c);
@@ -669,7 +675,8 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
     const long long per_sm = (long long)kWfBlock * c->tune_paths_per_thread * c->sm_count;
     long long want = (paths + per_sm - 1) / per_sm;
     if (want < c->tune_min_blocks) want = c->tune_min_blocks;
-    const int be = c->sc.nvol > 1 ? c->wf_blocks_extend_mv : c->wf_blocks_extend;  // the kernel variant this scene runs
+    const bool spare = c->tune_brickwalk && c->tune_spare && p.prepared && c->sc.nvol == 1 && c->sc.nsph + c->sc.ntri == 0 && !(fp->flags & VP_FLAG_COUNT_STEPS);
+    const int be = spare ? c->wf_blocks_extend_spare : (c->sc.nvol > 1 ? c->wf_blocks_extend_mv : c->wf_blocks_extend);  // the kernel variant this scene runs
     const int bs = c->sc.nvol > 1 ? c->wf_blocks_shadow_mv : c->wf_blocks_shadow;
     const long long we = want * c->sm_count < be ? want * c->sm_count : be;
     const long long ws = want * c->sm_count < bs ? want * c->sm_count : bs;
@@ -869,6 +876,9 @@ vp_ctx* vp_create(int device)
   cudaFuncSetAttribute(k_wf_shadow<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_reproject<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_reproject<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_extend_spare<kWfMinBlocksSpare>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_extend_spare<kWfMinBlocksSpare>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
+  c->wf_blocks_extend_spare = occ * c->sm_count;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_extend<false, true>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
   c->wf_blocks_extend = occ * c->sm_count;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_shadow<false, true>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
@@ -886,6 +896,8 @@ vp_ctx* vp_create(int device)
   if (const char* e = getenv("VP_LANES")) { const int n = atoi(e); c->nlanes = n < 1 ? 1 : (n > kLanes ? kLanes : n); c->lanes_fixed = true; }
   if (const char* e = getenv("VP_BULK_LANES")) c->tune_bulk = atoi(e);
   if (const char* e = getenv("VP_REFILL")) c->tune_refill = atoi(e);
+  if (const char* e = getenv("VP_SPARE")) c->tune_spare = atoi(e);
+  if (const char* e = getenv("VP_REFILL_SPARE")) c->tune_refill_spare = atoi(e);
   if (const char* e = getenv("VP_BRICKWALK")) c->tune_brickwalk = atoi(e);
   if (const char* e = getenv("VP_GRAPH")) c->tune_graph = atoi(e);
   if (const char* e = getenv("VP_PREPARE")) c->tune_prepare = atoi(e);
@@ -893,7 +905,7 @@ vp_ctx* vp_create(int device)
   if (const char* e = getenv("VP_BAND_STAGGER")) c->tune_band_stagger = atoi(e);
   if (const char* e = getenv("VP_BANDS")) c->tune_bands = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("VP_BAND_MIN_PIXELS")) c->tune_band_min_pixels = atoll(e);
-  if (const char* e = getenv("VP_BLOCKS_EXTEND")) { c->wf_blocks_extend = c->wf_blocks_extend_mv = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
+  if (const char* e = getenv("VP_BLOCKS_EXTEND")) { c->wf_blocks_extend = c->wf_blocks_extend_mv = c->wf_blocks_extend_spare = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
   if (const char* e = getenv("VP_BLOCKS_SHADOW")) { c->wf_blocks_shadow = c->wf_blocks_shadow_mv = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
   return c;
 }

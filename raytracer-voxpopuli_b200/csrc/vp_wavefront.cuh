@@ -36,6 +36,10 @@ constexpr int kWfBlock = 128;
 #define VP_BW_UNROLL 2
 #endif
 constexpr int kBwUnroll = VP_BW_UNROLL;        // brick-walk steps between two votes on the number of walking lanes
+#ifndef VP_WF_MINBLOCKS_SPARE
+#define VP_WF_MINBLOCKS_SPARE VP_WF_MINBLOCKS
+#endif
+constexpr int kWfMinBlocksSpare = VP_WF_MINBLOCKS_SPARE;
 #ifndef VP_WF_MINBLOCKS_SHADOW
 #define VP_WF_MINBLOCKS_SHADOW VP_WF_MINBLOCKS
 #endif
@@ -98,6 +102,7 @@ struct WfParams {
   int row_begin, row_end, row_tile, row_tile_stride, row_tile_phase;
   int iter;              // bounce iteration of this launch
   int refill;            // lanes still walking below which idle lanes refill from the queue
+  int refill_spare;      // ... in k_wf_extend_spare (a lane only idles after its spare ray, too)
   int bulk;              // with at most this many lanes walking, lanes in empty 8^3/16^3 blocks bulk-advance
   // compact path ids: only the 4-row tile rows a pass can own get ids, so a row band or one rank's share of the frame
   // sizes (and scans) a quarter / an eighth of the path state.  cmode 0: tile row = j; 1: j + ctrow0 (row range);
@@ -447,6 +452,112 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
   }
   wf_add_counter(p.counters + 0, nrays);
   if (CS) { wf_add_counter(p.counters + 3, steps); wf_add_counter(p.counters + 9, steps_er); wf_add_counter(p.counters + 10, steps_eb); wf_add_counter(p.counters + 11, steps); }
+}
+
+// ---- K2 for single-volume scenes: a spare ray per lane ---------------------------------------------------------------------
+// In k_wf_extend a lane whose walk has ended idles until fewer than `refill` lanes of its warp walk: the stepping loop, 84 %
+// of the stage's instructions, runs at 19 of 32 lanes (profiles/r2).  Refilling earlier does not pay there, because a refill
+// is a ticket atomic plus loads from L2.  Here every lane holds a SPARE: the ticket of its next queue entry, taken together
+// with the warp's other tickets in the same aggregated atomic as today, its records touched (prefetch to L1) when the
+// ticket arrives.  A lane whose walk ends writes its hit and switches to its spare at the next vote of the stepping loop -
+// the lanes that ended in the same round do it together, from L1, without an atomic - and only idles once the spare is
+// used up too.  Single-volume scenes without primitives only (there the end of a walk is the end of the ray); towards the
+// end of the queue no spares are handed out (no lane sits on an entry while others have run dry).  Same arithmetic,
+// records and results as k_wf_extend<false, true>.
+constexpr uint32_t kNoTicket = 0xFFFFFFFFu;
+template <int MINB>
+__global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend_spare(const __grid_constant__ WfParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (!wf_block_has_work(p.st.counts + 4 * p.iter + 2, p.st.counts[4 * p.iter])) return;
+  const Staged stg = wf_stage_scene(p.sc, smem);
+  const DVolume& v = stg.vol[0];
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t* cnt = p.st.counts + 4 * p.iter;
+  const uint32_t n = cnt[0];
+  const unsigned long long* const region = region_of(stg, v);
+  const unsigned long long* const fine = v.fine;
+  const uint32_t F = axis_field(v.jr, 0);
+  const uint32_t spare_floor = (uint32_t)gridDim.x * (uint32_t)kWfBlock;  // entries left below which no spares are handed out
+  bool has_ray = false, exhausted = false, nomore = false;
+  uint32_t pos = 0, spare = kNoTicket;
+  float tbest = 0;
+  DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = 0; s.t = 3.0e38f; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
+  Occ o; occ_reset(o);
+  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.F = F; bw.flip = bw.ac = bw.plain = 0;
+  unsigned int nrays = 0;
+  // the prepared walk of queue entry tk becomes the lane's ray (a ray that enters no volume ends at the next vote)
+#define VP_LOAD_RAY(tk_)                                                                                              \
+  {                                                                                                                   \
+    const float4 w0_ = p.st.ps[0][tk_], w1_ = p.st.ps[1][tk_], w2_ = p.st.ps[2][tk_];                                 \
+    const uint32_t fl_ = __float_as_uint(w2_.w);                                                                      \
+    pos = (tk_); tbest = 1e34f; has_ray = true; nrays++;                                                              \
+    s.tx = w0_.x; s.ty = w0_.y; s.tz = w0_.z; s.t = (fl_ & 63u) ? w0_.w : 3.0e38f;                                    \
+    s.dx = w1_.x; s.dy = w1_.y; s.dz = w1_.z; s.P = __float_as_uint(w1_.w);                                           \
+    bw.ex = w2_.x; bw.ey = w2_.y; bw.ez = w2_.z;                                                                      \
+    bw.flip = ((fl_ >> 7) & 1u ? F : 0u) | ((fl_ >> 8) & 1u ? F << 1 : 0u) | ((fl_ >> 9) & 1u ? F << 2 : 0u);         \
+    bw.plain = (fl_ >> 6) & 1u; bw.ac = 0u; bw.tc = __uint_as_float(0xFF800000u);                                     \
+    occ_reset(o);                                                                                                     \
+  }
+  for (;;) {
+    // 1. a lane without a ray takes a queue entry and a spare, a lane that walks but has used its spare takes a new spare:
+    //    one aggregated atomic for all tickets of the warp
+    if (!has_ray && spare != kNoTicket) { VP_LOAD_RAY(spare); spare = kNoTicket; }
+    {
+      const bool ask_ray = !has_ray && !exhausted;
+      const bool ask_spare = !exhausted && !nomore && spare == kNoTicket;
+      const unsigned m1 = __ballot_sync(0xFFFFFFFFu, ask_ray), m2 = __ballot_sync(0xFFFFFFFFu, ask_spare);
+      if (m1 | m2) {
+        const int leader = __ffs(m1 | m2) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(cnt + 2, (uint32_t)(__popc(m1) + __popc(m2)));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        uint32_t tk = base + (uint32_t)(__popc(m1 & lt) + __popc(m2 & lt));
+        if (ask_ray) {
+          if (tk < n) { VP_LOAD_RAY(tk); } else { exhausted = true; }
+          tk++;
+        }
+        if (ask_spare) {
+          // keep the spare only while the queue is long: at its end a held entry is a ray nobody walks
+          if (tk < n && n - tk > spare_floor) {
+            spare = tk;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.st.ps[0] + tk));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.st.ps[1] + tk));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.st.ps[2] + tk));
+          } else if (tk < n) {
+            spare = tk;  // too close to the end to ask for more, but the entry is ours
+            nomore = true;
+          } else nomore = true;
+        }
+      }
+    }
+    if (!__any_sync(0xFFFFFFFFu, has_ray)) break;
+    // 2. the brick walk; at every vote the lanes whose walk has ended write their hit and go on with their spare
+    const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted | nomore) ? 1u : (unsigned)p.refill_spare;
+    for (;;) {
+#pragma unroll
+      for (int u = 0; u < kBwUnroll; u++) {
+        if (s.t < tbest) {
+          const uint32_t Pr = s.P ^ bw.flip;
+          if ((Pr ^ o.key) >> 6) occ_fetch(region, fine, o, Pr);
+          const float t0 = s.t;
+          if (uw_step(s, bw, o.m, Pr, __uint_as_float(kHitTag))) tbest = t0;
+        }
+      }
+      if (has_ray && !(s.t < tbest)) {
+        const bool hit = __float_as_uint(s.t) == kHitTag;
+        p.st.h0[pos] = make_float2(tbest, __uint_as_float(hit ? (s.P ^ bw.flip) : 0u));
+        p.st.h1[pos] = (uint32_t)(hit ? 2 : 0) << 8;  // volume 0, or -2: no hit
+        has_ray = false;
+        s.t = 3.0e38f;
+        if (spare != kNoTicket) { VP_LOAD_RAY(spare); spare = kNoTicket; }
+      }
+      if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) < thr) break;
+    }
+  }
+#undef VP_LOAD_RAY
+  wf_add_counter(p.counters + 0, nrays);
 }
 
 // ---- K3: shade = the material switch of Renderer::Trace (renderer.cpp:1092-1327) -------------------
