@@ -97,7 +97,7 @@ struct WfLane {
   DevBuf<unsigned char> d_wf;
   uint32_t cap = 0;
   int levels = 0, samples = 0;
-  bool prims = false, prepared = false, masks = false, area = false;  // optional parts laid out
+  bool prims = false, prepared = false, masks = false, area = false, sprep = false;  // optional parts laid out
   size_t bytes = 0;
 };
 constexpr int kLanes = 6;       // most frames in flight (c->nlanes are used: 4 unless VP_LANES says otherwise)
@@ -334,23 +334,25 @@ int grid_blocks(const vp_ctx* c, long long work_warps)
 // path state of one lane (HBM-resident, sized for the largest pass / depth seen).  Optional parts are only laid out when
 // a scene needs them: primitive normals (spheres / triangles), prepared walks (passes that overlap), candidate masks
 // (multi-volume scenes).
-struct WfNeed { uint32_t cap; int levels, samples; bool prims, prepared, masks, area; };
+struct WfNeed { uint32_t cap; int levels, samples; bool prims, prepared, masks, area, sprep; };
 int wf_reserve(WfLane& L, const WfNeed& nd, size_t* bytes_only = nullptr)
 {
   if (bytes_only) *bytes_only = 0;
   if (nd.cap <= L.cap && nd.levels <= L.levels && nd.samples <= L.samples && (!nd.prims || L.prims) && (!nd.prepared || L.prepared) &&
-      (!nd.masks || L.masks) && (!nd.area || L.area) && L.d_wf.p)
+      (!nd.masks || L.masks) && (!nd.area || L.area) && (!nd.sprep || L.sprep) && L.d_wf.p)
     return 0;
   const uint32_t cap = nd.cap > L.cap ? nd.cap : L.cap;
   const int levels = nd.levels > L.levels ? nd.levels : L.levels;
   const int samples = nd.samples > L.samples ? nd.samples : L.samples;
-  const bool prims = nd.prims || L.prims, prepared = nd.prepared || L.prepared, masks = nd.masks || L.masks, area = nd.area || L.area;
+  const bool prims = nd.prims || L.prims, prepared = nd.prepared || L.prepared, masks = nd.masks || L.masks, area = nd.area || L.area,
+             sprep = nd.sprep || L.sprep;
   const size_t f4 = sizeof(float4);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_r0 = take(2 * cap * f4), o_r1 = take(2 * cap * f4), o_h0 = take(cap * 8), o_h1 = take(cap * 4), o_hn = take(prims ? cap * f4 : 0), o_term = take(cap * f4);
   const size_t o_lv = take((size_t)levels * cap * f4);
   const size_t o_rq0 = take((size_t)2 * cap * f4), o_rq1 = take((size_t)2 * cap * f4), o_rq2 = take((size_t)2 * cap * f4);
+  const size_t o_sp2 = take(sprep ? (size_t)2 * cap * f4 : 0), o_sp3 = take(sprep ? (size_t)2 * cap * f4 : 0);
   const size_t o_sqd = take(area ? (size_t)2 * samples * cap * f4 : 0), o_sql = take(area ? (size_t)2 * samples * cap * f4 : 0);
   const size_t o_q0 = take(cap * 4), o_q1 = take(cap * 4), o_cnt = take((size_t)(VP_MAX_LEVELS + 2) * 4 * sizeof(uint32_t));
   const size_t o_ps = take(prepared ? 3 * cap * f4 : 0);  // prepared walks of the bounce being extended, by queue position
@@ -365,11 +367,12 @@ int wf_reserve(WfLane& L, const WfNeed& nd, size_t* bytes_only = nullptr)
   w.h0 = (float2*)(b + o_h0); w.h1 = (uint32_t*)(b + o_h1); w.hn = (float4*)(b + o_hn);
   w.term = (float4*)(b + o_term); w.lv = (float4*)(b + o_lv);
   w.rq0 = (float4*)(b + o_rq0); w.rq1 = (float4*)(b + o_rq1); w.rq2 = (float4*)(b + o_rq2);
+  w.sp2 = (float4*)(b + o_sp2); w.sp3 = (float4*)(b + o_sp3);
   w.sqd = (float4*)(b + o_sqd); w.sql = (float4*)(b + o_sql); w.nsamp = (uint32_t)samples;
   w.q[0] = (uint32_t*)(b + o_q0); w.q[1] = (uint32_t*)(b + o_q1); w.counts = (uint32_t*)(b + o_cnt);
   for (int k = 0; k < 3; k++) w.ps[k] = (float4*)(b + o_ps) + (size_t)k * cap;
   w.smask = (uint32_t*)(b + o_sm);
-  L.cap = cap; L.levels = levels; L.samples = samples; L.prims = prims; L.prepared = prepared; L.masks = masks; L.area = area;
+  L.cap = cap; L.levels = levels; L.samples = samples; L.prims = prims; L.prepared = prepared; L.masks = masks; L.area = area; L.sprep = sprep;
   L.bytes = off;
   return 0;
 }
@@ -428,7 +431,14 @@ int enqueue_trace(vp_ctx* c, WfLane& L, WfParams& p, bool timing, bool capturing
       k_wf_shadow_mask<<<wide, kWfBlock, 0, L.side>>>(p);
       c->host_launches++;
     }
-    if (!CS && c->tune_brickwalk && p.sc.nvol > 1) k_wf_shadow<false, true, kWfMinBlocksMulti><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
+    // (a rank's share of a multi-GPU frame is latency-bound: the extra kernel per bounce costs more than it saves there)
+    const bool sspare = spare && p.sc.nal == 0 && !(c->tune_spare & 2) && p.st.cap > (1u << 19);
+    if (sspare) {
+      k_wf_shadow_prepare<<<wide, kWfBlock, 0, L.side>>>(p);
+      c->host_launches++;
+      k_wf_shadow_spare<kWfMinBlocksSpare><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
+    }
+    else if (!CS && c->tune_brickwalk && p.sc.nvol > 1) k_wf_shadow<false, true, kWfMinBlocksMulti><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
     else if (!CS && c->tune_brickwalk) k_wf_shadow<false, true><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
     else k_wf_shadow<CS, false><<<c->wf_grid_shadow, kWfBlock, sm, L.side>>>(p);
     CU(cudaEventRecord(L.ev_shadow[it], L.side));
@@ -454,7 +464,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
 {
   PassGraph& G = L.pg;
   const size_t sm = smem_bytes(c) + (smem_bytes_shade(c) << 20);
-  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 && G.smem == sm &&
+  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 + (p.sc.nal > 0 ? 64 : 0) + (p.sc.nsph + p.sc.ntri > 0 ? 128 : 0) && G.smem == sm &&
                        G.counts == (const void*)p.st.counts && G.nvol == p.sc.nvol && G.stagger == c->tune_band_stagger);
   if (fresh) {
     if (G.exec) CU(cudaStreamSynchronize(L.main));  // the old graph may still be running on this lane
@@ -480,11 +490,11 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
       x.kind = (x.kp.func == (void*)k_wf_extend<false, true> || x.kp.func == (void*)k_wf_extend<false, false> ||
                 x.kp.func == (void*)k_wf_extend<false, true, kWfMinBlocksMulti> || x.kp.func == (void*)k_wf_extend_spare<kWfMinBlocksSpare>) ? 1
              : (x.kp.func == (void*)k_wf_shadow<false, true> || x.kp.func == (void*)k_wf_shadow<false, false> ||
-                x.kp.func == (void*)k_wf_shadow<false, true, kWfMinBlocksMulti>) ? 2
+                x.kp.func == (void*)k_wf_shadow<false, true, kWfMinBlocksMulti> || x.kp.func == (void*)k_wf_shadow_spare<kWfMinBlocksSpare>) ? 2
              : (x.kp.func == (void*)k_wf_generate) ? 3 : (x.kp.func == (void*)k_wf_shade<false>) ? 4 : 0;
       G.nodes.push_back(x);
     }
-    G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4; G.smem = sm; G.counts = (const void*)p.st.counts;
+    G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 + (p.sc.nal > 0 ? 64 : 0) + (p.sc.nsph + p.sc.ntri > 0 ? 128 : 0); G.smem = sm; G.counts = (const void*)p.st.counts;
     G.nvol = p.sc.nvol; G.stagger = c->tune_band_stagger;
     G.captures++;
   } else {
@@ -664,6 +674,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   WfNeed need;
   need.cap = cap; need.levels = levels; need.samples = samples;
   need.prims = c->sc.nsph + c->sc.ntri > 0; need.prepared = p.prepared != 0; need.masks = c->sc.nvol > 1 && c->sc.nvol <= 32; need.area = c->sc.nal > 0;
+  need.sprep = p.prepared && c->tune_spare && c->tune_brickwalk && c->sc.nvol == 1 && c->sc.nsph + c->sc.ntri == 0 && c->sc.nal == 0 && cap > (1u << 19);
   // Persistent grids follow the number of paths this call can have: a warp that gets only ~1 ray per lane never refills
   // and ends at the SIMD efficiency of its longest ray, so small shards run fewer, longer-lived warps (>= 3 blocks per SM
   // to keep latency hidden; measured on 1/8 frame shares, profiles/README.md).
@@ -877,6 +888,7 @@ vp_ctx* vp_create(int device)
   cudaFuncSetAttribute(k_wf_reproject<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_reproject<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_wf_extend_spare<kWfMinBlocksSpare>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_wf_shadow_spare<kWfMinBlocksSpare>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_extend_spare<kWfMinBlocksSpare>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;
   c->wf_blocks_extend_spare = occ * c->sm_count;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wf_extend<false, true>, kWfBlock, 1024) != cudaSuccess || occ < 1) occ = 4;

@@ -80,6 +80,8 @@ struct WfState {
   float4* rq0;      // [parity][pos]: origin.xyz, w = bits nsamp(8) | level(5) << 8 | type(3) << 13 | area(1) << 16 | mat(8) << 24
   float4* rq1;      // [parity][pos]: single-light requests: dir.xyz, w = dist
   float4* rq2;      // [parity][pos]: li.xyz (single lights: the final contribution), w = path id
+  float4* sp2;      // [parity][pos]: k_wf_shadow_prepare: E.xyz, flags (rq0 / rq1 then hold tmax, t / tdelta, P')
+  float4* sp3;      // [parity][pos]: k_wf_shadow_prepare: distance to the light, request bits
   // area-light requests keep their samples by path (laid out only when the scene has area lights)
   uint32_t nsamp;   // samples allocated per request (>= area_samples)
   float4* sqd;      // [parity][sample][path]: dir.xyz, w = dist
@@ -1052,6 +1054,148 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow(const __grid_const
   }
   wf_add_counter(p.counters + 1, nrays);
   if (CS) wf_add_counter(p.counters + 3, steps);
+}
+
+// ---- K4 for single-volume scenes without area lights: prepared shadow rays and a spare request per lane --------------------
+// The shadow stage spends 44 % of its warp time refilling lanes: the request's loads, then - at ~11 of 32 lanes - the part
+// of Renderer::IsOccluded that precedes the walk (scalar world -> object transform, Setup3DDDA: ~240 instructions).  For
+// scenes where a request is one ray into one volume, k_wf_shadow_prepare does that part one lane per request at full width
+// and overwrites the request in place with the prepared walk (the records sit at the request's queue position, so this is
+// coalesced both ways), and k_wf_shadow_spare walks them like k_wf_extend_spare walks bounce rays: every lane holds the
+// ticket of a spare request and switches to it at the vote of the stepping loop.
+//   rq0[pos] = tmax.xyz, t      rq1[pos] = tdelta.xyz, P'      sp2[pos] = E.xyz, flags (bit 0: the ray enters the volume,
+//   bit 6: excluded from brick mode, bits 7..9: mirrored axes)     sp3[pos] = distance to the light, request bits
+//   rq2[pos] = light term, path id (as the shade stage wrote it)
+__global__ void __launch_bounds__(kWfBlock) k_wf_shadow_prepare(const __grid_constant__ WfParams p)
+{
+  const uint32_t n = p.st.counts[4 * p.iter + 1];
+  const size_t par = (size_t)(p.iter & 1);
+  float4* const rq0 = p.st.rq0 + par * p.st.cap;
+  float4* const rq1 = p.st.rq1 + par * p.st.cap;
+  float4* const sp2 = p.st.sp2 + par * p.st.cap;
+  float4* const sp3 = p.st.sp3 + par * p.st.cap;
+  const DVolume& v = p.sc.vol[0];
+  for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
+    const float4 q0 = rq0[qi], q1 = rq1[qi];
+    const f3 org = v3(q0.x, q0.y, q0.z);
+    const f3 D = normalize3(v3(q1.x, q1.y, q1.z));  // normalising Ray ctor of the shadow ray
+    const ORay r = make_oray(xform_scalar(org, 1.0f, v.iM), xform_scalar(D, 0.0f, v.iM));
+    DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = s.t = 0; s.P = 0;
+    BW bw; bw.ex = bw.ey = bw.ez = 0; bw.plain = 0; bw.flip = 0; bw.F = 0;
+    uint32_t flags = 0;
+    if (setup_dda(v, r, s)) {
+      bw_init(v, s, bw);
+      flags = 1u | (bw.plain << 6) | ((s.Sx != 1u ? 1u : 0u) << 7) | ((s.Sy != 2u ? 1u : 0u) << 8) | ((s.Sz != 4u ? 1u : 0u) << 9);
+    }
+    rq0[qi] = make_float4(s.tx, s.ty, s.tz, s.t);
+    rq1[qi] = make_float4(s.dx, s.dy, s.dz, __uint_as_float(s.P));
+    sp2[qi] = make_float4(bw.ex, bw.ey, bw.ez, __uint_as_float(flags));
+    sp3[qi] = make_float4(q1.w, q0.w, 0, 0);
+  }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow_spare(const __grid_constant__ WfParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (!wf_block_has_work(p.st.counts + 4 * p.iter + 3, p.st.counts[4 * p.iter + 1])) return;
+  const Staged stg = wf_stage_scene(p.sc, smem);
+  const DVolume& v = stg.vol[0];
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const DScene& sc = p.sc;
+  uint32_t* cnt = p.st.counts + 4 * p.iter;
+  const uint32_t n = cnt[1];
+  const uint32_t cap = p.st.cap;
+  const size_t par = (size_t)(p.iter & 1);
+  const float4* const rq0 = p.st.rq0 + par * cap;
+  const float4* const rq1 = p.st.rq1 + par * cap;
+  const float4* const rq2 = p.st.rq2 + par * cap;
+  const float4* const sp2 = p.st.sp2 + par * cap;
+  const float4* const sp3 = p.st.sp3 + par * cap;
+  const float lightCount = (float)(uint32_t)(sc.npl + sc.nsl + sc.nal + 1);
+  const unsigned long long* const region = region_of(stg, v);
+  const unsigned long long* const fine = v.fine;
+  const uint32_t F = axis_field(v.jr, 0);
+  const uint32_t spare_floor = (uint32_t)gridDim.x * (uint32_t)kWfBlock;
+  bool has_req = false, exhausted = false, nomore = false, occluded = false;
+  uint32_t path = 0, bits = 0, spare = kNoTicket;
+  f3 li = v3s(0);
+  float tmaxray = 0;
+  DDA s; s.tx = s.ty = s.tz = s.dx = s.dy = s.dz = 0; s.t = 3.0e38f; s.P = s.R = 0; s.Ax = s.Ay = s.Az = s.Sx = s.Sy = s.Sz = 0;
+  Occ o; occ_reset(o);
+  BW bw; bw.ex = bw.ey = bw.ez = bw.tc = 0; bw.F = F; bw.flip = bw.ac = bw.plain = 0;
+  unsigned int nrays = 0;
+#define VP_LOAD_REQ(tk_)                                                                                              \
+  {                                                                                                                   \
+    const float4 w0_ = rq0[tk_], w1_ = rq1[tk_], w2_ = sp2[tk_], w3_ = sp3[tk_], w4_ = rq2[tk_];                      \
+    const uint32_t fl_ = __float_as_uint(w2_.w);                                                                      \
+    has_req = true; occluded = false; nrays++;                                                                        \
+    tmaxray = w3_.x; bits = __float_as_uint(w3_.y);                                                                   \
+    li = v3(w4_.x, w4_.y, w4_.z); path = __float_as_uint(w4_.w);                                                      \
+    s.tx = w0_.x; s.ty = w0_.y; s.tz = w0_.z; s.t = (fl_ & 1u) ? w0_.w : 3.0e38f;                                     \
+    s.dx = w1_.x; s.dy = w1_.y; s.dz = w1_.z; s.P = __float_as_uint(w1_.w);                                           \
+    bw.ex = w2_.x; bw.ey = w2_.y; bw.ez = w2_.z;                                                                      \
+    bw.flip = ((fl_ >> 7) & 1u ? F : 0u) | ((fl_ >> 8) & 1u ? F << 1 : 0u) | ((fl_ >> 9) & 1u ? F << 2 : 0u);         \
+    bw.plain = (fl_ >> 6) & 1u; bw.ac = 0u; bw.tc = __uint_as_float(0xFF800000u);                                     \
+    occ_reset(o);                                                                                                     \
+  }
+  for (;;) {
+    if (!has_req && spare != kNoTicket) { VP_LOAD_REQ(spare); spare = kNoTicket; }
+    {
+      const bool ask_req = !has_req && !exhausted;
+      const bool ask_spare = !exhausted && !nomore && spare == kNoTicket;
+      const unsigned m1 = __ballot_sync(0xFFFFFFFFu, ask_req), m2 = __ballot_sync(0xFFFFFFFFu, ask_spare);
+      if (m1 | m2) {
+        const int leader = __ffs(m1 | m2) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(cnt + 3, (uint32_t)(__popc(m1) + __popc(m2)));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        uint32_t tk = base + (uint32_t)(__popc(m1 & lt) + __popc(m2 & lt));
+        if (ask_req) {
+          if (tk < n) { VP_LOAD_REQ(tk); } else { exhausted = true; }
+          tk++;
+        }
+        if (ask_spare) {
+          if (tk < n && n - tk > spare_floor) {
+            spare = tk;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rq0 + tk));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rq1 + tk));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(sp2 + tk));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(sp3 + tk));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rq2 + tk));
+          } else if (tk < n) {
+            spare = tk;
+            nomore = true;
+          } else nomore = true;
+        }
+      }
+    }
+    if (!__any_sync(0xFFFFFFFFu, has_req)) break;
+    const unsigned thr = __any_sync(0xFFFFFFFFu, exhausted | nomore) ? 1u : (unsigned)p.refill_spare;
+    for (;;) {
+#pragma unroll
+      for (int u = 0; u < kBwUnroll; u++) {
+        if (s.t < tmaxray) {
+          const uint32_t Pr = s.P ^ bw.flip;
+          if ((Pr ^ o.key) >> 6) occ_fetch(region, fine, o, Pr);
+          if (uw_step(s, bw, o.m, Pr, 3.0e38f)) occluded = true;
+        }
+      }
+      if (has_req && !(s.t < tmaxray)) {
+        // the ray is done: an unoccluded sample contributes its light term (Illumination: inc * lightCount)
+        const f3 A = muls(occluded ? v3s(0) : li, lightCount);
+        const uint32_t level = (bits >> 8) & 31u;
+        p.st.lv[(size_t)level * cap + path] = make_float4(A.x, A.y, A.z, __uint_as_float(((bits >> 13) & 7u) | ((bits >> 24) << 8)));
+        has_req = false;
+        s.t = 3.0e38f; tmaxray = 0.0f;
+        if (spare != kNoTicket) { VP_LOAD_REQ(spare); spare = kNoTicket; }
+      }
+      if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) < thr) break;
+    }
+  }
+#undef VP_LOAD_REQ
+  wf_add_counter(p.counters + 1, nrays);
 }
 
 // ---- K6: resolve = fold the levels in the recursion's order, BlendColor, tonemap, RGB8 ------------
