@@ -464,7 +464,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
 {
   PassGraph& G = L.pg;
   const size_t sm = smem_bytes(c) + (smem_bytes_shade(c) << 20);
-  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 + (p.sc.nal > 0 ? 64 : 0) + (p.sc.nsph + p.sc.ntri > 0 ? 128 : 0) && G.smem == sm &&
+  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 + (p.sc.nal > 0 ? 64 : 0) + (p.sc.nsph + p.sc.ntri > 0 ? 128 : 0) + (p.st.cap > (1u << 19) ? 256 : 0) && G.smem == sm &&
                        G.counts == (const void*)p.st.counts && G.nvol == p.sc.nvol && G.stagger == c->tune_band_stagger);
   if (fresh) {
     if (G.exec) CU(cudaStreamSynchronize(L.main));  // the old graph may still be running on this lane
@@ -494,7 +494,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
              : (x.kp.func == (void*)k_wf_generate) ? 3 : (x.kp.func == (void*)k_wf_shade<false>) ? 4 : 0;
       G.nodes.push_back(x);
     }
-    G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 + (p.sc.nal > 0 ? 64 : 0) + (p.sc.nsph + p.sc.ntri > 0 ? 128 : 0); G.smem = sm; G.counts = (const void*)p.st.counts;
+    G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 + (p.sc.nal > 0 ? 64 : 0) + (p.sc.nsph + p.sc.ntri > 0 ? 128 : 0) + (p.st.cap > (1u << 19) ? 256 : 0); G.smem = sm; G.counts = (const void*)p.st.counts;
     G.nvol = p.sc.nvol; G.stagger = c->tune_band_stagger;
     G.captures++;
   } else {
