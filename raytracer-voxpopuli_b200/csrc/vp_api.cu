@@ -415,7 +415,7 @@ int enqueue_trace(vp_ctx* c, WfLane& L, WfParams& p, bool timing, bool capturing
       c->host_launches++;
     }
     if (e0) CU(cudaEventRecord(e0, stream));
-    const bool spare = !CS && c->tune_brickwalk && c->tune_spare && p.prepared && p.sc.nvol == 1 && p.sc.nsph + p.sc.ntri == 0;
+    const bool spare = !CS && p.ps_fmt;  // single-volume scene without primitives: the records k_wf_prepare wrote are in that format
     if (spare) k_wf_extend_spare<kWfMinBlocksSpare><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
     else if (!CS && c->tune_brickwalk && p.sc.nvol > 1) k_wf_extend<false, true, kWfMinBlocksMulti><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
     else if (!CS && c->tune_brickwalk) k_wf_extend<false, true><<<c->wf_grid_extend, kWfBlock, sm, stream>>>(p);
@@ -671,6 +671,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   const bool piped = overlap || fp->spp > 1 || c->tune_graph >= 2;
   c->graph_now = c->tune_graph != 0 && piped;
   p.prepared = c->tune_prepare && piped && c->tune_brickwalk && !(fp->flags & VP_FLAG_COUNT_STEPS) && c->sc.nvol <= 60;
+  p.ps_fmt = p.prepared && c->tune_spare && c->sc.nvol == 1 && c->sc.nsph + c->sc.ntri == 0;
   WfNeed need;
   need.cap = cap; need.levels = levels; need.samples = samples;
   need.prims = c->sc.nsph + c->sc.ntri > 0; need.prepared = p.prepared != 0; need.masks = c->sc.nvol > 1 && c->sc.nvol <= 32; need.area = c->sc.nal > 0;

@@ -111,6 +111,7 @@ struct WfParams {
   // 2: interleaved row tiles of ck tile rows each: tile row = ((j / ck) * row_tile_stride + row_tile_phase) * ck + j % ck
   int cmode, ctrow0, ck;
   int prepared;          // 1: k_wf_prepare has set up the first walk of every ray of the bounce
+  int ps_fmt;            // 1: ... in the record format of the single-volume kernels (k_wf_extend_spare, k_wf_shadow_spare)
   int light_smem, light_smem_off;  // shade stage: the light lists are staged in shared memory at this byte offset
   int write_rgb8;
   float4* accum;
@@ -287,6 +288,12 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_prepare(const __grid_constant__
         break;
       }
     }
+    if (p.ps_fmt) {
+      // single-volume kernels (k_wf_extend_spare, k_wf_shadow_spare): the lane that takes the record does no decoding - the mirror
+      // word itself, and a ray that enters no volume starts beyond every stopping distance
+      flags = (flags & 63u) ? ((bw.flip << 2) | (bw.plain << 1) | 1u) : 0u;
+      if (!flags) s.t = 3.0e38f;
+    }
     p.st.ps[0][qi] = make_float4(s.tx, s.ty, s.tz, s.t);
     p.st.ps[1][qi] = make_float4(s.dx, s.dy, s.dz, __uint_as_float(s.P));
     p.st.ps[2][qi] = make_float4(bw.ex, bw.ey, bw.ez, __uint_as_float(flags));
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
 #endif
               bw.F = axis_field(v.jr, 0);
               bw.flip = ((fl >> 7) & 1u ? bw.F : 0u) | ((fl >> 8) & 1u ? bw.F << 1 : 0u) | ((fl >> 9) & 1u ? bw.F << 2 : 0u);
-              bw.plain = (fl >> 6) & 1u; bw.ac = 0u; bw.tc = __uint_as_float(0xFF800000u);
+              bw.plain = (fl >> 6) & 1u; bw.ac = kAcFirst; bw.tc = __uint_as_float(0xFF800000u);
               occ_reset(o); region = region_of(stg, v); fine = v.fine;
               in_dda = true;
             }
@@ -420,10 +427,8 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
 #pragma unroll
         for (int u = 0; u < kBwUnroll; u++) {
           if (s.t < tbest) {
-            const uint32_t Pr = s.P ^ bw.flip;  // the walk is mirrored: real cell
-            if ((Pr ^ o.key) >> 6) occ_fetch(region, fine, o, Pr);
             const float t0 = s.t;
-            if (uw_step(s, bw, o.m, Pr, __uint_as_float(kHitTag))) tbest = t0;  // NaN tag: stops the walk, recovered below
+            if (walk_step(region, fine, s, bw, o, __uint_as_float(kHitTag))) tbest = t0;  // NaN tag: stops the walk, recovered below
           }
         }
         if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tbest)) < thr) break;
@@ -495,11 +500,10 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend_spare(const __grid
     const float4 w0_ = p.st.ps[0][tk_], w1_ = p.st.ps[1][tk_], w2_ = p.st.ps[2][tk_];                                 \
     const uint32_t fl_ = __float_as_uint(w2_.w);                                                                      \
     pos = (tk_); tbest = 1e34f; has_ray = true; nrays++;                                                              \
-    s.tx = w0_.x; s.ty = w0_.y; s.tz = w0_.z; s.t = (fl_ & 63u) ? w0_.w : 3.0e38f;                                    \
+    s.tx = w0_.x; s.ty = w0_.y; s.tz = w0_.z; s.t = w0_.w;                                                            \
     s.dx = w1_.x; s.dy = w1_.y; s.dz = w1_.z; s.P = __float_as_uint(w1_.w);                                           \
     bw.ex = w2_.x; bw.ey = w2_.y; bw.ez = w2_.z;                                                                      \
-    bw.flip = ((fl_ >> 7) & 1u ? F : 0u) | ((fl_ >> 8) & 1u ? F << 1 : 0u) | ((fl_ >> 9) & 1u ? F << 2 : 0u);         \
-    bw.plain = (fl_ >> 6) & 1u; bw.ac = 0u; bw.tc = __uint_as_float(0xFF800000u);                                     \
+    bw.flip = fl_ >> 2; bw.plain = (fl_ >> 1) & 1u; bw.ac = kAcFirst; bw.tc = __uint_as_float(0xFF800000u);                 \
     occ_reset(o);                                                                                                     \
   }
   for (;;) {
@@ -541,10 +545,8 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend_spare(const __grid
 #pragma unroll
       for (int u = 0; u < kBwUnroll; u++) {
         if (s.t < tbest) {
-          const uint32_t Pr = s.P ^ bw.flip;
-          if ((Pr ^ o.key) >> 6) occ_fetch(region, fine, o, Pr);
           const float t0 = s.t;
-          if (uw_step(s, bw, o.m, Pr, __uint_as_float(kHitTag))) tbest = t0;
+          if (walk_step(region, fine, s, bw, o, __uint_as_float(kHitTag))) tbest = t0;
         }
       }
       if (has_ray && !(s.t < tbest)) {
@@ -1020,9 +1022,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow(const __grid_const
 #pragma unroll
         for (int u = 0; u < kBwUnroll; u++) {
           if (s.t < tmaxray) {
-            const uint32_t Pr = s.P ^ bw.flip;
-            if ((Pr ^ o.key) >> 6) occ_fetch(region, fine, o, Pr);
-            if (uw_step(s, bw, o.m, Pr, 3.0e38f)) occluded = true;
+            if (walk_step(region, fine, s, bw, o, 3.0e38f)) occluded = true;
           }
         }
         if ((unsigned)__popc(__ballot_sync(0xFFFFFFFFu, s.t < tmaxray)) < thr) break;
@@ -1064,7 +1064,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow(const __grid_const
 // coalesced both ways), and k_wf_shadow_spare walks them like k_wf_extend_spare walks bounce rays: every lane holds the
 // ticket of a spare request and switches to it at the vote of the stepping loop.
 //   rq0[pos] = tmax.xyz, t      rq1[pos] = tdelta.xyz, P'      sp2[pos] = E.xyz, flags (bit 0: the ray enters the volume,
-//   bit 6: excluded from brick mode, bits 7..9: mirrored axes)     sp3[pos] = distance to the light, request bits
+//   bit 1: excluded from brick mode, bits 2..: the mirror word)    sp3[pos] = distance to the light, request bits
 //   rq2[pos] = light term, path id (as the shade stage wrote it)
 __global__ void __launch_bounds__(kWfBlock) k_wf_shadow_prepare(const __grid_constant__ WfParams p)
 {
@@ -1085,8 +1085,8 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shadow_prepare(const __grid_con
     uint32_t flags = 0;
     if (setup_dda(v, r, s)) {
       bw_init(v, s, bw);
-      flags = 1u | (bw.plain << 6) | ((s.Sx != 1u ? 1u : 0u) << 7) | ((s.Sy != 2u ? 1u : 0u) << 8) | ((s.Sz != 4u ? 1u : 0u) << 9);
-    }
+      flags = (bw.flip << 2) | (bw.plain << 1) | 1u;
+    } else s.t = 3.0e38f;  // the request's ray enters no volume: beyond every stopping distance
     rq0[qi] = make_float4(s.tx, s.ty, s.tz, s.t);
     rq1[qi] = make_float4(s.dx, s.dy, s.dz, __uint_as_float(s.P));
     sp2[qi] = make_float4(bw.ex, bw.ey, bw.ez, __uint_as_float(flags));
@@ -1133,11 +1133,10 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow_spare(const __grid
     has_req = true; occluded = false; nrays++;                                                                        \
     tmaxray = w3_.x; bits = __float_as_uint(w3_.y);                                                                   \
     li = v3(w4_.x, w4_.y, w4_.z); path = __float_as_uint(w4_.w);                                                      \
-    s.tx = w0_.x; s.ty = w0_.y; s.tz = w0_.z; s.t = (fl_ & 1u) ? w0_.w : 3.0e38f;                                     \
+    s.tx = w0_.x; s.ty = w0_.y; s.tz = w0_.z; s.t = w0_.w;                                                            \
     s.dx = w1_.x; s.dy = w1_.y; s.dz = w1_.z; s.P = __float_as_uint(w1_.w);                                           \
     bw.ex = w2_.x; bw.ey = w2_.y; bw.ez = w2_.z;                                                                      \
-    bw.flip = ((fl_ >> 7) & 1u ? F : 0u) | ((fl_ >> 8) & 1u ? F << 1 : 0u) | ((fl_ >> 9) & 1u ? F << 2 : 0u);         \
-    bw.plain = (fl_ >> 6) & 1u; bw.ac = 0u; bw.tc = __uint_as_float(0xFF800000u);                                     \
+    bw.flip = fl_ >> 2; bw.plain = (fl_ >> 1) & 1u; bw.ac = kAcFirst; bw.tc = __uint_as_float(0xFF800000u);                 \
     occ_reset(o);                                                                                                     \
   }
   for (;;) {
@@ -1177,9 +1176,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow_spare(const __grid
 #pragma unroll
       for (int u = 0; u < kBwUnroll; u++) {
         if (s.t < tmaxray) {
-          const uint32_t Pr = s.P ^ bw.flip;
-          if ((Pr ^ o.key) >> 6) occ_fetch(region, fine, o, Pr);
-          if (uw_step(s, bw, o.m, Pr, 3.0e38f)) occluded = true;
+          if (walk_step(region, fine, s, bw, o, 3.0e38f)) occluded = true;
         }
       }
       if (has_req && !(s.t < tmaxray)) {
