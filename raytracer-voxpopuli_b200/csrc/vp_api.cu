@@ -178,6 +178,7 @@ struct vp_ctx {
   int tune_spare = 1;         // VP_SPARE: single-volume scenes: every lane of the extend stage holds a spare ray (k_wf_extend_spare)
   int tune_refill_spare = 24; // VP_REFILL_SPARE (8: 3.83 ms, 16: 3.73, 20: 3.69, 24: 3.67, 28: 3.68 per cfg-2 frame)
   int wf_blocks_extend_spare = 0;
+  int tune_ov_extend = 4, tune_ov_shadow = 2, tune_ov_shade = 2;  // VP_OV_EXTEND / _SHADOW / _SHADE: resident blocks per SM of a stage when passes of a single-volume scene overlap (0: no cap)
   int tune_refill = kRefill;  // VP_REFILL
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
   int tune_brickwalk = 1;     // VP_BRICKWALK: 0 = cell walk only (A/B)
@@ -697,6 +698,15 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
     c->wf_grid_shadow = full ? bs : (int)ws;
     const long long wh = want * c->sm_count < c->wf_blocks_shade ? want * c->sm_count : c->wf_blocks_shade;
     c->wf_grid_shade = (full || c->wf_shade_fixed) ? c->wf_blocks_shade : (int)wh;
+    // Single-volume scenes whose passes overlap: the stages of the four frames in flight share the SMs, and a warp of a
+    // smaller persistent grid sees more rays per lane (its lanes refill, its spares get used) - fewer resident blocks per
+    // stage win there (cfg 2: 3.19 -> 2.9 ms per frame).  Multi-volume scenes lose with the same caps (cfg 5 +6 %): theirs stay.
+    if (!full && spare) {
+      const auto cap_to = [&](int& grid, int per_sm) { if (per_sm > 0 && grid > per_sm * c->sm_count) grid = per_sm * c->sm_count; };
+      cap_to(c->wf_grid_extend, c->tune_ov_extend);
+      cap_to(c->wf_grid_shadow, c->tune_ov_shadow);
+      if (!c->wf_shade_fixed) cap_to(c->wf_grid_shade, c->tune_ov_shade);
+    }
   }
   const bool cs = (fp->flags & VP_FLAG_COUNT_STEPS) != 0;
   CU(cudaEventRecord(c->ev_in, stream));
@@ -918,6 +928,9 @@ vp_ctx* vp_create(int device)
   if (const char* e = getenv("VP_BAND_STAGGER")) c->tune_band_stagger = atoi(e);
   if (const char* e = getenv("VP_BANDS")) c->tune_bands = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("VP_BAND_MIN_PIXELS")) c->tune_band_min_pixels = atoll(e);
+  if (const char* e = getenv("VP_OV_EXTEND")) c->tune_ov_extend = atoi(e);
+  if (const char* e = getenv("VP_OV_SHADOW")) c->tune_ov_shadow = atoi(e);
+  if (const char* e = getenv("VP_OV_SHADE")) c->tune_ov_shade = atoi(e);
   if (const char* e = getenv("VP_BLOCKS_EXTEND")) { c->wf_blocks_extend = c->wf_blocks_extend_mv = c->wf_blocks_extend_spare = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
   if (const char* e = getenv("VP_BLOCKS_SHADOW")) { c->wf_blocks_shadow = c->wf_blocks_shadow_mv = atoi(e) * c->sm_count; c->wf_blocks_fixed = true; }
   return c;
