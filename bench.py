@@ -37,6 +37,12 @@ import time
 
 import numpy as np
 
+# Passes in flight use two streams each (4-6 passes); the default of 8 hardware queues makes streams
+# share queues and serialises kernels that do not depend on each other (a rank's share of an 8-GPU frame: 0.486 -> 0.456 ms).
+# Read by the driver when the CUDA context is created, so it is set before anything touches CUDA; the library's
+# load-time constructor does the same for hosts that load it first.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 vp = importlib.import_module("raytracer-voxpopuli_b200")
@@ -515,10 +521,10 @@ def main():
                           "replaces them by register bit tests (DESIGN.md section 3), its measured L2 traffic is in profiles/"}
             l2["frac"] = l2["achieved"] / l2["peak"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_wf_extend", "peak_source": peak_src,
+                "kernel": meta.get("extend_kernel", "k_wf_extend"), "peak_source": peak_src,
                 "launches_per_step": int(ext_launches_per_frame), "kernel_ms_per_step": ext_ms_frame, "steps_with_stage_events": timed_steps,
                 "kernel_share_of_step": ext_ms.value / lone_ms[0] if lone_ms[0] > 0 else None,
-                "kernel_share_note": "k_wf_extend time / device time of the same steps (the steps that run alone with stage events); "
+                "kernel_share_note": "extend-stage time / device time of the same steps (the steps that run alone with stage events); "
                                      "against the average pipelined step it is kernel_ms_per_step / ms_per_step",
                 "algorithmic_bytes_per_launch": int(ext_bytes_frame / ext_launches_per_frame),
                 "algorithmic_bytes_per_step_all_stages": int(frame_bytes),

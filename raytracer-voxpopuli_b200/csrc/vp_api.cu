@@ -100,7 +100,7 @@ struct WfLane {
   bool prims = false, prepared = false, masks = false, area = false, sprep = false;  // optional parts laid out
   size_t bytes = 0;
 };
-constexpr int kLanes = 6;       // most frames in flight (c->nlanes are used: 4 unless VP_LANES says otherwise)
+constexpr int kLanes = 12;      // most frames in flight (c->nlanes are used: 4 unless VP_LANES says otherwise)
 constexpr int kCallRing = 8;    // completion events kept for vp_render_fence
 
 constexpr int kTickets = 16;     // vp_render_async calls whose completion events are kept
@@ -178,6 +178,7 @@ struct vp_ctx {
   int tune_spare = 1;         // VP_SPARE: single-volume scenes: every lane of the extend stage holds a spare ray (k_wf_extend_spare)
   int tune_refill_spare = 24; // VP_REFILL_SPARE (8: 3.83 ms, 16: 3.73, 20: 3.69, 24: 3.67, 28: 3.68 per cfg-2 frame)
   int wf_blocks_extend_spare = 0;
+  int tune_shard_lanes = 2;   // VP_SHARD_LANES: passes in flight beyond nlanes for calls of at most 2^19 paths (a rank's share of a multi-GPU frame)
   int tune_ov_extend = 4, tune_ov_shadow = 2, tune_ov_shade = 2;  // VP_OV_EXTEND / _SHADOW / _SHADE: resident blocks per SM of a stage when passes of a single-volume scene overlap (0: no cap)
   int tune_refill = kRefill;  // VP_REFILL
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
@@ -671,7 +672,9 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   // stage sets up the walks itself (reprojection cfg 2: 5.94 against 6.32 ms per frame).
   const bool piped = overlap || fp->spp > 1 || c->tune_graph >= 2;
   c->graph_now = c->tune_graph != 0 && piped;
-  p.prepared = c->tune_prepare && piped && c->tune_brickwalk && !(fp->flags & VP_FLAG_COUNT_STEPS) && c->sc.nvol <= 60;
+  // (a stage-timed pass is launched directly, but with the prepare stage and the kernel variants of the pipelined passes:
+  // what bench.py times alone is what runs in the steady state)
+  p.prepared = c->tune_prepare && (piped || c->time_stages_now) && c->tune_brickwalk && !(fp->flags & VP_FLAG_COUNT_STEPS) && c->sc.nvol <= 60;
   p.ps_fmt = p.prepared && c->tune_spare && c->sc.nvol == 1 && c->sc.nsph + c->sc.ntri == 0;
   WfNeed need;
   need.cap = cap; need.levels = levels; need.samples = samples;
@@ -713,7 +716,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   bool entered[kLanes] = {};
   const bool rotate = overlap || fp->spp > 1;  // lanes rotate only when passes can overlap (several samples in this call, or a deferred call)
   // small shards (a rank's share of a multi-GPU frame) are latency-bound: two more passes in flight, their state is small
-  const int lanes = (!c->lanes_fixed && cap <= (1u << 19) && c->nlanes + 2 <= kLanes) ? c->nlanes + 2 : c->nlanes;
+  const int lanes = (!c->lanes_fixed && cap <= (1u << 19) && c->nlanes + c->tune_shard_lanes <= kLanes) ? c->nlanes + c->tune_shard_lanes : c->nlanes;
   const int passes = rp ? 1 : fp->spp;
   for (int s = 0; s < passes; s++) {
     p.frame = fp->frame_index + (uint32_t)s;
@@ -824,6 +827,11 @@ extern "C" {
 
 const char* vp_last_error(void) { return g_err.c_str(); }
 
+// Six passes in flight are twelve streams; with the default of 8 hardware queues independent kernels of different passes
+// queue up behind each other.  The variable is read when the CUDA context is created, so a host that loads the library
+// before it touches CUDA gets 32 queues; a value the host has set is kept.
+__attribute__((constructor)) static void vp_default_hw_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 vp_ctx* vp_create(int device)
 {
   int ndev = 0;
@@ -928,6 +936,7 @@ vp_ctx* vp_create(int device)
   if (const char* e = getenv("VP_BAND_STAGGER")) c->tune_band_stagger = atoi(e);
   if (const char* e = getenv("VP_BANDS")) c->tune_bands = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("VP_BAND_MIN_PIXELS")) c->tune_band_min_pixels = atoll(e);
+  if (const char* e = getenv("VP_SHARD_LANES")) c->tune_shard_lanes = atoi(e) < 0 ? 0 : atoi(e);
   if (const char* e = getenv("VP_OV_EXTEND")) c->tune_ov_extend = atoi(e);
   if (const char* e = getenv("VP_OV_SHADOW")) c->tune_ov_shadow = atoi(e);
   if (const char* e = getenv("VP_OV_SHADE")) c->tune_ov_shade = atoi(e);
@@ -1554,10 +1563,11 @@ int vp_info(vp_ctx* c, char* buf, int cap)
            "\"k_wf_shade_regs\": %d, \"k_wf_shade_local_bytes\": %zu, \"wf_blocks_extend\": %d, \"wf_blocks_shadow\": %d, \"volumes\": %d, \"max_levels\": %d, "
            "\"region_words_staged\": %d, \"dbg_extend_steps_in_empty_region\": %llu, \"dbg_extend_steps_in_empty_brick\": %llu, \"extend_steps\": %llu, "
            "\"hbm_scene_bytes\": %zu, \"hbm_lane_bytes\": %zu, \"hbm_frame_bytes\": %zu, \"hbm_in_use\": %zu, \"lanes\": %d, \"lanes_allocated\": %d, "
-           "\"graph_replays\": %llu, \"graph_node_updates\": %llu, \"graph_captures\": %llu, \"graph_enabled\": %d}",
+           "\"graph_replays\": %llu, \"graph_node_updates\": %llu, \"graph_captures\": %llu, \"graph_enabled\": %d, \"extend_kernel\": \"%s\"}",
            c->device, ndev, peer ? "true" : "false", prop.name, prop.major, prop.minor, c->sm_count, c->blocks_per_sm, kBlock, fa.numRegs, fa.localSizeBytes,
            fe.numRegs, fs.numRegs, fh.numRegs, fh.localSizeBytes, c->wf_blocks_extend, c->wf_blocks_shadow, c->sc.nvol, VP_MAX_LEVELS,
-           c->sc.region_words, dbg[9], dbg[10], dbg[11], scene, lanes, frames, scene + lanes + frames, c->nlanes, lanes_held, replays, updates, captures, c->tune_graph);
+           c->sc.region_words, dbg[9], dbg[10], dbg[11], scene, lanes, frames, scene + lanes + frames, c->nlanes, lanes_held, replays, updates, captures, c->tune_graph,
+           (c->tune_prepare && c->tune_brickwalk && c->tune_spare && c->sc.nvol == 1 && c->sc.nsph + c->sc.ntri == 0) ? "k_wf_extend_spare" : "k_wf_extend");
   return 0;
 }
 

@@ -639,7 +639,10 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, const Lights
       A_now = muls(inc, (float)lightCount);
     }
   } else {
-    f3 dirn, contrib; float tshadow; bool lit;
+    // The light term is only evaluated where it is used (the sample faces the light / lies inside the cone): the reference
+    // computes it before its early return, unobserved - and here an unlit spot sample is 0 / dst^2 three times, which the
+    // IEEE division takes through its out-of-line path (7 % of the stage's instructions, profiles/r2d).
+    f3 dirn, contrib = v3s(0); float tshadow; bool lit;
     if (idx < (uint32_t)sc.npl) {
       const VpPointLight L = lights.pl[idx];
       const f3 dir = sub(ld3(L.position), ip);
@@ -647,7 +650,7 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, const Lights
       dirn = muls(dir, 1.0f / dst);
       const float ct = dot3(dirn, n);
       lit = !(ct <= 0.0f);
-      contrib = mul(muls(muls(ld3(L.color), stdmax(0.0f, ct)), 1.0f / (dst * dst)), k);
+      if (lit) contrib = mul(muls(muls(ld3(L.color), stdmax(0.0f, ct)), 1.0f / (dst * dst)), k);
       tshadow = dst;
     } else if (idx < (uint32_t)(sc.nal + sc.nsl + sc.npl)) {
       const VpSpotLight L = lights.sl[idx - sc.nal - sc.npl];
@@ -656,15 +659,17 @@ __device__ __forceinline__ void wf_light_request(const WfParams& p, const Lights
       dirn = divs(dir, dst);
       const float ct = dot3(dirn, ld3(L.direction));
       lit = !(ct <= L.angle);
-      const float alpha = 1.0f - (1.0f - ct) * 1.0f / (1.0f - L.angle);
-      const f3 li = divs(muls(ld3(L.color), stdmax(0.0f, ct)), dst * dst);
-      contrib = muls(mul(li, k), alpha);
+      if (lit) {
+        const float alpha = 1.0f - (1.0f - ct) * 1.0f / (1.0f - L.angle);
+        const f3 li = divs(muls(ld3(L.color), stdmax(0.0f, ct)), dst * dst);
+        contrib = muls(mul(li, k), alpha);
+      }
       tshadow = dst;
     } else {
       dirn = neg(ld3(sc.dl.direction));
       const float ct = dot3(dirn, n);
       lit = !(ct <= 0);
-      contrib = mul(muls(ld3(sc.dl.color), stdmax(0.0f, ct)), k);
+      if (lit) contrib = mul(muls(ld3(sc.dl.color), stdmax(0.0f, ct)), k);
       tshadow = 1e34f;
     }
     if (lit) {
