@@ -281,6 +281,12 @@ int vp_stats_end(vp_ctx* ctx, VpStats* stats);
  * the previous call, and their number; synchronises the device. */
 int vp_stage_times(vp_ctx* ctx, double* extend_ms, uint64_t* extend_launches);
 
+/* Self-check of a determinism pin: RandomSphereSample's sinf / cosf (reference template/tmpl8math.h:2502-2512)
+ * are pinned to "fp64 sincos, one rounding to fp32"; the shade stage evaluates the fp64 routine's main path inline, because
+ * its arguments all lie in [0, 2 pi].  The call runs both on every fp32 whose bit pattern lies in [first_bits, last_bits]
+ * and reports how many results differ in either output (bit patterns compared) and the first such argument. */
+int vp_check_sincos_pin(vp_ctx* ctx, uint32_t first_bits, uint32_t last_bits, uint64_t* mismatches, uint32_t* first_bad_bits);
+
 /* ---- display interop ------------------------------------------------------------------------------
  * The template blits screen->pixels through an RGBA8 texture it re-uploads every frame (reference
  * template/opengl.cpp:144-150 GLTexture::CopyFrom with GL_BGRA, template/template.cpp:305-309).  vp_render_to_gl writes the

@@ -97,7 +97,7 @@ assert HIT_DTYPE.itemsize == 28 and RAY_DTYPE.itemsize == 32
 ABI_SYMBOLS = [
     "create", "destroy", "last_error", "set_volumes", "update_volume_grid", "update_volume_transform",
     "set_materials", "set_lights", "set_prims", "set_sky", "render", "render_resident", "accum_reset",
-    "accum_download", "render_device", "trace_primary", "find_nearest", "is_occluded", "trace", "info", "stats_begin", "stats_end", "stage_times",
+    "accum_download", "render_device", "trace_primary", "find_nearest", "is_occluded", "trace", "info", "stats_begin", "stats_end", "stage_times", "check_sincos_pin",
     "render_fence", "render_reproject", "render_reproject_device", "in_light", "find_nearest_player", "focus_distance",
     "create_multi", "device_count", "render_async", "render_wait", "host_register", "host_unregister",
     "render_to_gl", "share_create", "share_open", "share_ptr", "share_signal", "share_wait", "share_error", "share_close",
@@ -158,6 +158,7 @@ class Lib:
         f("stats_begin", C.c_int, [C.c_void_p], optional=True)
         f("stats_end", C.c_int, [C.c_void_p, C.POINTER(VpStats)], optional=True)
         f("stage_times", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)], optional=True)
+        f("check_sincos_pin", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)], optional=True)
         f("render_fence", C.c_int, [C.c_void_p, C.c_void_p, C.c_int], optional=True)
         f("create_multi", C.c_void_p, [C.POINTER(C.c_int), C.c_int], optional=True)
         f("device_count", C.c_int, [C.c_void_p], optional=True)

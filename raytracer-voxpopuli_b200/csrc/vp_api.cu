@@ -1514,6 +1514,28 @@ int vp_stats_end(vp_ctx* c, VpStats* stats)
   return 0;
 }
 
+int vp_check_sincos_pin(vp_ctx* c, uint32_t first_bits, uint32_t last_bits, uint64_t* mismatches, uint32_t* first_bad_bits)
+{
+  KID0(vp_check_sincos_pin(k, first_bits, last_bits, mismatches, first_bad_bits))
+  if (!c || !mismatches || last_bits < first_bits) return fail(VP_EINVAL, "bad arguments to vp_check_sincos_pin");
+  if (bind(c)) return VP_ECUDA;
+  DevBuf<unsigned long long> d;
+  if (d.reserve(2)) return fail(VP_ECUDA, "vp_check_sincos_pin: out of device memory");
+  const unsigned long long init[2] = {0ull, 0xFFFFFFFFull};
+  unsigned long long out[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(d.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    k_check_sincos<<<c->sm_count * 16, 256, 0, c->stream>>>(first_bits, last_bits, d.p);
+    e = cudaMemcpyAsync(out, d.p, sizeof(out), cudaMemcpyDeviceToHost, c->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  d.release();
+  CU(e);
+  *mismatches = out[0];
+  if (first_bad_bits) *first_bad_bits = (uint32_t)out[1];
+  return VP_OK;
+}
+
 int vp_stage_times(vp_ctx* c, double* extend_ms, uint64_t* extend_launches)
 {
   KID0(vp_stage_times(k, extend_ms, extend_launches))

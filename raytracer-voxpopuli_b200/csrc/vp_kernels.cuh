@@ -280,4 +280,26 @@ __global__ void k_region(const unsigned long long* __restrict__ fine, uint32_t j
   }
 }
 
+// vp_check_sincos_pin: the inline main path of the fp64 sincos against the library routine, one argument per bit pattern.
+// out[0] = differing arguments, out[1] = the smallest differing bit pattern (0xFFFFFFFF when none)
+__global__ void k_check_sincos(uint32_t first, uint32_t last, unsigned long long* out)
+{
+  unsigned long long bad = 0;
+  uint32_t first_bad = 0xFFFFFFFFu;
+  const unsigned long long n = (unsigned long long)last - first + 1ull;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t bits = first + (uint32_t)i;
+    const float x = __uint_as_float(bits);
+    float s0, c0, s1, c1;
+    p_sincosf_2pi(x, &s0, &c0);
+    p_sincosf_lib(x, &s1, &c1);
+    if (__float_as_uint(s0) != __float_as_uint(s1) || __float_as_uint(c0) != __float_as_uint(c1)) { bad++; first_bad = min(first_bad, bits); }
+  }
+  for (int o = 16; o; o >>= 1) {
+    bad += __shfl_xor_sync(0xFFFFFFFFu, bad, o);
+    first_bad = min(first_bad, __shfl_xor_sync(0xFFFFFFFFu, first_bad, o));
+  }
+  if ((threadIdx.x & 31) == 0 && bad) { atomicAdd(out, bad); atomicMin(out + 1, (unsigned long long)first_bad); }
+}
+
 }  // namespace vp

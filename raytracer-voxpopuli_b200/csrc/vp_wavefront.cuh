@@ -50,7 +50,10 @@ constexpr int kWfMinBlocks = VP_WF_MINBLOCKS;  // resident blocks per SM the tra
 #define VP_WF_MINBLOCKS_SHADE 5
 #endif
 constexpr int kWfMinBlocksShade = VP_WF_MINBLOCKS_SHADE;
-constexpr int kWfMinBlocksMulti = 8;           // multi-volume scenes (more time between volumes, more latency to hide) prefer the extra warps
+#ifndef VP_WF_MINBLOCKS_MULTI
+#define VP_WF_MINBLOCKS_MULTI 7
+#endif
+constexpr int kWfMinBlocksMulti = VP_WF_MINBLOCKS_MULTI;          // multi-volume scenes: 7 since the round-2 step body (72 registers instead of 64 with spills: cfg 4 -3.7 %, cfg 5 -1.7 %)
 constexpr int kRefill = 20;           // refill when fewer lanes than this are still stepping
 constexpr int kBulkLanes = 12;        // with at most this many lanes walking, lanes in empty 8^3/16^3 blocks bulk-advance
 constexpr int kMaskVolumes = 23;      // scenes up to this size carry the bounding-sphere candidates of a ray in its prepared record

@@ -374,3 +374,19 @@ print("GL-OK")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
     assert "GL-OK" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-1500:])
+
+
+@pytest.mark.gpu
+def test_sincos_pin_exhaustive(product):
+    """RandomSphereSample's sinf / cosf are pinned to fp64 sincos + one rounding.  The shade stage
+    evaluates the main path of the library's fp64 routine inline (its arguments are rnd() * pi and rnd() * 2 pi, all in
+    [0, 2 pi], so the huge-argument branch is dead code there): every fp32 in [0, 8] - 1.09 G arguments, the whole domain
+    and a margin - and every negative fp32 down to -8 must give the same two floats, bit for bit."""
+    import ctypes as C
+    import struct
+    with vp.Session(product, 0) as s:
+        hi = struct.unpack("<I", struct.pack("<f", 8.0))[0]
+        for first, last in ((0, hi), (0x80000000, 0x80000000 | hi)):
+            bad, where = C.c_uint64(1), C.c_uint32(0)
+            product.check(product.c_check_sincos_pin(s.ctx, first, last, C.byref(bad), C.byref(where)), "check_sincos_pin")
+            assert bad.value == 0, f"{bad.value} arguments differ, first at bit pattern {where.value:#010x}"
