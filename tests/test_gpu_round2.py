@@ -390,3 +390,24 @@ def test_sincos_pin_exhaustive(product):
             bad, where = C.c_uint64(1), C.c_uint32(0)
             product.check(product.c_check_sincos_pin(s.ctx, first, last, C.byref(bad), C.byref(where)), "check_sincos_pin")
             assert bad.value == 0, f"{bad.value} arguments differ, first at bit pattern {where.value:#010x}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"VP_SPARE": "0"}, {"VP_SPARE": "3"}, {"VP_OV_EXTEND": "0", "VP_OV_SHADOW": "0", "VP_OV_SHADE": "0"},
+                                 {"VP_OV_EXTEND": "1", "VP_OV_SHADOW": "1", "VP_OV_SHADE": "1", "VP_LANES": "9"}])
+def test_single_volume_switches(product, monkeypatch, env):
+    """The switches of the single-volume kernels (spare ray / request per lane, prepared shadow walks, grid caps while
+    passes overlap, more passes in flight) change how the work is handed out, never the result: cfg 2 at a size whose
+    calls exceed 2^19 paths (the prepared shadow stage is on), four samples in flight, against the default build-up."""
+    sc, cam, fpd = small_config(2, 1024, 576, spp=4)
+    monkeypatch.setenv("VP_BANDS", "1")  # one pass per sample over the whole frame: 589 824 paths per call
+    res = []
+    for e in ({}, env):
+        for k, v in e.items():
+            monkeypatch.setenv(k, v)
+        with vp.Session(product, 0) as s:
+            s.set_scene(sc)
+            res.append(s.render(cam, params(fpd)))
+    assert np.count_nonzero(bits(res[0][0]) != bits(res[1][0])) == 0, env
+    assert np.array_equal(res[0][1], res[1][1])
+    assert res[0][2].rays == res[1][2].rays and res[0][2].shadow_rays == res[1][2].shadow_rays
