@@ -1,19 +1,11 @@
 #!/bin/bash
-# GPU box: one traversal stage per bounce (VP_MERGE) against the separate extend / shadow stages
-run() { echo "$1 $(env $1 python tools/shard_probe.py ${2:-2 1} ${3:-60} 2>&1 | tail -1 | cut -c1-40)"; }
+# GPU box: parked light samples (VP_LIGHT_DEFER, the default build) against the variant build without them
+P=$PWD/raytracer-voxpopuli_b200
+run() { echo "$1 $(env $2 python tools/shard_probe.py ${3:-2 1} ${4:-60} 2>&1 | tail -1 | cut -c1-40)"; }
 {
 python -m pytest tests -m gpu -x -q 2>&1 | tail -1
-run "VP_MERGE=0"
-run "VP_MERGE=1"
-run "VP_MERGE=1 VP_OV_EXTEND=5"
-run "VP_MERGE=1 VP_OV_EXTEND=6"
-run "VP_MERGE=1 VP_OV_EXTEND=3"
-run "VP_MERGE=0" "2 8" 120
-run "VP_MERGE=1" "2 8" 120
-run "VP_MERGE=0" "2 2"
-run "VP_MERGE=1" "2 2"
-run "VP_MERGE=0" "3 1"
-run "VP_MERGE=1" "3 1"
-run "VP_MERGE=0" "1 1"
-run "VP_MERGE=1" "1 1"
+for c in "2 1" "3 1" "4 1" "5 1" "1 1" "2 8"; do
+run "defer   $c" "A=0" "$c"
+run "nodefer $c" "VP_PRODUCT_SO=$P/libvoxpop_b200_nodefer.so" "$c"
+done
 } | tee gpurun_out/${1:-x4}_sweep.log
