@@ -7,7 +7,7 @@ A "step" is one Renderer::Update() pass (1 spp) of the workload over the whole f
             and timed with one CUDA-event pair around exactly K steps.
   e2e       the same metric through the reference-facing C-ABI calls with HOST buffers (page-locked):
             every step uploads the float4 accumulator and downloads accumulator + RGB8 image.
-            vp_render_async / vp_render_wait keep three frames in flight (the reference's Tick only
+            vp_render_async / vp_render_wait keep six frames in flight (the reference's Tick only
             needs frame k's pixels when it blits them); the synchronous vp_render figure is reported
             next to it.  With N > 1 GPUs rank 0 drives all N GPUs through ONE multi-device context
             (vp_create_multi): one C call per step, the frame assembled in ONE host buffer.
@@ -201,7 +201,7 @@ class NcclGather:
         return self.g(frame)
 
 
-def async_e2e(lib, sess, cc, fpd, steps, W, H, torch, in_flight=3):
+def async_e2e(lib, sess, cc, fpd, steps, W, H, torch, in_flight=5):
     """Update() through vp_render_async with page-locked host buffers: every step uploads the accumulator and downloads
     accumulator + image; two accumulators / images alternate so that the host could read frame k while k+1 is in flight."""
     h_acc = [torch.zeros((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -217,7 +217,7 @@ def async_e2e(lib, sess, cc, fpd, steps, W, H, torch, in_flight=3):
         if len(tickets) > in_flight:
             lib.check(lib.c_render_wait(sess.ctx, tickets[-1 - in_flight]), "render_wait")
 
-    WARM = 8  # every lane of every device has allocated its path state and captured its graph (up to six lanes for small shards)
+    WARM = 12  # every lane of every device has allocated its path state and captured its graph (six lanes, eight for small shards)
     for i in range(WARM):
         issue(i)
     lib.check(lib.c_render_wait(sess.ctx, tickets[-1]), "render_wait")
@@ -274,7 +274,7 @@ def main():
     # Frames in flight: a step is enqueued with VP_FLAG_DEFER, so its latency-bound tail overlaps the next step's wide first
     # bounces.  With several ranks every frame in flight needs its own image (its tiles land in rank 0's HBM while later
     # frames are traced), plus two so that a frame never waits for the consumer of the frame that last used its image.
-    NBUF = int(os.environ.get("VP_BENCH_IMAGES", "6")) if world > 1 else 1
+    NBUF = int(os.environ.get("VP_BENCH_IMAGES", "8")) if world > 1 else 1
     stream = torch.cuda.current_stream(dev)
     comm = torch.cuda.Stream(dev) if world > 1 else None
     img_bytes = W * H * 4
@@ -360,10 +360,10 @@ def main():
     sampler = ClockSampler(local, period_s=float(os.environ.get("VP_BENCH_CLOCK_PERIOD", "0.02")))
     if os.environ.get("VP_BENCH_NO_SAMPLER") != "1":
         sampler.start()
-    # set-up, not warm-up: the first frame on each of the library's lanes (four, six for small shards) allocates that lane's path state and
+    # set-up, not warm-up: the first frame on each of the library's lanes (six, eight for small shards) allocates that lane's path state and
     # captures its CUDA graph (into a scratch accumulator; frame indices of the measured frames are untouched)
     scratch = torch.zeros_like(accum)
-    for k in range(6):
+    for k in range(12):
         fp0 = frame_params(fpd, frame_index=0, flags=abi.VP_FLAG_DEFER, **shard)
         lib.check(lib.c_render_device(sess.ctx, C.byref(cc), C.byref(fp0), scratch.data_ptr(), None, stream.cuda_stream, None), "render_device(set-up)")
     fence(stream)
@@ -461,7 +461,7 @@ def main():
                 s_rays += s1.rays
                 s_t += dt
         e2e = {"value": av, "unit": "Mrays/s", "h2d_bytes_per_step": W * H * 16, "d2h_bytes_per_step": W * H * 16 + W * H * 4, "ms_per_step": ams,
-               "api": "vp_render_async + vp_render_wait (page-locked host float4 accumulator in / out + RGB8 out every step, 3 frames in flight)",
+               "api": "vp_render_async + vp_render_wait (page-locked host float4 accumulator in / out + RGB8 out every step, 6 frames in flight)",
                "steps": e2e_steps, "timer": "host wall clock around the steps, last ticket waited for",
                "synchronous": {"value": s_rays / s_t / 1e6, "ms_per_step": 1e3 * s_t / min(e2e_steps, 10), "api": "vp_render (one blocking call per frame)"}}
     elif rank == 0:
@@ -473,7 +473,7 @@ def main():
         g.close()
         e2e = {"value": av, "unit": "Mrays/s", "h2d_bytes_per_step": W * H * 16, "d2h_bytes_per_step": W * H * 16 + W * H * 4, "ms_per_step": ams,
                "api": f"vp_create_multi({world} devices) + vp_render_async / vp_render_wait from ONE process: one C call per step, every GPU moves its own "
-                      "row tiles over its own PCIe link into ONE page-locked host accumulator / image, 3 frames in flight",
+                      "row tiles over its own PCIe link into ONE page-locked host accumulator / image, 6 frames in flight",
                "steps": e2e_steps, "timer": "host wall clock around the steps, last ticket waited for", "peer_access": ginfo.get("peer_access")}
     if world > 1:
         dist.barrier(group=host_group)
@@ -571,7 +571,7 @@ def main():
                                           "sample": f"64-row band (rows {band[0]}..{band[1] - 1}) of one {W}x{H} frame, 1 thread"}
     if world == 1 and not args.no_also:
         # the other configurations of BASELINE.json and room.vox with its native (glass) materials, device-resident,
-        # four frames in flight, 1 spp per step at full size: short runs so that they are driver-visible
+        # six frames in flight, 1 spp per step at full size: short runs so that they are driver-visible
         also = {}
         for idx in (1, 3, 4, 5, 6):
             sc_i, cam_i, fpd_i = bench_inputs(idx)
@@ -613,7 +613,7 @@ def main():
                        "exchange_check": exchange_check,
                        "l2": "not flushed: every step streams its own path state through HBM (~1.3 GB per 1080p frame, >> 126 MB L2); the "
                              "2.3 MB scene is L2-resident by design (DESIGN.md section 3)",
-                       "frames_in_flight": 4, "traversal": "brick walk (one exact merge step per empty 4x4x4 brick), prepare stage",
+                       "frames_in_flight": int(meta.get("lanes", 6)), "traversal": "brick walk (one exact merge step per empty 4x4x4 brick), prepare stage",
                        "timed_region": "one CUDA-event pair around all steps; " + ("the first step runs alone with stage events (VP_FLAG_TIME_STAGES)" if staged_inside else "all steps pipelined (the stage-timed step follows the region)"),
                        "hbm_in_use": meta.get("hbm_in_use"), "graph_node_updates_per_replay": (meta["graph_node_updates"] / meta["graph_replays"]) if meta.get("graph_replays") else None,
                        "also": also},

@@ -100,7 +100,7 @@ struct WfLane {
   bool prims = false, prepared = false, masks = false, area = false, sprep = false;  // optional parts laid out
   size_t bytes = 0;
 };
-constexpr int kLanes = 12;      // most frames in flight (c->nlanes are used: 4 unless VP_LANES says otherwise)
+constexpr int kLanes = 12;      // most frames in flight (c->nlanes are used: 6 unless VP_LANES says otherwise)
 constexpr int kCallRing = 8;    // completion events kept for vp_render_fence
 
 constexpr int kTickets = 16;     // vp_render_async calls whose completion events are kept
@@ -135,7 +135,7 @@ struct vp_ctx {
   cudaStream_t stream = nullptr;
   WfLane lane[kLanes];
   int next_lane = 0;
-  int nlanes = 4;      // frames in flight (VP_LANES); lowered only when a lane's path state cannot be allocated
+  int nlanes = 6;      // frames in flight (VP_LANES; 4 until the end of round 2: cfg 2 -2.5 %, cfg 4 -5.7 % with six and 32 hardware queues); lowered only when a lane's path state cannot be allocated
   bool lanes_fixed = false;
   cudaEvent_t ev_in = nullptr;      // recorded on the caller's stream when a render call enters
   cudaEvent_t ev_direct = nullptr;  // recorded after a launch made directly on the caller's stream (single-kernel formulations)
@@ -179,7 +179,7 @@ struct vp_ctx {
   int tune_refill_spare = 24; // VP_REFILL_SPARE (8: 3.83 ms, 16: 3.73, 20: 3.69, 24: 3.67, 28: 3.68 per cfg-2 frame)
   int wf_blocks_extend_spare = 0;
   int tune_shard_lanes = 2;   // VP_SHARD_LANES: passes in flight beyond nlanes for calls of at most 2^19 paths (a rank's share of a multi-GPU frame)
-  int tune_ov_extend = 4, tune_ov_shadow = 2, tune_ov_shade = 2;  // VP_OV_EXTEND / _SHADOW / _SHADE: resident blocks per SM of a stage when passes of a single-volume scene overlap (0: no cap)
+  int tune_ov_extend = 2, tune_ov_shadow = 2, tune_ov_shade = 2;  // VP_OV_EXTEND / _SHADOW / _SHADE: resident blocks per SM of a stage when passes of a single-volume scene overlap (0: no cap)
   int tune_refill = kRefill;  // VP_REFILL
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
   int tune_brickwalk = 1;     // VP_BRICKWALK: 0 = cell walk only (A/B)
