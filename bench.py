@@ -588,12 +588,12 @@ def main():
                     lib.check(lib.c_render_device(sess.ctx, C.byref(cci), C.byref(fp_i), acc_i.data_ptr(), rgb_i.data_ptr(), stream.cuda_stream, None), "render_device")
                 fence(stream)
 
-            run(0, 4)
+            run(0, 12)  # set-up: every lane (six; eight for small calls) has sized its path state for this frame and captured its graph
             torch.cuda.synchronize(dev)
             lib.check(lib.c_stats_begin(sess.ctx), "stats_begin")
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            run(4, n_i)
+            run(12, n_i)
             e1.record(stream)
             torch.cuda.synchronize(dev)
             sti = abi.VpStats()
