@@ -836,7 +836,6 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocksShade) k_wf_shade(const 
   if (blockIdx.x * blockDim.x >= p.st.counts[4 * p.iter]) return;  // grid-stride loop below would be empty
   const Staged stg = wf_stage_scene(p.sc, smem);
   const Lights lights = wf_stage_lights(p.sc, smem, p.light_smem_off, p.light_smem);
-  const uint32_t* queue = p.st.q[p.iter & 1];
   uint32_t* qnext = p.st.q[(p.iter + 1) & 1];
   uint32_t* cnt = p.st.counts + 4 * p.iter;
   const uint32_t n = cnt[0];
