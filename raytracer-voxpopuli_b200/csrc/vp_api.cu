@@ -178,8 +178,9 @@ struct vp_ctx {
   int tune_spare = 1;         // VP_SPARE: single-volume scenes: every lane of the extend stage holds a spare ray (k_wf_extend_spare)
   int tune_refill_spare = 24; // VP_REFILL_SPARE (8: 3.83 ms, 16: 3.73, 20: 3.69, 24: 3.67, 28: 3.68 per cfg-2 frame)
   int wf_blocks_extend_spare = 0;
+  uint32_t tune_sspare_min = 1u << 16;  // VP_SSPARE_MIN: calls of more paths than this run the prepared shadow stage (k_wf_shadow_prepare + k_wf_shadow_spare)
   int tune_shard_lanes = 2;   // VP_SHARD_LANES: passes in flight beyond nlanes for calls of at most 2^19 paths (a rank's share of a multi-GPU frame)
-  int tune_ov_extend = 2, tune_ov_shadow = 2, tune_ov_shade = 2;  // VP_OV_EXTEND / _SHADOW / _SHADE: resident blocks per SM of a stage when passes of a single-volume scene overlap (0: no cap)
+  int tune_ov_extend = 2, tune_ov_shadow = 1, tune_ov_shade = 1;  // VP_OV_EXTEND / _SHADOW / _SHADE: resident blocks per SM of a stage when passes of a single-volume scene overlap (0: no cap)
   int tune_refill = kRefill;  // VP_REFILL
   int tune_bulk = kBulkLanes; // VP_BULK_LANES
   int tune_brickwalk = 1;     // VP_BRICKWALK: 0 = cell walk only (A/B)
@@ -434,7 +435,7 @@ int enqueue_trace(vp_ctx* c, WfLane& L, WfParams& p, bool timing, bool capturing
       c->host_launches++;
     }
     // (a rank's share of a multi-GPU frame is latency-bound: the extra kernel per bounce costs more than it saves there)
-    const bool sspare = spare && p.sc.nal == 0 && !(c->tune_spare & 2) && p.st.cap > (1u << 19);
+    const bool sspare = spare && p.sc.nal == 0 && !(c->tune_spare & 2) && p.st.cap > c->tune_sspare_min;
     if (sspare) {
       k_wf_shadow_prepare<<<wide, kWfBlock, 0, L.side>>>(p);
       c->host_launches++;
@@ -466,7 +467,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
 {
   PassGraph& G = L.pg;
   const size_t sm = smem_bytes(c) + (smem_bytes_shade(c) << 20);
-  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 + (p.sc.nal > 0 ? 64 : 0) + (p.sc.nsph + p.sc.ntri > 0 ? 128 : 0) + (p.st.cap > (1u << 19) ? 256 : 0) && G.smem == sm &&
+  const bool fresh = !(G.exec && G.max_bounces == p.max_bounces && G.brickwalk == c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 + (p.sc.nal > 0 ? 64 : 0) + (p.sc.nsph + p.sc.ntri > 0 ? 128 : 0) + (p.st.cap > c->tune_sspare_min ? 256 : 0) && G.smem == sm &&
                        G.counts == (const void*)p.st.counts && G.nvol == p.sc.nvol && G.stagger == c->tune_band_stagger);
   if (fresh) {
     if (G.exec) CU(cudaStreamSynchronize(L.main));  // the old graph may still be running on this lane
@@ -496,7 +497,7 @@ int graph_trace(vp_ctx* c, WfLane& L, WfParams& p)
              : (x.kp.func == (void*)k_wf_generate) ? 3 : (x.kp.func == (void*)k_wf_shade<false>) ? 4 : 0;
       G.nodes.push_back(x);
     }
-    G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 + (p.sc.nal > 0 ? 64 : 0) + (p.sc.nsph + p.sc.ntri > 0 ? 128 : 0) + (p.st.cap > (1u << 19) ? 256 : 0); G.smem = sm; G.counts = (const void*)p.st.counts;
+    G.max_bounces = p.max_bounces; G.brickwalk = c->tune_brickwalk * 2 + p.prepared + c->tune_spare * 4 + (p.sc.nal > 0 ? 64 : 0) + (p.sc.nsph + p.sc.ntri > 0 ? 128 : 0) + (p.st.cap > c->tune_sspare_min ? 256 : 0); G.smem = sm; G.counts = (const void*)p.st.counts;
     G.nvol = p.sc.nvol; G.stagger = c->tune_band_stagger;
     G.captures++;
   } else {
@@ -679,7 +680,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
   WfNeed need;
   need.cap = cap; need.levels = levels; need.samples = samples;
   need.prims = c->sc.nsph + c->sc.ntri > 0; need.prepared = p.prepared != 0; need.masks = c->sc.nvol > 1 && c->sc.nvol <= 32; need.area = c->sc.nal > 0;
-  need.sprep = p.prepared && c->tune_spare && c->tune_brickwalk && c->sc.nvol == 1 && c->sc.nsph + c->sc.ntri == 0 && c->sc.nal == 0 && cap > (1u << 19);
+  need.sprep = p.prepared && c->tune_spare && c->tune_brickwalk && c->sc.nvol == 1 && c->sc.nsph + c->sc.ntri == 0 && c->sc.nal == 0 && cap > c->tune_sspare_min;
   // Persistent grids follow the number of paths this call can have: a warp that gets only ~1 ray per lane never refills
   // and ends at the SIMD efficiency of its longest ray, so small shards run fewer, longer-lived warps (>= 3 blocks per SM
   // to keep latency hidden; measured on 1/8 frame shares, profiles/README.md).
@@ -936,6 +937,7 @@ vp_ctx* vp_create(int device)
   if (const char* e = getenv("VP_BAND_STAGGER")) c->tune_band_stagger = atoi(e);
   if (const char* e = getenv("VP_BANDS")) c->tune_bands = atoi(e) < 1 ? 1 : atoi(e);
   if (const char* e = getenv("VP_BAND_MIN_PIXELS")) c->tune_band_min_pixels = atoll(e);
+  if (const char* e = getenv("VP_SSPARE_MIN")) c->tune_sspare_min = (uint32_t)atoll(e);
   if (const char* e = getenv("VP_SHARD_LANES")) c->tune_shard_lanes = atoi(e) < 0 ? 0 : atoi(e);
   if (const char* e = getenv("VP_OV_EXTEND")) c->tune_ov_extend = atoi(e);
   if (const char* e = getenv("VP_OV_SHADOW")) c->tune_ov_shadow = atoi(e);
