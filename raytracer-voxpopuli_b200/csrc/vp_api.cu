@@ -191,10 +191,10 @@ struct vp_ctx {
   int tune_prepare = 1;       // VP_PREPARE: 0 = the extend stage sets up every walk itself
   bool graph_now = false;     // this call's passes go through the lane graphs
   int tune_band_ramp = 0;     // VP_BAND_RAMP: band heights 1 : 2 : ... : n instead of equal
-  int tune_band_stagger = 0;  // VP_BAND_STAGGER: band k+1 of a vp_render call starts when band k has shaded this bounce (-1: all at once)
+  int tune_band_stagger = -1; // VP_BAND_STAGGER: band k+1 of a vp_render call starts when band k has shaded this bounce (-1: all at once - the default since six passes are in flight: 4.25 -> 4.17 ms per synchronous cfg-2 frame; 0 until then)
   int band_last_lane = -1;    // lane the most recent pass went to
   int band_wait_lane = -1;    // lane whose ev_mid the next pass has to wait for (set by vp_render between its bands)
-  int tune_bands = 4;         // VP_BANDS: row bands a vp_render call is cut into (1 = off)
+  int tune_bands = 6;         // VP_BANDS: row bands a vp_render call is cut into (1 = off; one per lane: 4 bands 4.50 ms, 6 bands 4.25 ms per synchronous cfg-2 frame)
   long long tune_band_min_pixels = 1 << 18;  // VP_BAND_MIN_PIXELS: smaller calls are not cut
   int tune_paths_per_thread = 8;  // VP_PATHS_PER_THREAD: paths of a call per thread of the persistent traversal grids (small shards: fewer, longer-lived warps)
   int tune_min_blocks = 2;        // VP_MIN_BLOCKS: ... but at least this many blocks per SM (1/8 frame shares: 0.636 ms with 1-2, 0.654 with 3, 0.669 with 4)

@@ -486,8 +486,9 @@ def test_render_row_bands(product, oracle, monkeypatch):
         w1, w1_rgb, st1 = s.render(cam, params(fpd, spp=1))
         w3, w3_rgb, st3 = s.render(cam, params(fpd, spp=3, frame_index=1), accum=w1.copy())
         wr, wr_rgb, str_ = s.render(cam, params(fpd, spp=2, frame_index=7, row_begin=10, row_end=61))
-    for bands in ("4", "3", "1"):
+    for bands, stagger in (("6", "-1"), ("4", "0"), ("3", "1"), ("1", "-1")):  # the default cut, round 2's, a late start, none
         monkeypatch.setenv("VP_BANDS", bands)
+        monkeypatch.setenv("VP_BAND_STAGGER", stagger)
         monkeypatch.setenv("VP_BAND_MIN_PIXELS", "0")
         with vp.Session(product) as s:  # the knobs are read when the context is created
             s.set_scene(sc)
