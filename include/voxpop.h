@@ -207,7 +207,7 @@ int vp_host_unregister(vp_ctx* ctx, void* ptr);
  * rgb8_dev: W*H uint32 or NULL.  cuda_stream: a cudaStream_t (NULL = default stream).
  * With stats == NULL the call only enqueues work and returns; otherwise it synchronises
  * the stream and fills the counters.  The samples of one call (spp > 1) are pipelined over
- * up to four internal stream pairs; cuda_stream orders the call: it starts after what the
+ * up to six internal stream pairs (eight for small calls); cuda_stream orders the call: it starts after what the
  * stream holds and (unless VP_FLAG_DEFER) the stream waits for its last resolve. */
 int vp_render_device(vp_ctx* ctx, const VpCamera* cam, const VpFrameParams* fp, void* accum_rgba_dev, void* rgb8_dev,
                      void* cuda_stream, VpStats* stats);

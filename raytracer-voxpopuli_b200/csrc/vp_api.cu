@@ -702,7 +702,7 @@ int launch_wavefront(vp_ctx* c, const VpCamera* cam, const VpFrameParams* fp, fl
     c->wf_grid_shadow = full ? bs : (int)ws;
     const long long wh = want * c->sm_count < c->wf_blocks_shade ? want * c->sm_count : c->wf_blocks_shade;
     c->wf_grid_shade = (full || c->wf_shade_fixed) ? c->wf_blocks_shade : (int)wh;
-    // Single-volume scenes whose passes overlap: the stages of the four frames in flight share the SMs, and a warp of a
+    // Single-volume scenes whose passes overlap: the stages of the frames in flight (six) share the SMs, and a warp of a
     // smaller persistent grid sees more rays per lane (its lanes refill, its spares get used) - fewer resident blocks per
     // stage win there (cfg 2: 3.19 -> 2.9 ms per frame).  Multi-volume scenes lose with the same caps (cfg 5 +6 %): theirs stay.
     if (!full && spare) {
