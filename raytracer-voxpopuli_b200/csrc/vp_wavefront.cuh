@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend(const __grid_const
 #endif
               bw.F = axis_field(v.jr, 0);
               bw.flip = ((fl >> 7) & 1u ? bw.F : 0u) | ((fl >> 8) & 1u ? bw.F << 1 : 0u) | ((fl >> 9) & 1u ? bw.F << 2 : 0u);
-              bw.plain = (fl >> 6) & 1u; bw.ac = kAcFirst; bw.tc = __uint_as_float(0xFF800000u);
+              bw.plain = (fl >> 6) & 1u; bw.ac = kAcFirst; bw.tc = __uint_as_float(kTcFirst);
               occ_reset(o); region = region_of(stg, v); fine = v.fine;
               in_dda = true;
             }
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_extend_spare(const __grid
     s.tx = w0_.x; s.ty = w0_.y; s.tz = w0_.z; s.t = w0_.w;                                                            \
     s.dx = w1_.x; s.dy = w1_.y; s.dz = w1_.z; s.P = __float_as_uint(w1_.w);                                           \
     bw.ex = w2_.x; bw.ey = w2_.y; bw.ez = w2_.z;                                                                      \
-    bw.flip = fl_ >> 2; bw.plain = (fl_ >> 1) & 1u; bw.ac = kAcFirst; bw.tc = __uint_as_float(0xFF800000u);                 \
+    bw.flip = fl_ >> 2; bw.plain = (fl_ >> 1) & 1u; bw.ac = kAcFirst; bw.tc = __uint_as_float(kTcFirst);                 \
     occ_reset(o);                                                                                                     \
   }
   for (;;) {
@@ -1143,7 +1143,7 @@ __global__ void __launch_bounds__(kWfBlock, MINB) k_wf_shadow_spare(const __grid
     s.tx = w0_.x; s.ty = w0_.y; s.tz = w0_.z; s.t = w0_.w;                                                            \
     s.dx = w1_.x; s.dy = w1_.y; s.dz = w1_.z; s.P = __float_as_uint(w1_.w);                                           \
     bw.ex = w2_.x; bw.ey = w2_.y; bw.ez = w2_.z;                                                                      \
-    bw.flip = fl_ >> 2; bw.plain = (fl_ >> 1) & 1u; bw.ac = kAcFirst; bw.tc = __uint_as_float(0xFF800000u);                 \
+    bw.flip = fl_ >> 2; bw.plain = (fl_ >> 1) & 1u; bw.ac = kAcFirst; bw.tc = __uint_as_float(kTcFirst);                 \
     occ_reset(o);                                                                                                     \
   }
   for (;;) {

@@ -194,7 +194,7 @@ static Res unified_walk(const uint64_t* fine, int n, St s, float tlimit, Stats* 
       E[a] = e;
     }
   int brick = 0, ac = 0, have = 0;
-  float tc = -INFINITY;  /* key (tc, ac) of the lane's last brick step: cell steps below it are silent */
+  float tc = NAN;  /* key (tc, ac) of the lane's last brick step: cell steps below it are silent; NaN before the first (no element is below or equal: a tmax of -inf is possible, see kTcFirst in csrc/vp_device.cuh) */
   int key[3] = {-1, -1, -1};
   uint64_t m = 0;
   while (s.t < tlimit) {
@@ -230,6 +230,114 @@ static Res unified_walk(const uint64_t* fine, int n, St s, float tlimit, Stats* 
   return r;
 }
 
+/* ---- mode 3: the kernels' step at the BIT level (csrc/vp_device.cuh: setup of the walk word, bw_init, walk_step and uw_step
+ * under VP_STEP_V2) ---------------------------------------------------------------------------------------------------------
+ * Cell coordinates in one Morton word P (bit 3i + a = bit i of axis a), the walk mirrored on the axes the ray descends
+ * (P' = P ^ flip: every step is +1, leaving the padded grid is the carry out of the masked add), the stepped axis carried
+ * as its lowest field bit (1, 2, 4; BW::ac too), field masks as products, the forward-box table indexed by the mirrored
+ * cell and holding the one-hot mask of the real cell, the brick key kept in mirrored coordinates.  finem: brick masks in
+ * Morton order (index P >> 6, bit P & 63), the padded grid being (16 << jr)^3. */
+static uint32_t dilate3_(uint32_t v)
+{
+  v &= 0x3FFu;
+  v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+static uint32_t compact3_(uint32_t v)
+{
+  v &= 0x09249249u;
+  v = (v | (v >> 2)) & 0x030C30C3u; v = (v | (v >> 4)) & 0x0300F00Fu; v = (v | (v >> 8)) & 0x030000FFu; v = (v | (v >> 16)) & 0x3FFu;
+  return v;
+}
+static uint64_t fwd_box_[512], fwd_bit_[512];
+static void fwd_table_(void)  /* k_fwd_table */
+{
+  for (uint32_t idx = 0; idx < 512; idx++) {
+    const uint32_t sg = idx >> 6;
+    const uint32_t mir = ((sg & 1u) ? 9u : 0u) | ((sg & 2u) ? 18u : 0u) | ((sg & 4u) ? 36u : 0u);
+    const uint32_t cell = (idx & 63u) ^ mir;
+    const uint32_t cx = compact3_(cell), cy = compact3_(cell >> 1), cz = compact3_(cell >> 2);
+    uint64_t m = 0;
+    for (uint32_t q = 0; q < 64; q++) {
+      const uint32_t x = compact3_(q), y = compact3_(q >> 1), z = compact3_(q >> 2);
+      const int ok = ((sg & 1u) ? x <= cx : x >= cx) && ((sg & 2u) ? y <= cy : y >= cy) && ((sg & 4u) ? z <= cz : z >= cz);
+      if (ok) m |= 1ull << q;
+    }
+    fwd_box_[idx] = m; fwd_bit_[idx] = 1ull << cell;
+  }
+}
+void bw_build_fine_morton(const uint8_t* grid, int n, int jr, uint64_t* finem)
+{
+  memset(finem, 0, sizeof(uint64_t) * ((size_t)64 << (3 * jr)));
+  for (int z = 0; z < n; z++) for (int y = 0; y < n; y++) for (int x = 0; x < n; x++)
+    if (grid[x + n * (y + n * z)] != 255) {
+      const uint32_t P = dilate3_((uint32_t)x) | (dilate3_((uint32_t)y) << 1) | (dilate3_((uint32_t)z) << 2);
+      finem[P >> 6] |= 1ull << (P & 63u);
+    }
+}
+static Res bit_walk(const uint64_t* finem, int jr, St s0, float tlimit, Stats* st)
+{
+  Res r; memset(&r, 0, sizeof r);
+  static int ready = 0;
+  if (!ready) { fwd_table_(); ready = 1; }
+  float tx = s0.F[0], ty = s0.F[1], tz = s0.F[2];
+  const float dx = s0.d[0], dy = s0.d[1], dz = s0.d[2];
+  float t = s0.t;
+  uint32_t P = dilate3_((uint32_t)s0.X[0]) | (dilate3_((uint32_t)s0.X[1]) << 1) | (dilate3_((uint32_t)s0.X[2]) << 2);
+  /* bw_init */
+  uint32_t ac = 1u; float tc = NAN;
+  const uint32_t plain = (tx == tx && ty == ty && tz == tz) ? 0u : 1u;
+  const uint32_t F = 0x09249249u & ((1u << (3u * (4u + (uint32_t)jr))) - 1u);
+  const uint32_t flip = (s0.dir[0] < 0 ? F : 0u) | (s0.dir[1] < 0 ? F << 1 : 0u) | (s0.dir[2] < 0 ? F << 2 : 0u);
+  P ^= flip;
+  const uint32_t nx = ~P & 9u, ny = ~P & 18u, nz = ~P & 36u;
+  float e, ex, ey, ez;
+  e = tx; if (nx & 1u) e += dx; if (nx & 8u) { e += dx; e += dx; } ex = e;
+  e = ty; if (ny & 2u) e += dy; if (ny & 16u) { e += dy; e += dy; } ey = e;
+  e = tz; if (nz & 4u) e += dz; if (nz & 32u) { e += dz; e += dz; } ez = e;
+  uint32_t key = 0xFFFFFFFFu; uint64_t m = 0;
+  if (plain) st->nan_rays++;
+  while (t < tlimit) {
+    const float t0 = t;
+    /* walk_step: the brick mask is fetched when the (mirrored) brick changes */
+    if ((P ^ key) >> 6) { key = P; m = finem[(P ^ flip) >> 6]; }
+    /* uw_step */
+    const uint32_t idx = ((flip & 7u) << 6) | (P & 63u);
+    const int brick = (m & fwd_box_[idx]) == 0ull && plain == 0u;
+    const float vx = brick ? ex : tx, vy = brick ? ey : ty, vz = brick ? ez : tz;
+    const int xy = vx < vy;
+    const int ax = xy & (vx < vz);
+    const int ay = (!xy) & (vy < vz);
+    const int az = !(ax | ay);
+    const float T = ax ? vx : (ay ? vy : vz);
+    const uint32_t lowb = ax ? 1u : (ay ? 2u : 4u);
+    const int silent = !brick & ((T < tc) | ((T == tc) & (lowb > ac)));
+    const int hit = !brick & !silent & ((m & fwd_bit_[idx]) != 0ull);
+    if (brick) { tc = T; ac = lowb; st->brick_steps++; } else st->cell_steps++;
+    const uint32_t M9 = lowb * 9u, Fa = lowb * F;
+    if (brick) P |= M9;
+    const int cross = (P & M9) == M9;
+    if (ax) tx = vx + dx;
+    if (ay) ty = vy + dy;
+    if (az) tz = vz + dz;
+    if (ax && cross) ex = ((tx + dx) + dx) + dx;
+    if (ay && cross) ey = ((ty + dy) + dy) + dy;
+    if (az && cross) ez = ((tz + dz) + dz) + dz;
+    const uint32_t q = (P | ~Fa) + lowb;
+    const int out = q < lowb;
+    if (!hit) P = (q & Fa) | (P & ~Fa);
+    if (!silent) t = T;
+    if (out) t = 3.0e38f;
+    if (hit) {
+      const uint32_t Pr = P ^ flip;
+      r.hit = 1; r.t = t0;
+      r.X[0] = (int)compact3_(Pr); r.X[1] = (int)compact3_(Pr >> 1); r.X[2] = (int)compact3_(Pr >> 2);
+      return r;
+    }
+  }
+  return r;
+}
+
 /* fine[bx + nb*(by + nb*bz)] bit (x&3)|(y&3)<<2|(z&3)<<4 */
 void bw_build_fine(const uint8_t* grid, int n, uint64_t* fine)
 {
@@ -243,7 +351,7 @@ void bw_build_fine(const uint8_t* grid, int n, uint64_t* fine)
 /* rays: O[3], D[3] per ray (object space of the unit cube), tlimit per ray.  Returns the number of mismatching rays;
  * first_bad = index of the first one (or -1).  out (optional): per ray {hit, t bits, cell} of the cell walk. */
 int64_t bw_compare(const uint8_t* grid, const uint64_t* fine, int n, const float* O, const float* D, const float* tlimit, int64_t count,
-                   int mode, Stats* st, int64_t* first_bad, uint32_t* out)
+                   int mode, Stats* st, int64_t* first_bad, uint32_t* out)  /* mode 3: fine = Morton-ordered masks (bw_build_fine_morton) */
 {
   int64_t bad = 0;
   *first_bad = -1;
@@ -255,7 +363,8 @@ int64_t bw_compare(const uint8_t* grid, const uint64_t* fine, int n, const float
     if (setup(O + 3 * i, D + 3 * i, n, &s)) {
       st->rays++;
       a = cell_walk(grid, n, s, tlimit[i]);
-      b = mode ? unified_walk(fine, n, s, tlimit[i], st, mode == 2) : brick_walk(grid, fine, n, s, tlimit[i], st);
+      if (mode == 3) { int jr = 0; while ((16 << jr) < n) jr++; b = bit_walk(fine, jr, s, tlimit[i], st); }
+      else b = mode ? unified_walk(fine, n, s, tlimit[i], st, mode == 2) : brick_walk(grid, fine, n, s, tlimit[i], st);
       st->ref_steps += a.steps;
     }
     uint32_t ta, tb; memcpy(&ta, &a.t, 4); memcpy(&tb, &b.t, 4);

@@ -1,8 +1,10 @@
 """CPU model of the kernels' brick walk (tests/brickwalk_model.c) against the reference's cell walk:
 hit / no hit, hit cell and the bits of t must be identical on every ray - random rays, rays with a
 stopping distance (shadow rays), axis-parallel and grid-aligned rays (inf / NaN tmax), -0 directions and
-exact diagonals (ties between axes).  Three formulations: explicit catch-up (mode 0), the unified step
-(mode 1) and the unified step with the forward-box rule, which is what the kernels use (mode 2)."""
+exact diagonals (ties between axes).  Four formulations: explicit catch-up (mode 0), the unified step
+(mode 1), the unified step with the forward-box rule, which is what the kernels use (mode 2), and that rule at the bit
+level of the kernels' round-2 step body - Morton walk word, mirrored walk, axis carried as its lowest field bit, forward-box
+table with the cell's one-hot mask, brick key in mirrored coordinates (mode 3: uw_step / walk_step under VP_STEP_V2)."""
 import ctypes as C
 import os
 import subprocess
@@ -54,12 +56,19 @@ def _ray_sets(n, count, rng):
 
 
 @pytest.mark.parametrize("name", ["room", "monu2", "player"])
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_brick_walk_equals_cell_walk(model, name, mode):
     grid, n, _ = scenes.load_grid(name)
     grid = np.ascontiguousarray(grid.reshape(-1))
-    fine = np.zeros((n // 4) ** 3, np.uint64)
-    model.bw_build_fine(grid.ctypes.data_as(C.c_void_p), n, fine.ctypes.data_as(C.c_void_p))
+    if mode == 3:
+        jr = 0
+        while (16 << jr) < n:
+            jr += 1
+        fine = np.zeros(64 << (3 * jr), np.uint64)
+        model.bw_build_fine_morton(grid.ctypes.data_as(C.c_void_p), n, jr, fine.ctypes.data_as(C.c_void_p))
+    else:
+        fine = np.zeros((n // 4) ** 3, np.uint64)
+        model.bw_build_fine(grid.ctypes.data_as(C.c_void_p), n, fine.ctypes.data_as(C.c_void_p))
     rng = np.random.default_rng(5 + mode)
     for what, O, D, tl in _ray_sets(n, 60000, rng):
         O, D, tl = (np.ascontiguousarray(a, np.float32) for a in (O, D, tl))
@@ -71,3 +80,28 @@ def test_brick_walk_equals_cell_walk(model, name, mode):
         assert st.rays > 0 and st.ref_steps >= st.rays
         if name == "room" and what == "inside":
             assert st.brick_steps > 0 and st.brick_steps + st.cell_steps < st.ref_steps  # the walk really skips cells
+
+
+@pytest.mark.parametrize("n", [20, 37, 44, 100])
+def test_bit_level_step_on_padded_grids(model, n):
+    """Grid sizes that are not a power of two (and not a multiple of the brick size): the kernels walk the empty padding
+    of the (16 << jr)^3 lattice until the masked add carries out; hits, cells and t must still equal the cell walk."""
+    rng = np.random.default_rng(100 + n)
+    grid = np.full((n, n, n), 255, np.uint8)
+    solid = rng.uniform(size=grid.shape) < 0.02
+    solid[:, :, : max(1, n // 10)] = True   # a floor, so that long walks end in hits as well
+    grid[solid] = 1
+    grid = np.ascontiguousarray(grid.transpose(2, 1, 0).reshape(-1))  # x fastest
+    jr = 0
+    while (16 << jr) < n:
+        jr += 1
+    fine = np.zeros(64 << (3 * jr), np.uint64)
+    model.bw_build_fine_morton(grid.ctypes.data_as(C.c_void_p), n, jr, fine.ctypes.data_as(C.c_void_p))
+    for what, O, D, tl in _ray_sets(n, 40000, rng):
+        O, D, tl = (np.ascontiguousarray(a, np.float32) for a in (O, D, tl))
+        st, first = Stats(), C.c_int64()
+        bad = model.bw_compare(grid.ctypes.data_as(C.c_void_p), fine.ctypes.data_as(C.c_void_p), n, O.ctypes.data_as(C.c_void_p),
+                               D.ctypes.data_as(C.c_void_p), tl.ctypes.data_as(C.c_void_p), C.c_int64(len(O)), 3, C.byref(st),
+                               C.byref(first), None)
+        assert bad == 0, f"n={n} / {what}: {bad} rays differ, first {first.value}"
+        assert st.rays > 0

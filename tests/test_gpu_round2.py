@@ -412,3 +412,49 @@ def test_single_volume_switches(product, monkeypatch, env):
     assert np.count_nonzero(bits(res[0][0]) != bits(res[1][0])) == 0, env
     assert np.array_equal(res[0][1], res[1][1])
     assert res[0][2].rays == res[1][2].rays and res[0][2].shadow_rays == res[1][2].shadow_rays
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [44, 100, 128])
+def test_axis_parallel_rays_on_cell_boundaries(product, oracle, n):
+    """Rays with exactly zero direction components that start exactly on cell boundaries: tmax of such an axis is
+    (plane - origin) * (1 / 0) - NaN when the difference is 0 (the walk then never enters brick mode), +inf, or -inf when
+    the plane's product with the cell size rounds below the origin, which needs a grid size that is not a power of two.
+    The reference then takes that axis' step first, at t = -inf.  Batched nearest / any-hit queries through the brick walk
+    against the oracle, bit for bit (a -inf tmax used to equal the brick walk's initial 'last brick step' key: found by
+    tests/test_brickwalk_model.py on a 100^3 grid, fixed with kTcFirst)."""
+    from _util import host
+    rng = np.random.default_rng(1000 + n)
+    g = np.full((n, n, n), 255, np.uint8)  # [z, y, x]
+    g[:, : max(1, n // 10), :] = 3
+    fill = rng.uniform(size=(n, n, n)) < 0.02
+    g[fill] = rng.integers(0, 8, int(fill.sum())).astype(np.uint8)
+    M, iM, a, b = host.make_transform((0.0, 0.0, 0.0))
+    sc = vp.SceneDesc(volumes=[vp.Volume(np.ascontiguousarray(g.reshape(-1)), n, a, b, M, iM)], materials=host.default_materials(),
+                      point_lights=[((0.5, 2.5, -0.5), (6, 6, 6))])
+    count = 30000
+    lo, hi = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    o = rng.uniform(0.02, 0.9, (count, 3)).astype(np.float32)
+    o = (np.round(o * n) / n).astype(np.float32) * (hi - lo) + lo  # exactly on cell boundaries of the volume's cube
+    d = rng.normal(size=(count, 3)).astype(np.float32)
+    d[rng.uniform(size=(count, 3)) < 0.3] = 0.0
+    d[np.all(d == 0, axis=1)] = (1, 0, 0)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[count // 2:][d[count // 2:] == 0] = -0.0
+    t = np.where(rng.uniform(size=count) < 0.5, 1e34, rng.uniform(0, 1.0, count)).astype(np.float32)
+    rays = vp.make_rays(o, d.astype(np.float32), t=t)
+    res = []
+    for lib in (oracle, product):
+        with vp.Session(lib) as s:
+            s.set_scene(sc)
+            res.append((s.find_nearest(rays), s.is_occluded(rays)))
+    want, got = res[0][0], res[1][0]
+    for k in ("volume", "cell", "material", "face", "inside"):
+        assert np.array_equal(want[k], got[k]), f"n={n} nearest: {k}"
+    assert np.array_equal(bits(want["t"]), bits(got["t"])), f"n={n} nearest: t"
+    # a hit at t = -inf (see above) has a NaN normal: -inf * 0 in Ray::GetNormalVoxel.  x86 and the GPU give an invalid
+    # operation's NaN different payloads, so normals are compared as values, NaN where NaN
+    wn, gn = want["normal"], got["normal"]
+    assert np.array_equal(np.isnan(wn), np.isnan(gn)) and np.array_equal(bits(np.nan_to_num(wn)), bits(np.nan_to_num(gn))), f"n={n} nearest: normal"
+    assert np.array_equal(res[0][1], res[1][1])
+    assert np.count_nonzero(want["volume"] >= 0) > count // 10
