@@ -123,3 +123,45 @@ def test_gameplay_side_channels(ref, oracle):
     # the side channel differs from the ordinary nearest hit (player volume skipped, smoke transparent) and the chunk rule bites
     assert np.count_nonzero(a["player0"]["volume"] != a["nearest"]["volume"]) > 0
     assert np.count_nonzero(a["player0"]["volume"] != a["player2"]["volume"]) > 0
+
+
+@pytest.mark.parametrize("n", [44, 100, 128])
+def test_axis_parallel_rays_on_cell_boundaries(ref, oracle, n):
+    """The reference's own walk on rays with exactly zero direction components that start exactly on cell boundaries
+    (tmax of such an axis is NaN, +inf or - on grids whose size is not a power of two - -inf): the plain-C restatement
+    must reproduce whatever the reference does there, bit for bit (NaN normals compared as NaN).  The GPU twin of this
+    test is tests/test_gpu_round2.py::test_axis_parallel_rays_on_cell_boundaries."""
+    from _util import host
+    rng = np.random.default_rng(1000 + n)
+    g = np.full((n, n, n), 255, np.uint8)  # [z, y, x]
+    g[:, : max(1, n // 10), :] = 3
+    fill = rng.uniform(size=(n, n, n)) < 0.02
+    g[fill] = rng.integers(0, 8, int(fill.sum())).astype(np.uint8)
+    M, iM, a, b = host.make_transform((0.0, 0.0, 0.0))
+    sc = vp.SceneDesc(volumes=[vp.Volume(np.ascontiguousarray(g.reshape(-1)), n, a, b, M, iM)], materials=host.default_materials(),
+                      point_lights=[((0.5, 2.5, -0.5), (6, 6, 6))])
+    count = 30000
+    lo, hi = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    o = rng.uniform(0.02, 0.9, (count, 3)).astype(np.float32)
+    o = (np.round(o * n) / n).astype(np.float32) * (hi - lo) + lo
+    d = rng.normal(size=(count, 3)).astype(np.float32)
+    d[rng.uniform(size=(count, 3)) < 0.3] = 0.0
+    d[np.all(d == 0, axis=1)] = (1, 0, 0)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[count // 2:][d[count // 2:] == 0] = -0.0
+    t = np.where(rng.uniform(size=count) < 0.5, 1e34, rng.uniform(0, 1.0, count)).astype(np.float32)
+    rays = vp.make_rays(o, d.astype(np.float32), t=t)
+    res = []
+    for lib in (ref, oracle):
+        with vp.Session(lib) as s:
+            s.set_scene(sc)
+            res.append((s.find_nearest(rays), s.is_occluded(rays)))
+    want, got = res[0][0], res[1][0]
+    for k in ("volume", "cell", "material", "face", "inside"):
+        assert np.array_equal(want[k], got[k]), f"n={n} nearest: {k}"
+    assert np.array_equal(bits(want["t"]), bits(got["t"])), f"n={n} nearest: t"
+    wn, gn = want["normal"], got["normal"]
+    assert np.array_equal(np.isnan(wn), np.isnan(gn)) and np.array_equal(bits(np.nan_to_num(wn)), bits(np.nan_to_num(gn)))
+    assert np.array_equal(res[0][1], res[1][1])
+    if n == 100:
+        assert np.count_nonzero(np.isneginf(want["t"])) > 0  # the case this test exists for does occur
