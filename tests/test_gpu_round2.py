@@ -458,3 +458,43 @@ def test_axis_parallel_rays_on_cell_boundaries(product, oracle, n):
     assert np.array_equal(np.isnan(wn), np.isnan(gn)) and np.array_equal(bits(np.nan_to_num(wn)), bits(np.nan_to_num(gn))), f"n={n} nearest: normal"
     assert np.array_equal(res[0][1], res[1][1])
     assert np.count_nonzero(want["volume"] >= 0) > count // 10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [256, 512])
+def test_largest_grids(product, oracle, n):
+    """The largest grids the walk word holds (10 bits per axis: 512^3 = 128 MiB of material bytes, 27 bits of Morton
+    coordinate, 32 768 region masks - more than fit into shared memory, so the traversal stages read them from global
+    memory - and 256^3, whose 4 096 region masks are staged): batched nearest / any-hit queries, primary hits and a small
+    accumulated frame against the oracle, bit for bit."""
+    from _util import host, assert_hits_equal
+    rng = np.random.default_rng(n)
+    g = np.full((n, n, n), 255, np.uint8)  # [z, y, x]
+    g[:, : n // 16, :] = 3                 # a floor
+    g[n // 2 - 2 : n // 2 + 2, :, :] = 5   # a mirror wall
+    k = 40 * n * n // 64
+    zi, yi, xi = (rng.integers(0, n, k) for _ in range(3))
+    g[zi, yi, xi] = rng.integers(0, 8, k).astype(np.uint8)
+    M, iM, a, b = host.make_transform((0.0, 0.0, 0.0))
+    sc = vp.SceneDesc(volumes=[vp.Volume(np.ascontiguousarray(g.reshape(-1)), n, a, b, M, iM)], materials=host.default_materials(),
+                      point_lights=[((0.5, 0.9, 0.2), (6, 6, 6)), ((0.2, 0.5, 0.8), (3, 3, 4))])
+    cam = host.look_at((0.15, 0.8, 0.1), (0.7, 0.2, 0.45), 64, 36)
+    fp = vp.frame_params(64, 36, max_bounces=4, spp=2)
+    count = 20000
+    o = rng.uniform(0.02, 0.98, (count, 3)).astype(np.float32)
+    o[::3] = (np.round(o[::3] * n) / n).astype(np.float32)
+    d = rng.normal(size=(count, 3)).astype(np.float32)
+    d[::5, 1] = 0.0
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = vp.make_rays(o, d.astype(np.float32))
+    res = []
+    for lib in (oracle, product):
+        with vp.Session(lib) as s:
+            s.set_scene(sc)
+            res.append((s.trace_primary(cam, fp), s.render(cam, fp), s.find_nearest(rays), s.is_occluded(rays)))
+    assert_hits_equal(res[0][0], res[1][0], f"n={n} primary")
+    assert np.count_nonzero(bits(res[0][1][0]) != bits(res[1][1][0])) == 0
+    assert res[0][1][2].rays == res[1][1][2].rays
+    assert_hits_equal(res[0][2], res[1][2], f"n={n} nearest")
+    assert np.array_equal(res[0][3], res[1][3])
+    assert np.count_nonzero(res[1][0]["volume"] >= 0) > 1000 and np.count_nonzero(res[0][2]["volume"] >= 0) > count // 2
