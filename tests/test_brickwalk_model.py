@@ -53,6 +53,13 @@ def _ray_sets(n, count, rng):
     D5[rng.uniform(size=(count, 3)) < 0.2] *= 0.5
     D5 /= np.linalg.norm(D5, axis=1, keepdims=True)
     yield "diagonal ties", O3, D5.astype(np.float32), far
+    # direction components so small that tdelta is huge, overflows to inf (1 / denormal) or tmax * 0 games start
+    D6 = D.copy()
+    tiny = np.array([1e-30, -1e-30, 1e-38, -1e-38, 1e-39, -1e-39, 1e-44, -1e-44], np.float32)
+    sel = rng.uniform(size=(count, 3)) < 0.3
+    D6[sel] = rng.choice(tiny, int(sel.sum()))
+    yield "tiny components", O, D6.astype(np.float32), far
+    yield "tiny components, grid-aligned", O3, D6.astype(np.float32), far
 
 
 @pytest.mark.parametrize("name", ["room", "monu2", "player"])
@@ -82,7 +89,7 @@ def test_brick_walk_equals_cell_walk(model, name, mode):
             assert st.brick_steps > 0 and st.brick_steps + st.cell_steps < st.ref_steps  # the walk really skips cells
 
 
-@pytest.mark.parametrize("n", [20, 37, 44, 100])
+@pytest.mark.parametrize("n", [20, 37, 44, 100, 256])
 def test_bit_level_step_on_padded_grids(model, n):
     """Grid sizes that are not a power of two (and not a multiple of the brick size): the kernels walk the empty padding
     of the (16 << jr)^3 lattice until the masked add carries out; hits, cells and t must still equal the cell walk."""

@@ -149,6 +149,10 @@ def test_axis_parallel_rays_on_cell_boundaries(ref, oracle, n):
     d[np.all(d == 0, axis=1)] = (1, 0, 0)
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     d[count // 2:][d[count // 2:] == 0] = -0.0
+    # ... and components so small that tdelta is huge or overflows to inf (1 / denormal)
+    tiny = np.array([1e-30, -1e-30, 1e-38, -1e-38, 1e-39, -1e-39, 1e-44, -1e-44], np.float32)
+    sel = rng.uniform(size=(count // 4, 3)) < 0.3
+    d[: count // 4][sel] = rng.choice(tiny, int(sel.sum()))
     t = np.where(rng.uniform(size=count) < 0.5, 1e34, rng.uniform(0, 1.0, count)).astype(np.float32)
     rays = vp.make_rays(o, d.astype(np.float32), t=t)
     res = []
