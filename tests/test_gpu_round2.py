@@ -498,3 +498,44 @@ def test_largest_grids(product, oracle, n):
     assert_hits_equal(res[0][2], res[1][2], f"n={n} nearest")
     assert np.array_equal(res[0][3], res[1][3])
     assert np.count_nonzero(res[1][0]["volume"] >= 0) > 1000 and np.count_nonzero(res[0][2]["volume"] >= 0) > count // 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nvol", [23, 24, 32, 33, 61])
+def test_volume_count_thresholds(product, oracle, nvol):
+    """Scenes on both sides of the volume counts at which the traversal stages change their bookkeeping: 23 (the last count
+    whose bounding-sphere candidates travel in the prepared record), 24 and 32 (candidate masks of the shadow stage only),
+    33 (no masks: the pre-test runs inside the stages), 61 (no prepare stage).  16^3 volumes on a rotated lattice, a light
+    among them; primary hits, an accumulated frame of pipelined passes and batched queries against the oracle."""
+    from _util import host, assert_hits_equal
+    rng = np.random.default_rng(nvol)
+    vols = []
+    for i in range(nvol):
+        g = np.full((16, 16, 16), 255, np.uint8)
+        g[:, :2, :] = 3
+        fill = rng.uniform(size=g.shape) < 0.08
+        g[fill] = rng.integers(0, 8, int(fill.sum())).astype(np.uint8)
+        pos = (0.9 * (i % 8) - 3.0, 0.35 * ((i // 8) % 2), 0.9 * (i // 8) + 0.3 * (i % 3))
+        M, iM, a, b = host.make_transform(pos, (0.0, 0.2 * (i % 5), 0.0), (0.7, 0.7 + 0.1 * (i % 3), 0.7))
+        vols.append(vp.Volume(np.ascontiguousarray(g.reshape(-1)), 16, a, b, M, iM))
+    sc = vp.SceneDesc(volumes=vols, materials=host.default_materials(),
+                      point_lights=[((0.0, 2.5, 2.0), (8, 8, 8)), ((-2.0, 1.0, 5.0), (4, 4, 5))])
+    cam = host.look_at((0.3, 2.2, -3.5), (0.2, 0.2, 3.0), 96, 54)
+    fp = vp.frame_params(96, 54, max_bounces=5, spp=3)
+    count = 6000
+    o = rng.uniform((-4, 0, -1), (4, 2, 8), (count, 3)).astype(np.float32)
+    d = rng.normal(size=(count, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = vp.make_rays(o, d)
+    res = []
+    for lib in (oracle, product):
+        with vp.Session(lib) as s:
+            s.set_scene(sc)
+            res.append((s.trace_primary(cam, fp), s.render(cam, fp), s.find_nearest(rays), s.is_occluded(rays)))
+    assert_hits_equal(res[0][0], res[1][0], f"{nvol} volumes primary")
+    assert np.count_nonzero(bits(res[0][1][0]) != bits(res[1][1][0])) == 0
+    assert np.count_nonzero(res[0][1][1] != res[1][1][1]) == 0
+    assert res[0][1][2].rays == res[1][1][2].rays and res[0][1][2].shadow_rays == res[1][1][2].shadow_rays
+    assert_hits_equal(res[0][2], res[1][2], f"{nvol} volumes nearest")
+    assert np.array_equal(res[0][3], res[1][3])
+    assert np.count_nonzero(res[0][0]["volume"] >= 0) > 800 and len(np.unique(res[0][0]["volume"])) > min(nvol, 12) // 2
